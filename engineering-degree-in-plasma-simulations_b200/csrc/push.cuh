@@ -1,0 +1,41 @@
+// Device pieces shared by the push kernels (push.cu, push_deposit.cu, heavy.cu).
+#pragma once
+#include "common.cuh"
+
+struct PushArrays { double *x, *y, *z, *u, *v, *w; };
+
+namespace picg {
+int compact_dead(picg_species_s* s, size_t cap);
+size_t compact_scratch_bytes(size_t cap);
+int push_grid(size_t n_upper);
+}
+
+#ifdef __CUDACC__
+// Species::advanceElectronsSerial body (Species.cpp:368-373):
+//   lc = XtoL(pos); E = ef.gather(lc); vel += E*(dt*charge/mass); pos += vel*dt
+// qm_dt is the scalar dt*charge/mass formed on the host exactly as the reference forms it.
+__device__ __forceinline__ void push_kick_drift(const Grid& g, const double* __restrict__ ef, double qm_dt, double dt,
+                                                double& x, double& y, double& z, double& u, double& v, double& w) {
+    double ex, ey, ez;
+    gather_ef(g, ef, x_to_l(x, g.x0[0], g.inv_dx[0]), x_to_l(y, g.x0[1], g.inv_dx[1]), x_to_l(z, g.x0[2], g.inv_dx[2]), ex, ey, ez);
+    u = __dadd_rn(u, __dmul_rn(ex, qm_dt));
+    v = __dadd_rn(v, __dmul_rn(ey, qm_dt));
+    w = __dadd_rn(w, __dmul_rn(ez, qm_dt));
+    x = __dadd_rn(x, __dmul_rn(u, dt));
+    y = __dadd_rn(y, __dmul_rn(v, dt));
+    z = __dadd_rn(z, __dmul_rn(w, dt));
+}
+
+// Warp-aggregated append of dead particle indices to the dead list (one atomic per warp).
+// Must be called by all 32 lanes.
+__device__ __forceinline__ void record_dead(bool dead, int lane, u64 p, SpeciesCounters* ctr, unsigned* __restrict__ dead_list) {
+    unsigned mask = __ballot_sync(0xffffffffu, dead);
+    if (mask) {
+        int leader = __ffs(mask) - 1;
+        u64 base = 0;
+        if (lane == leader) base = atomicAdd(&ctr->n_dead, (u64)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (dead) dead_list[base + __popc(mask & ((1u << lane) - 1))] = (unsigned)p;
+    }
+}
+#endif

@@ -1,0 +1,192 @@
+// Cell sort of the SoA particle store: stable LSD radix sort (8-bit digits) on 32-bit cell keys.
+// Replaces Species::sortIndexes (ch4/v3/src/Species.cpp:905-929): instead of per-cell index vectors
+// the particles themselves are permuted into cell order and cell_start[] (nc+1 offsets) is produced.
+//
+// Pass structure (classic three-kernel radix pass with a fixed number of blocks):
+//   k_sort_upsweep   : per-block digit histogram over the block's contiguous key range
+//   k_sort_scan      : exclusive scan of the [256][blocks] count table (digit-major)
+//   k_sort_downsweep : each block walks its range tile by tile, ranks keys stably (warp match-any
+//                      multisplit + per-warp counters) and scatters (key, index) pairs
+// followed by k_sort_permute (gather each particle array through the final index list) and
+// k_cell_start.  ceil(log2(num_cells)/8) passes: 3 for the 256^3 mesh.
+#include "common.cuh"
+#include <algorithm>
+
+using namespace picg;
+
+#define SORT_THREADS 256
+#define SORT_WARPS (SORT_THREADS / 32)
+#define SORT_ITEMS 8                               // keys per thread per tile
+#define SORT_TILE (SORT_THREADS * SORT_ITEMS)      // 2048 keys per tile
+
+__global__ void __launch_bounds__(256) k_sort_keys(Grid g, const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pz,
+                                                   const SpeciesCounters* ctr, unsigned* __restrict__ keys, unsigned* __restrict__ idx) {
+    const u64 n = ctr->n;
+    for (u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x; p < n; p += (u64)gridDim.x * blockDim.x) {
+        int i = min(max((int)x_to_l(px[p], g.x0[0], g.inv_dx[0]), 0), g.ci - 1);
+        int j = min(max((int)x_to_l(py[p], g.x0[1], g.inv_dx[1]), 0), g.cj - 1);
+        int k = min(max((int)x_to_l(pz[p], g.x0[2], g.inv_dx[2]), 0), g.ck - 1);
+        keys[p] = (unsigned)cell_of(g, i, j, k);
+        idx[p] = (unsigned)p;
+    }
+}
+
+// block b owns tiles [b*tiles_per_block, (b+1)*tiles_per_block)
+__device__ __forceinline__ void block_range(u64 n, int nblocks, u64& begin, u64& end) {
+    u64 tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    u64 per = (tiles + nblocks - 1) / nblocks;
+    begin = min(n, (u64)blockIdx.x * per * SORT_TILE);
+    end = min(n, begin + per * SORT_TILE);
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_upsweep(const SpeciesCounters* ctr, const unsigned* __restrict__ keys, int shift,
+                                                               unsigned* __restrict__ counts /*[256][gridDim.x]*/) {
+    __shared__ unsigned hist[SORT_WARPS][256];
+    for (int t = threadIdx.x; t < SORT_WARPS * 256; t += SORT_THREADS) (&hist[0][0])[t] = 0;
+    __syncthreads();
+    u64 begin, end; block_range(ctr->n, gridDim.x, begin, end);
+    const int warp = threadIdx.x >> 5;
+    for (u64 p = begin + threadIdx.x; p < end; p += SORT_THREADS) atomicAdd(&hist[warp][(keys[p] >> shift) & 255u], 1u);
+    __syncthreads();
+    for (int d = threadIdx.x; d < 256; d += SORT_THREADS) {
+        unsigned s = 0;
+        for (int w = 0; w < SORT_WARPS; w++) s += hist[w][d];
+        counts[(size_t)d * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// single-block exclusive scan over m = 256*blocks entries
+__global__ void __launch_bounds__(1024) k_sort_scan(unsigned* __restrict__ counts, int m) {
+    __shared__ unsigned warp_tot[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < m; base += 1024) {
+        int t = base + threadIdx.x;
+        unsigned v = t < m ? counts[t] : 0, x = v;
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned wv = warp_tot[lane], wx = wv;
+            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, wx, o); if (lane >= o) wx += y; }
+            warp_tot[lane] = wx - wv;
+        }
+        __syncthreads();
+        unsigned excl = carry + warp_tot[warp] + x - v;
+        if (t < m) counts[t] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_downsweep(const SpeciesCounters* ctr, const unsigned* __restrict__ keys_in,
+                                                                 const unsigned* __restrict__ idx_in, unsigned* __restrict__ keys_out,
+                                                                 unsigned* __restrict__ idx_out, int shift, const unsigned* __restrict__ counts) {
+    __shared__ unsigned wcount[SORT_WARPS][256];     // per-warp digit counts of the current tile, then exclusive warp offsets
+    __shared__ unsigned running[256];                // block's running global offset per digit
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int d = threadIdx.x; d < 256; d += SORT_THREADS) running[d] = counts[(size_t)d * gridDim.x + blockIdx.x];
+    u64 begin, end; block_range(ctr->n, gridDim.x, begin, end);
+    for (u64 tile = begin; tile < end; tile += SORT_TILE) {
+        for (int t = threadIdx.x; t < SORT_WARPS * 256; t += SORT_THREADS) (&wcount[0][0])[t] = 0;
+        __syncthreads();
+        // warp w owns the contiguous segment [tile + w*32*ITEMS, +32*ITEMS); rounds are visited in order => stable
+        unsigned key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
+        u64 seg = tile + (u64)warp * 32 * SORT_ITEMS;
+#pragma unroll
+        for (int r = 0; r < SORT_ITEMS; r++) {
+            u64 p = seg + r * 32 + lane;
+            bool ok = p < end;
+            key[r] = ok ? keys_in[p] : 0xffffffffu; val[r] = ok ? idx_in[p] : 0;
+            unsigned d = ok ? ((key[r] >> shift) & 255u) : 256u;          // 256 = inactive lanes group together
+            unsigned peers = __match_any_sync(0xffffffffu, d);
+            unsigned before = 0;
+            if (ok) before = wcount[warp][d];
+            __syncwarp();
+            if (ok && lane == __ffs(peers) - 1) wcount[warp][d] = before + __popc(peers);
+            __syncwarp();
+            rank[r] = before + __popc(peers & ((1u << lane) - 1));
+        }
+        __syncthreads();
+        // exclusive scan over warps for every digit; add the tile totals to the running offsets afterwards
+        for (int d = threadIdx.x; d < 256; d += SORT_THREADS) {
+            unsigned s = 0;
+            for (int w = 0; w < SORT_WARPS; w++) { unsigned c = wcount[w][d]; wcount[w][d] = s; s += c; }
+            unsigned base = running[d];
+            for (int w = 0; w < SORT_WARPS; w++) wcount[w][d] += base;
+            running[d] = base + s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < SORT_ITEMS; r++) {
+            u64 p = seg + r * 32 + lane;
+            if (p < end) {
+                unsigned d = (key[r] >> shift) & 255u;
+                unsigned dst = wcount[warp][d] + rank[r];
+                keys_out[dst] = key[r]; idx_out[dst] = val[r];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sort_permute(const SpeciesCounters* ctr, const unsigned* __restrict__ idx, const double* __restrict__ in,
+                                                      double* __restrict__ out) {
+    const u64 n = ctr->n;
+    for (u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x; p < n; p += (u64)gridDim.x * blockDim.x) out[p] = in[idx[p]];
+}
+
+// cell_start[c] = first sorted position whose key >= c ; cell_start[nc] = n
+__global__ void __launch_bounds__(256) k_cell_start(const SpeciesCounters* ctr, const unsigned* __restrict__ keys, int nc, unsigned* __restrict__ cell_start) {
+    const u64 n = ctr->n;
+    for (u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x; p <= n; p += (u64)gridDim.x * blockDim.x) {
+        int lo = (p == 0) ? 0 : (int)keys[p - 1] + 1;
+        int hi = (p == n) ? nc : (int)keys[p];
+        for (int c = lo; c <= hi; c++) cell_start[c] = (unsigned)p;
+    }
+}
+
+namespace picg {
+// Sorts species s by cell.  Scratch: keysA | keysB | idxA | idxB | counts.
+int sort_species(picg_species_s* s) {
+    const Grid& g = s->w->g;
+    size_t cap = std::max<size_t>(s->n_upper, 1);
+    if (cap >= 0xffffffffull) return set_error(PICG_ERR_ARG, "picg_species_sort: more than 2^32-1 particles per GPU are not supported");
+    int nblocks = std::max(1, std::min(div_up(cap, SORT_TILE), g_sm_count * 4));
+    size_t capa = (cap + 63) & ~(size_t)63;
+    size_t bytes = capa * 16 + (size_t)256 * nblocks * 4 + 256;
+    int rc = ensure_scratch(s->w, bytes); if (rc) return rc;
+    unsigned* keysA = (unsigned*)s->w->scratch; unsigned* keysB = keysA + capa;
+    unsigned* idxA = keysB + capa; unsigned* idxB = idxA + capa;
+    unsigned* counts = idxB + capa;
+    int pgrid = std::max(1, std::min(div_up(cap, 256), g_sm_count * 8));
+    LAUNCH(K_SORT_KEYS, k_sort_keys, pgrid, 256, 0, g, s->a[0], s->a[1], s->a[2], s->ctr, keysA, idxA); CHECK_LAUNCH();
+    int bits = 1; while ((1ull << bits) < (u64)g.nc) bits++;
+    int passes = (bits + 7) / 8;
+    for (int pass = 0; pass < passes; pass++) {
+        int shift = pass * 8;
+        LAUNCH(K_SORT_HIST, k_sort_upsweep, nblocks, SORT_THREADS, 0, s->ctr, keysA, shift, counts); CHECK_LAUNCH();
+        LAUNCH(K_SORT_SCAN, k_sort_scan, 1, 1024, 0, counts, 256 * nblocks); CHECK_LAUNCH();
+        LAUNCH(K_SORT_SCATTER, k_sort_downsweep, nblocks, SORT_THREADS, 0, s->ctr, keysA, idxA, keysB, idxB, shift, counts); CHECK_LAUNCH();
+        std::swap(keysA, keysB); std::swap(idxA, idxB);
+    }
+    // gather every particle array through the index list into the spare array, then rotate pointers
+    for (int c = 0; c < 7; c++) {
+        LAUNCH(K_SORT_PERMUTE, k_sort_permute, pgrid, 256, 0, s->ctr, idxA, s->a[c], s->spare); CHECK_LAUNCH();
+        std::swap(s->a[c], s->spare);
+    }
+    LAUNCH(K_CELL_START, k_cell_start, pgrid, 256, 0, s->ctr, keysA, g.nc, s->cell_start); CHECK_LAUNCH();
+    s->sorted_valid = true;
+    return PICG_OK;
+}
+}  // namespace picg
+
+extern "C" {
+int picg_species_sort(picg_species_t s) {
+    REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_species_sort: null species");
+    return sort_species(s);
+}
+}

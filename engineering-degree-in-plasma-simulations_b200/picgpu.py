@@ -1,0 +1,411 @@
+"""ctypes binding of libpicgpu.so (include/picgpu.h) with the reference's class names.
+
+The classes mirror the public surface of the reference's ch4/v3 classes that the main loop
+uses (ch4/v3/src/main.cpp:177-288): World, Species, PotentialSolver, MC_MEX_Ionization,
+ColdBeamSource / WarmBeamSource.  Everything forwards to the C ABI; nothing is computed in
+Python and there is no CPU fallback: without the CUDA library or a GPU, calls raise.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpicgpu.so")
+
+
+class PicgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"picgpu error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Loads libpicgpu.so (fails loudly if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback for the particle loop)")
+        l = C.CDLL(LIB_PATH)
+        l.picg_last_error.restype = C.c_char_p
+        l.picg_version.restype = C.c_char_p
+        l.picg_timer_name.restype = C.c_char_p
+        l.picg_stream.restype = C.c_void_p
+        l.picg_launch_count.restype = C.c_uint64
+        l.picg_launch_count_reset.restype = None
+        _lib = l
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise PicgError(rc, lib().picg_last_error().decode())
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _d3(v):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+def init(device=0):
+    _chk(lib().picg_init(int(device)))
+
+
+def device_count():
+    n = C.c_int(0)
+    lib().picg_device_count(C.byref(n))
+    return n.value
+
+
+def seed(s):
+    _chk(lib().picg_seed(C.c_uint64(int(s))))
+
+
+def set_rank(rank, world_size):
+    _chk(lib().picg_set_rank(int(rank), int(world_size)))
+
+
+def synchronize():
+    _chk(lib().picg_synchronize())
+
+
+def stream_ptr():
+    return lib().picg_stream()
+
+
+def launch_count():
+    return int(lib().picg_launch_count())
+
+
+def launch_count_reset():
+    lib().picg_launch_count_reset()
+
+
+def timers_enable(on=True):
+    _chk(lib().picg_timers_enable(int(bool(on))))
+
+
+def timers_reset():
+    _chk(lib().picg_timers_reset())
+
+
+def timers_read():
+    """{kernel name: (total ms, launches)} for kernels launched since the last reset."""
+    out = {}
+    i = 0
+    while True:
+        name = lib().picg_timer_name(i)
+        if name is None:
+            break
+        ms = C.c_double(0)
+        n = C.c_uint64(0)
+        _chk(lib().picg_timer_read(i, C.byref(ms), C.byref(n)))
+        if n.value:
+            out[name.decode()] = (ms.value, n.value)
+        i += 1
+    return out
+
+
+# field ids (include/picgpu.h)
+F_PHI, F_RHO, F_NODE_VOL, F_EF, F_OBJECT_ID, F_NODE_TYPE = range(6)
+(SF_DEN, SF_DEN_AVG, SF_T, SF_VEL, SF_MACRO_COUNT, SF_N_SUM, SF_NV_SUM, SF_NUU_SUM, SF_NVV_SUM, SF_NWW_SUM,
+ SF_DEN_FIXED) = range(11)
+
+
+class World:
+    """World (ch4/v3/src/World.h:14-116)."""
+
+    def __init__(self, ni, nj, nk, x0, xm):
+        self.ni, self.nj, self.nk = int(ni), int(nj), int(nk)
+        self.nv = self.ni * self.nj * self.nk
+        self.num_cells = (self.ni - 1) * (self.nj - 1) * (self.nk - 1)
+        self.x0 = np.asarray(x0, dtype=np.float64)
+        self.xm = np.asarray(xm, dtype=np.float64)
+        self.dx = (self.xm - self.x0) / (np.array([ni, nj, nk]) - 1)
+        self.h = C.c_void_p()
+        _chk(lib().picg_world_create(self.ni, self.nj, self.nk, _d3(x0), _d3(xm), C.byref(self.h)))
+        self.dt = 1e-4
+
+    def close(self):
+        if self.h:
+            lib().picg_world_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def setTime(self, dt, num_ts):
+        self.dt = float(dt)
+        _chk(lib().picg_world_set_time(self.h, C.c_double(dt), int(num_ts)))
+
+    def addRectangle(self, centre, phi, sides):
+        _chk(lib().picg_world_add_rectangle(self.h, _d3(centre), C.c_double(phi), _d3(sides)))
+
+    def addSphere(self, centre, phi, radius):
+        _chk(lib().picg_world_add_sphere(self.h, _d3(centre), C.c_double(phi), C.c_double(radius)))
+
+    def computeObjectID(self):
+        _chk(lib().picg_world_compute_object_id(self.h))
+
+    def _shape(self, field):
+        return (self.ni, self.nj, self.nk, 3) if field == F_EF else (self.ni, self.nj, self.nk)
+
+    def download(self, field):
+        out = np.empty(self._shape(field), dtype=np.float64)
+        _chk(lib().picg_world_download(self.h, int(field), _dp(out)))
+        return out
+
+    def upload(self, field, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        assert a.size == int(np.prod(self._shape(field)))
+        _chk(lib().picg_world_upload(self.h, int(field), _dp(a)))
+
+    phi = property(lambda self: self.download(F_PHI))
+    rho = property(lambda self: self.download(F_RHO))
+    ef = property(lambda self: self.download(F_EF))
+    node_vol = property(lambda self: self.download(F_NODE_VOL))
+    object_id = property(lambda self: self.download(F_OBJECT_ID))
+
+    def computeChargeDensity(self, species):
+        arr = (C.c_void_p * len(species))(*[s.h for s in species])
+        _chk(lib().picg_world_charge_density(self.h, arr, len(species)))
+
+    def getPE(self):
+        pe = C.c_double(0)
+        _chk(lib().picg_world_potential_energy(self.h, C.byref(pe)))
+        return pe.value
+
+    def device_ptr(self, field):
+        p = C.c_void_p()
+        n = C.c_size_t(0)
+        _chk(lib().picg_world_device_ptr(self.h, int(field), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+
+class Species:
+    """Species (ch4/v3/src/Species.h:31-131) on a device SoA store."""
+
+    def __init__(self, name, mass, charge, world, mpw0, E_ion=-666.0):
+        self.name, self.mass, self.charge, self.world, self.mpw0, self.E_ion = name, float(mass), float(charge), world, float(mpw0), float(E_ion)
+        self.h = C.c_void_p()
+        _chk(lib().picg_species_create(world.h, C.c_double(mass), C.c_double(charge), C.c_double(mpw0), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().picg_species_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def reserve(self, n):
+        _chk(lib().picg_species_reserve(self.h, C.c_size_t(int(n))))
+
+    def getNumParticles(self):
+        n = C.c_size_t(0)
+        _chk(lib().picg_species_count(self.h, C.byref(n)))
+        return n.value
+
+    def setParticles(self, aos7):
+        a = np.ascontiguousarray(aos7, dtype=np.float64).reshape(-1, 7)
+        _chk(lib().picg_species_upload(self.h, C.c_size_t(a.shape[0]), _dp(a)))
+
+    def getParticles(self):
+        n = self.getNumParticles()
+        out = np.empty((n, 7), dtype=np.float64)
+        m = C.c_size_t(0)
+        _chk(lib().picg_species_download(self.h, C.c_size_t(n), _dp(out), C.byref(m)))
+        return out[:m.value]
+
+    def addParticles(self, aos7):
+        a = np.ascontiguousarray(aos7, dtype=np.float64).reshape(-1, 7)
+        acc = C.c_size_t(0)
+        _chk(lib().picg_species_add_particles(self.h, C.c_size_t(a.shape[0]), _dp(a), C.byref(acc)))
+        return acc.value
+
+    def advanceElectrons(self, dt):
+        _chk(lib().picg_species_push_electrons(self.h, C.c_double(dt)))
+
+    def advanceNonElectron(self, neutrals, spherium, dt, sputtering=False):
+        _chk(lib().picg_species_push_heavy(self.h, neutrals.h, spherium.h, C.c_double(dt), int(sputtering)))
+
+    def advanceReflect(self, dt):
+        _chk(lib().picg_species_push_reflect(self.h, C.c_double(dt)))
+
+    def advanceElectronsDeposit(self, dt, count_cells=False):
+        _chk(lib().picg_species_push_electrons_deposit(self.h, C.c_double(dt), int(count_cells)))
+
+    def computeNumberDensity(self):
+        _chk(lib().picg_species_deposit_density(self.h))
+
+    def depositPartial(self):
+        _chk(lib().picg_species_deposit_density_partial(self.h))
+
+    def finalizeDensity(self):
+        _chk(lib().picg_species_finalize_density(self.h))
+
+    def densityScale(self):
+        s = C.c_int(0)
+        _chk(lib().picg_species_density_scale(self.h, C.byref(s)))
+        return s.value
+
+    def setDensityScale(self, S):
+        _chk(lib().picg_species_set_density_scale(self.h, int(S)))
+
+    def sampleMoments(self):
+        _chk(lib().picg_species_sample_moments(self.h))
+
+    def computeGasProperties(self):
+        _chk(lib().picg_species_compute_gas_properties(self.h))
+
+    def clearSamples(self):
+        _chk(lib().picg_species_clear_samples(self.h))
+
+    def updateAverages(self):
+        _chk(lib().picg_species_update_averages(self.h))
+
+    def computeMacroParticlesCount(self):
+        _chk(lib().picg_species_count_per_cell(self.h))
+
+    def sort(self):
+        _chk(lib().picg_species_sort(self.h))
+
+    def diagnostics(self):
+        mc = C.c_double(0)
+        ke = C.c_double(0)
+        mom = (C.c_double * 3)()
+        _chk(lib().picg_species_diagnostics(self.h, C.byref(mc), mom, C.byref(ke)))
+        return mc.value, np.array(list(mom)), ke.value
+
+    def download(self, field):
+        w = self.world
+        if field in (SF_VEL, SF_NV_SUM):
+            out = np.empty((w.ni, w.nj, w.nk, 3), dtype=np.float64)
+        elif field == SF_MACRO_COUNT:
+            out = np.empty((w.ni - 1, w.nj - 1, w.nk - 1), dtype=np.float64)
+        elif field == SF_DEN_FIXED:
+            out = np.empty((w.ni, w.nj, w.nk), dtype=np.int64)
+        else:
+            out = np.empty((w.ni, w.nj, w.nk), dtype=np.float64)
+        _chk(lib().picg_species_download_field(self.h, int(field), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    den = property(lambda self: self.download(SF_DEN))
+    den_fixed = property(lambda self: self.download(SF_DEN_FIXED))
+    macro_part_count = property(lambda self: self.download(SF_MACRO_COUNT))
+
+    def device_ptr(self, field):
+        p = C.c_void_p()
+        n = C.c_size_t(0)
+        _chk(lib().picg_species_device_ptr(self.h, int(field), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+
+class PotentialSolver:
+    """PotentialSolver with SolverType GS (ch4/v3/src/PotentialSolver.h:26-92)."""
+
+    def __init__(self, world, max_solver_it, tolerance):
+        self.world = world
+        self.h = C.c_void_p()
+        _chk(lib().picg_solver_create(world.h, C.c_uint(int(max_solver_it)), C.c_double(tolerance), C.byref(self.h)))
+        self.iterations = 0
+        self.L2 = 0.0
+
+    def close(self):
+        if self.h:
+            lib().picg_solver_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def setReferenceValues(self, phi0, n0, Te0):
+        _chk(lib().picg_solver_set_reference(self.h, C.c_double(phi0), C.c_double(n0), C.c_double(Te0)))
+
+    def setBoundaryMode(self, mode):
+        _chk(lib().picg_solver_set_boundary_mode(self.h, int(mode)))
+
+    def solveGS(self):
+        conv = C.c_int(0)
+        it = C.c_uint(0)
+        l2 = C.c_double(0)
+        _chk(lib().picg_solver_solve_gs(self.h, C.byref(conv), C.byref(it), C.byref(l2)))
+        self.iterations, self.L2 = it.value, l2.value
+        return bool(conv.value)
+
+    solve = solveGS
+
+    def iterate(self, n):
+        _chk(lib().picg_solver_iterate(self.h, C.c_uint(int(n))))
+
+    def residual(self):
+        l2 = C.c_double(0)
+        _chk(lib().picg_solver_residual(self.h, C.byref(l2)))
+        return l2.value
+
+    def computeEF(self):
+        _chk(lib().picg_solver_compute_ef(self.h))
+
+
+class MccStats(C.Structure):
+    _fields_ = [("candidates", C.c_uint64), ("collisions", C.c_uint64), ("ionizations", C.c_uint64), ("w_sigma_v_max", C.c_double)]
+
+
+class MC_MEX_Ionization:
+    """MC_MEX_Ionization (ch4/v3/src/Interactions.h:99-144); the cross-section table is passed as arrays."""
+
+    def __init__(self, neutrals, ions, electrons, world, table_E, table_sigma):
+        e = np.ascontiguousarray(table_E, dtype=np.float64)
+        s = np.ascontiguousarray(table_sigma, dtype=np.float64)
+        self.h = C.c_void_p()
+        _chk(lib().picg_mcc_create(neutrals.h, ions.h, electrons.h, world.h, _dp(e), _dp(s), int(e.size), C.c_double(neutrals.E_ion), C.byref(self.h)))
+        self.stats = MccStats()
+
+    def close(self):
+        if self.h:
+            lib().picg_mcc_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def apply(self, dt):
+        _chk(lib().picg_mcc_apply(self.h, C.c_double(dt), C.byref(self.stats)))
+        return self.stats
+
+    def setWsvMax(self, v):
+        _chk(lib().picg_mcc_set_wsv_max(self.h, C.c_double(v)))
+
+    def sigma(self, E_eV):
+        e = np.ascontiguousarray(E_eV, dtype=np.float64)
+        sc = np.empty_like(e)
+        si = np.empty_like(e)
+        _chk(lib().picg_mcc_sigma(self.h, int(e.size), _dp(e), _dp(sc), _dp(si)))
+        return sc, si
+
+
+_FACES = {"x-": 0, "-x": 0, "x+": 1, "+x": 1, "y-": 2, "-y": 2, "y+": 3, "+y": 3, "z-": 4, "-z": 4, "z+": 5, "+z": 5}
+
+
+class _Source:
+    def __init__(self, species, world, v_drift, den, T, inlet_face):
+        self.h = C.c_void_p()
+        _chk(lib().picg_source_create(species.h, world.h, C.c_double(v_drift), C.c_double(den), C.c_double(T), _FACES[inlet_face.lower()], C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().picg_source_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def sample(self):
+        n = C.c_size_t(0)
+        _chk(lib().picg_source_sample(self.h, C.byref(n)))
+        return n.value
+
+
+class ColdBeamSource(_Source):
+    """ColdBeamSource (ch4/v3/src/Source.h:41-52)."""
+
+    def __init__(self, species, world, v_drift, den, inlet_face="-z"):
+        super().__init__(species, world, v_drift, den, 0.0, inlet_face)
+
+
+class WarmBeamSource(_Source):
+    """WarmBeamSource (ch4/v3/src/Source.h:54-66)."""
+
+    def __init__(self, species, world, v_drift, den, T, inlet_face="-z"):
+        super().__init__(species, world, v_drift, den, T, inlet_face)

@@ -1,0 +1,192 @@
+/* picgpu.h -- C ABI of the B200-native PIC-DSMC particle loop (libpicgpu.so).
+ *
+ * This is the drop-in boundary for the per-timestep particle loop of the
+ * reference's ch4/v3 main (ch4/v3/src/main.cpp:177-288).  The reference has no
+ * FFI of its own; its "API" is the public C++ surface of World / Species /
+ * PotentialSolver / Source / Interaction.  Each entry point below names the
+ * reference member (file:line under /root/reference) whose device-side
+ * replacement it is.  The host-side C++ facade in
+ * engineering-degree-in-plasma-simulations_b200/host/ forwards those members
+ * to these functions; see INTEGRATION.md for the binding a maintainer adds.
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 on success or a negative
+ *    picg_status; picg_last_error() gives a human-readable message
+ *    (thread-local).  No exception crosses this boundary.
+ *  - one host thread drives one GPU; all kernels are issued on one CUDA stream
+ *    per process (picg_stream()), so call order == execution order, matching
+ *    the reference's sequential semantics.  Not re-entrant per handle.
+ *  - node fields are double[nv] in Field<T> order u=(i*nj+j)*nk+k
+ *    (ch4/v3/src/Field.h:16,88); vector fields are double[3*nv] xyz-interleaved;
+ *    cell fields are double[(ni-1)(nj-1)(nk-1)] in Field order
+ *    (i*(nj-1)+j)*(nk-1)+k; particles cross the boundary as the reference's
+ *    AoS record x y z u v w mpw (7 doubles, ch4/v3/src/Species.h:12-29).
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails
+ *    with PICG_ERR_NO_DEVICE.
+ */
+#ifndef PICGPU_H
+#define PICGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PICG_API __attribute__((visibility("default")))
+
+typedef enum {
+    PICG_OK = 0,
+    PICG_ERR_NO_DEVICE = -1,   /* no CUDA device / picg_init not called          */
+    PICG_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed           */
+    PICG_ERR_ARG = -3,         /* invalid argument (maps to std::invalid_argument)*/
+    PICG_ERR_OOM = -4,         /* device allocation failed                       */
+    PICG_ERR_OVERFLOW = -5,    /* fixed-point density accumulator overflowed     */
+    PICG_ERR_STATE = -6        /* call not valid in the current state            */
+} picg_status;
+
+typedef struct picg_world_s*   picg_world_t;
+typedef struct picg_species_s* picg_species_t;
+typedef struct picg_solver_s*  picg_solver_t;
+typedef struct picg_mcc_s*     picg_mcc_t;
+typedef struct picg_source_s*  picg_source_t;
+
+/* ------------------------------------------------------------------ runtime */
+PICG_API int         picg_init(int device);                 /* select device, create the stream */
+PICG_API int         picg_shutdown(void);
+PICG_API const char* picg_last_error(void);
+PICG_API const char* picg_version(void);
+PICG_API int         picg_device_count(int* n);
+PICG_API void*       picg_stream(void);                     /* cudaStream_t all kernels run on  */
+PICG_API int         picg_synchronize(void);
+PICG_API int         picg_seed(uint64_t seed);              /* Philox key for every stochastic kernel (replaces `rnd = Rnd(seed)`, Rnd.cpp:7) */
+PICG_API int         picg_set_rank(int rank, int world_size); /* multi-GPU: decorrelates RNG streams, rescales MC candidate counts */
+/* number of kernels this library launched since the last reset (bench.py's gpu_launches) */
+PICG_API uint64_t    picg_launch_count(void);
+PICG_API void        picg_launch_count_reset(void);
+/* per-kernel CUDA-event timers: enable, then read accumulated ms and launch counts by kernel id */
+PICG_API int         picg_timers_enable(int on);
+PICG_API int         picg_timers_reset(void);
+PICG_API int         picg_timer_read(int kernel_id, double* total_ms, uint64_t* launches);
+PICG_API const char* picg_timer_name(int kernel_id);        /* NULL past the last id */
+
+/* -------------------------------------------------------------------- World */
+/* World::World(int,int,int,type_calc3,type_calc3)  ch4/v3/src/World.cpp:23-27, setExtents :63-77, computeNodeVolumes :353-367 */
+PICG_API int picg_world_create(int ni, int nj, int nk, const double x0[3], const double xm[3], picg_world_t* out);
+PICG_API int picg_world_destroy(picg_world_t w);
+/* World::setTime  World.cpp:323-326 (dt is what addParticle's half-step rewind uses, Species.cpp:431) */
+PICG_API int picg_world_set_time(picg_world_t w, double dt, int num_ts);
+/* World::addObject<Rectangle>/<Sphere>  World.h:119-131, Object.cpp:163-171,111-115 */
+PICG_API int picg_world_add_rectangle(picg_world_t w, const double centre[3], double phi, const double sides[3]);
+PICG_API int picg_world_add_sphere(picg_world_t w, const double centre[3], double phi, double radius);
+/* World::computeObjectID  World.cpp:276-292 -- rasterised on the host with the reference's closed fp64 test
+ * (SURVEY B18), then uploaded: sets object_id, node_type=DIRICHLET and phi on object nodes. */
+PICG_API int picg_world_compute_object_id(picg_world_t w);
+
+typedef enum {
+    PICG_F_PHI = 0, PICG_F_RHO = 1, PICG_F_NODE_VOL = 2, PICG_F_EF = 3 /*3*nv*/,
+    PICG_F_OBJECT_ID = 4 /*as double*/, PICG_F_NODE_TYPE = 5 /*as double*/
+} picg_world_field;
+/* public Field members World::{phi,rho,node_vol,ef,object_id,node_type}  World.h:51-57 */
+PICG_API int picg_world_download(picg_world_t w, int field, double* host);
+PICG_API int picg_world_upload(picg_world_t w, int field, const double* host);
+/* World::computeChargeDensity  World.cpp:193-200 : rho = sum_s charge_s * den_s over charged species */
+PICG_API int picg_world_charge_density(picg_world_t w, const picg_species_t* species, int n);
+/* World::getPE  World.cpp:108-118 */
+PICG_API int picg_world_potential_energy(picg_world_t w, double* pe);
+/* device pointers for zero-copy interop (torch.distributed all-reduce of the grids) */
+PICG_API int picg_world_device_ptr(picg_world_t w, int field, void** dptr, size_t* bytes);
+
+/* ------------------------------------------------------------------ Species */
+/* Species::Species(name,mass,charge,World&,mpw0[,E_ion])  Species.cpp:29-40 */
+PICG_API int picg_species_create(picg_world_t w, double mass, double charge, double mpw0, picg_species_t* out);
+PICG_API int picg_species_destroy(picg_species_t s);
+PICG_API int picg_species_reserve(picg_species_t s, size_t capacity);
+/* Species::getNumParticles  Species.cpp:44-46 */
+PICG_API int picg_species_count(picg_species_t s, size_t* n);
+/* raw store access == Species::getPartRef() / getConstPartRef()  Species.cpp:820-828 */
+PICG_API int picg_species_upload(picg_species_t s, size_t n, const double* aos7);
+PICG_API int picg_species_download(picg_species_t s, size_t capacity, double* aos7, size_t* n);
+/* Species::addParticle(pos,vel,mpw)  Species.cpp:420-434: reject NaN / out of bounds / in object, then
+ * vel -= charge/mass*E(pos)*(0.5*world.dt).  n particles at once; *accepted returns how many were kept. */
+PICG_API int picg_species_add_particles(picg_species_t s, size_t n, const double* aos7, size_t* accepted);
+/* Species::advanceElectrons(dt)  Species.cpp:258-399 (gather, kick, drift, absorb on walls/objects, remove) */
+PICG_API int picg_species_push_electrons(picg_species_t s, double dt);
+/* Species::advanceNonElectron(neutrals, spherium, dt)  Species.cpp:47-256 */
+PICG_API int picg_species_push_heavy(picg_species_t s, picg_species_t neutrals, picg_species_t spherium, double dt, int sputtering);
+/* ch2 Species::advance(): kick, drift, specular reflection on the six faces  ch2/v2/Species.cpp:18-55 */
+PICG_API int picg_species_push_reflect(picg_species_t s, double dt);
+/* ch3 Species::advance(): kick, drift, delete in object / out of bounds  ch3/v1/Species.cpp:28-45 (== electron push arithmetic) */
+/* Species::computeNumberDensity  Species.cpp:401-416 + Field::scatter Field.h:157-199 + operator/= :563-583.
+ * Deterministic: contributions are quantised llrint(c*2^S) and summed in int64. */
+PICG_API int picg_species_deposit_density(picg_species_t s);
+/* fused Species::advanceElectrons + computeNumberDensity (+ computeMacroParticlesCount): one pass over the particles */
+PICG_API int picg_species_push_electrons_deposit(picg_species_t s, double dt, int count_cells);
+PICG_API int picg_species_density_scale(picg_species_t s, int* S);           /* the S of the last deposit */
+PICG_API int picg_species_set_density_scale(picg_species_t s, int S);        /* pin S (tests); <-1000 = automatic */
+/* Species::sampleMoments :767-776, computeGasProperties :777-804, clearSamples :805-812 */
+PICG_API int picg_species_sample_moments(picg_species_t s);
+PICG_API int picg_species_compute_gas_properties(picg_species_t s);
+PICG_API int picg_species_clear_samples(picg_species_t s);
+/* Species::updateAverages -> Field::updateMovingAverage  Field.h:246-261 */
+PICG_API int picg_species_update_averages(picg_species_t s);
+/* Species::computeMacroParticlesCount  Species.cpp:813-819 */
+PICG_API int picg_species_count_per_cell(picg_species_t s);
+/* Species::sortIndexes  Species.cpp:905-929 -> device: cell-sorted SoA layout + cell_start[] */
+PICG_API int picg_species_sort(picg_species_t s);
+/* diagnostics: getMicroCount, getMomentum, getKE  Species.cpp:726-755 */
+PICG_API int picg_species_diagnostics(picg_species_t s, double* micro_count, double momentum[3], double* ke);
+
+typedef enum {
+    PICG_SF_DEN = 0, PICG_SF_DEN_AVG = 1, PICG_SF_T = 2, PICG_SF_VEL = 3 /*3*nv*/,
+    PICG_SF_MACRO_COUNT = 4 /*cells*/, PICG_SF_N_SUM = 5, PICG_SF_NV_SUM = 6 /*3*nv*/,
+    PICG_SF_NUU_SUM = 7, PICG_SF_NVV_SUM = 8, PICG_SF_NWW_SUM = 9,
+    PICG_SF_DEN_FIXED = 10 /* int64[nv]: the raw fixed-point accumulator */
+} picg_species_field;
+PICG_API int picg_species_download_field(picg_species_t s, int field, void* host);
+PICG_API int picg_species_device_ptr(picg_species_t s, int field, void** dptr, size_t* bytes);
+/* multi-GPU: after all-reducing DEN_FIXED across ranks, turn it into den (divide by 2^S and node_vol) */
+PICG_API int picg_species_finalize_density(picg_species_t s);
+/* multi-GPU: deposit into the fixed-point accumulator only (no finalize) */
+PICG_API int picg_species_deposit_density_partial(picg_species_t s);
+
+/* ---------------------------------------------------------- PotentialSolver */
+/* PotentialSolver(World&, max_it, tol, GS)  PotentialSolver.cpp:44-52, precalculate :473-491 */
+PICG_API int picg_solver_create(picg_world_t w, unsigned max_it, double tol, picg_solver_t* out);
+PICG_API int picg_solver_destroy(picg_solver_t s);
+/* setReferenceValues(phi0,n0,Te0)  PotentialSolver.cpp:409-413 */
+PICG_API int picg_solver_set_reference(picg_solver_t s, double phi0, double n0, double Te0);
+/* boundary mode: 0 = v3/ch3 zero-gradient faces updated in-sweep (PotentialSolver.cpp:96-107),
+ *                1 = ch2 interior-only sweep, faces keep their (Dirichlet) values (ch2/v2/PotentialSolver.cpp:39-52) */
+PICG_API int picg_solver_set_boundary_mode(picg_solver_t s, int mode);
+/* solveGS  PotentialSolver.cpp:69-166 as red-black SOR (w=1.4), residual every 25 iterations normalised by nv */
+PICG_API int picg_solver_solve_gs(picg_solver_t s, int* converged, unsigned* iterations, double* L2);
+/* run exactly n iterations without convergence checks (benchmarks) */
+PICG_API int picg_solver_iterate(picg_solver_t s, unsigned n);
+PICG_API int picg_solver_residual(picg_solver_t s, double* L2);
+/* computeEF  PotentialSolver.cpp:354-408 */
+PICG_API int picg_solver_compute_ef(picg_solver_t s);
+
+/* -------------------------------------------------------- MC_MEX_Ionization */
+/* MC_MEX_Ionization(neutrals, ions, electrons, world, table)  Interactions.cpp:476-539; the cross-section table
+ * (2 columns eV, m^2) is passed in memory instead of by path; the ctor preconditions are checked (PICG_ERR_ARG). */
+PICG_API int picg_mcc_create(picg_species_t neutrals, picg_species_t ions, picg_species_t electrons, picg_world_t w,
+                             const double* table_E, const double* table_sigma, int n_table, double E_ion_J, picg_mcc_t* out);
+PICG_API int picg_mcc_destroy(picg_mcc_t m);
+typedef struct { uint64_t candidates, collisions, ionizations; double w_sigma_v_max; } picg_mcc_stats;
+/* Interaction::apply(dt) -> MC_MEX_Ionization::apply_vector_indexes  Interactions.cpp:567-762 */
+PICG_API int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* stats /*may be NULL*/);
+PICG_API int picg_mcc_set_wsv_max(picg_mcc_t m, double v);
+PICG_API int picg_mcc_sigma(picg_mcc_t m, int n, const double* E_eV, double* sigma_coll, double* sigma_ion); /* evaluateSigmaColl/Ion :541-566 */
+
+/* ------------------------------------------------------------------- Source */
+/* ColdBeamSource / WarmBeamSource  Source.cpp:3-191; face: 0 x- 1 x+ 2 y- 3 y+ 4 z- 5 z+ ; T<=0 => cold */
+PICG_API int picg_source_create(picg_species_t s, picg_world_t w, double v_drift, double den, double T, int face, picg_source_t* out);
+PICG_API int picg_source_destroy(picg_source_t src);
+/* Source::sample()  Source.cpp:99-103,187-191 */
+PICG_API int picg_source_sample(picg_source_t src, size_t* injected /*may be NULL*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PICGPU_H */

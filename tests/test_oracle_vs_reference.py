@@ -1,0 +1,160 @@
+"""Pins the C restatement (oracle/pic_oracle.c) against the compiled, unmodified reference
+(oracle/_ref/libref_v3.so).  CPU only.  Skipped where the reference library is absent (it is built
+from /root/reference by oracle/Makefile and travels to the GPU box as a prebuilt file)."""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.reference
+
+
+def _worlds(orc, ref, ni=11, nj=9, nk=13, electrodes=True, spheres=()):
+    if electrodes:
+        x0, xm, rects = util.discharge_geometry(ni, nj, nk)
+    else:
+        x0, xm, rects = np.array([-0.1, -0.1, 0.0]), np.array([0.1, 0.1, 0.2]), []
+    w = util.build_world(ref.World, ni, nj, nk, x0, xm, rects, spheres)
+    g = util.build_grid(orc, ni, nj, nk, x0, xm, rects, spheres)
+    return w, g, x0, xm
+
+
+def test_geometry_node_volumes_and_object_mask(orc, ref):
+    w, g, x0, xm = _worlds(orc, ref, 41, 41, 61)
+    assert np.array_equal(w.get(2), g.node_volumes())
+    oid, phi = g.compute_object_id()
+    assert np.array_equal(w.get(4), oid.astype(float))
+    assert np.array_equal(w.get(0), phi)
+    # the two nominally symmetric electrodes rasterise asymmetrically (k=0..3 and k=58..60)
+    planes = np.nonzero(oid[20, 20, :])[0]
+    assert list(planes) == [0, 1, 2, 3, 58, 59, 60]
+    w.close()
+
+
+def test_in_object_in_bounds_pointwise(orc, ref):
+    sph = [((0.0, 0.0, 0.0025), -100.0, 0.0007)]
+    w, g, x0, xm = _worlds(orc, ref, spheres=sph)
+    rng = np.random.default_rng(1)
+    pts = x0 + (rng.random((4000, 3)) * 1.2 - 0.1) * (xm - x0)
+    for p in pts:
+        assert w.inObject(p) == g.in_object(p)
+        assert w.inBounds(p) == g.in_bounds(p)
+    w.close()
+
+
+def test_push_electrons_bit_exact(orc, ref):
+    w, g, x0, xm = _worlds(orc, ref)
+    ef = util.smooth_ef(w.shape, x0, xm, seed=3, amp=3e6)
+    w.set(3, ef)
+    parts = util.random_particles(5000, x0, xm, seed=4, vth=2e6)
+    sp = ref.Species("e-", util.ME, -util.QE, w, 100.0)
+    sp.setParticles(parts)
+    dt = 2e-10
+    sp.advanceElectrons(dt)               # serial path (multithreading off in the fixture)
+    got, alive = g.push_electrons(ef, -util.QE, util.ME, dt, parts)
+    assert 0 < alive.sum() < len(parts)   # both survivors and absorbed particles are exercised
+    # the reference removes by swap-with-last: compare as multisets, bit for bit
+    assert np.array_equal(util.sort_rows(sp.getParticles()), util.sort_rows(got[alive]))
+    sp.close(); w.close()
+
+
+def test_add_particle_filter_and_rewind_bit_exact(orc, ref):
+    w, g, x0, xm = _worlds(orc, ref)
+    ef = util.smooth_ef(w.shape, x0, xm, seed=5, amp=1e6)
+    w.set(3, ef)
+    parts = util.random_particles(2000, x0 - 0.1 * (xm - x0), xm + 0.1 * (xm - x0), seed=6)   # some outside, some in electrodes
+    sp = ref.Species("O+", 16 * util.AMU, util.QE, w, 100.0)
+    for p in parts:
+        sp.addParticle(p)
+    got = g.add_particles(ef, util.QE, 16 * util.AMU, 1e-12, parts)
+    assert 0 < len(got) < len(parts)
+    assert np.array_equal(sp.getParticles(), got)
+    # NaN rejection (Species.cpp:421-423) is checked on the restatement only: the reference's NaN branch
+    # prints through Vec3::isNan and crashes inside this harness, so it is not driven here.
+    bad = parts[:4].copy(); bad[1, 3] = np.nan; bad[2, 0] = np.nan
+    kept = g.add_particles(ef, util.QE, 16 * util.AMU, 1e-12, bad)
+    assert len(kept) == len(g.add_particles(ef, util.QE, 16 * util.AMU, 1e-12, parts[[0, 3]]))
+    sp.close(); w.close()
+
+
+def test_deposit_fp64_bit_exact_and_fixed_point_normwise(orc, ref):
+    w, g, x0, xm = _worlds(orc, ref)
+    parts = util.random_particles(20000, x0, xm, seed=7, mpw=(1.0, 5e11))
+    sp = ref.Species("O", 16 * util.AMU, 0.0, w, 5e11)
+    sp.setParticles(parts)
+    sp.computeNumberDensity()
+    den_ref = sp.get(0)
+    vol = g.node_volumes()
+    # same summation order => same bits
+    assert np.array_equal(den_ref, g.deposit_fp64(parts, vol))
+    # fixed point: quantisation + order noise only, normwise 1e-12
+    S = 62 - 50
+    den_fx = g.finalize_density(g.deposit_fixed(parts, S), S, vol)
+    assert util.norm_err(den_fx, den_ref) < 1e-12
+    # invariant: sum(den*vol) == sum(mpw)
+    assert abs((den_fx * vol).sum() - parts[:, 6].sum()) / parts[:, 6].sum() < 1e-12
+    sp.close(); w.close()
+
+
+def test_count_per_cell_and_moments(orc, ref):
+    w, g, x0, xm = _worlds(orc, ref)
+    parts = util.random_particles(6000, x0, xm, seed=8)
+    sp = ref.Species("e-", util.ME, -util.QE, w, 100.0)
+    sp.setParticles(parts)
+    sp.computeMacroParticlesCount()
+    assert np.array_equal(sp.get(4), g.count_per_cell(parts))
+    sp.sampleMoments(); sp.sampleMoments()          # accumulates: no clear between calls (Species.cpp:767-776)
+    sums = g.sample_moments(parts)
+    sums = g.sample_moments(parts, sums)
+    for fid, s in zip((5, 6, 7, 8, 9), sums):
+        assert np.array_equal(sp.get(fid), s)
+    sp.close(); w.close()
+
+
+def test_charge_density_bit_exact(orc, ref):
+    w, g, x0, xm = _worlds(orc, ref)
+    vol = g.node_volumes()
+    sps, dens, qs = [], [], []
+    for i, (m, q) in enumerate([(16 * util.AMU, 0.0), (16 * util.AMU, util.QE), (util.ME, -util.QE)]):
+        parts = util.random_particles(3000, x0, xm, seed=20 + i)
+        sp = ref.Species("s%d" % i, m, q, w, 1.0)
+        sp.setParticles(parts); sp.computeNumberDensity()
+        sps.append(sp); dens.append(g.deposit_fp64(parts, vol)); qs.append(q)
+    w.computeChargeDensity(sps)
+    assert np.array_equal(w.get(1), g.charge_density(dens, qs))
+    for sp in sps:
+        sp.close()
+    w.close()
+
+
+@pytest.mark.parametrize("n0,Te0", [(0.0, 1e20), (1.5, 1e10), (1e12, 5000.0)])
+def test_solve_gs_and_ef_bit_exact(orc, ref, n0, Te0):
+    w, g, x0, xm = _worlds(orc, ref, 13, 11, 17)
+    rng = np.random.default_rng(9)
+    rho = rng.normal(0, 1e-7, w.shape)
+    w.set(1, rho)
+    phi_start = w.get(0)
+    oid = w.get(4).astype(np.int32)
+    sol = ref.PotentialSolver(w, 400, 1e-3, ref.PotentialSolver.GS)
+    sol.setReferenceValues(0.0, n0, Te0)
+    conv_ref = sol.solveGS()
+    phi, conv, its, l2 = g.solve_gs(oid, rho, phi_start, 400, 1e-3, 0.0, n0, Te0)
+    assert conv == conv_ref
+    assert np.array_equal(w.get(0), phi)             # same sweep order, same arithmetic => same bits
+    sol.computeEF()
+    assert np.array_equal(w.get(3), g.compute_ef(phi))
+    sol.close(); w.close()
+
+
+def test_red_black_shares_the_fixed_point(orc, ref):
+    """The device runs red-black; the reference lexicographic GS.  Both driven to a 1e-9 residual must agree to 1e-6 relative."""
+    w, g, x0, xm = _worlds(orc, ref, 13, 11, 17)
+    rng = np.random.default_rng(10)
+    rho = rng.normal(0, 1e-7, w.shape)
+    oid = w.get(4).astype(np.int32)
+    phi0 = w.get(0)
+    a, ca, ia, _ = g.solve_gs(oid, rho, phi0, 20000, 1e-9)
+    b, cb, ib, _ = g.solve_rb(oid, rho, phi0, 20000, 1e-9)
+    assert ca and cb
+    assert util.norm_err(b, a) < 1e-6
+    w.close()
