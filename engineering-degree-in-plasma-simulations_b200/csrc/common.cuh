@@ -57,7 +57,8 @@ struct picg_world_s {
 struct picg_species_s {
     picg_world_s* w;
     double mass, charge, mpw0;
-    size_t cap = 0;                    // allocated particles per array
+    uint32_t id = 0;                   // creation order; decorrelates the species' RNG streams
+    size_t cap = 0;                   // allocated particles per array
     size_t n_host = 0;                 // last count known to the host
     bool n_host_valid = true;
     size_t n_upper = 0;                // always >= the true device count (sizes scratch buffers)

@@ -1,0 +1,309 @@
+// Variable-weight Monte-Carlo electron-neutral collisions with electron-impact ionisation.
+//   k_mcc : MC_MEX_Ionization::apply_vector_indexes   ch4/v3/src/Interactions.cpp:600-762
+//           collide :885-947, newVelocityElecton :845-862, evaluateSigmaColl :541-558, evaluateSigmaIon :559-566
+// Both species are cell-sorted on the device (sort.cu); cell c's particles are the index ranges
+// [cell_start[c], cell_start[c+1]).  One thread owns one cell and runs the reference's candidate loop
+// sequentially (weights and the neutral list mutate inside the loop, :687-725), cells are independent.
+// RNG: Philox stream (RNG_MCC) addressed by (cell, apply-call number), so results are independent of the
+// launch geometry.  New ions / electrons / split-off neutrals are appended through atomic cursors.
+#include "common.cuh"
+#include "philox.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+using namespace picg;
+
+namespace picg { int sort_species(picg_species_s* s); }
+
+#define MCC_EXTRA 16          // split-off neutrals created in this call that remain selectable within the cell (:699-701)
+
+struct MccParams {
+    double m_n, m_e, sum_mass, E_rel_eV, E_ele_eV, two_qe_me, c0, c1, c2, B_inc, E_ion_eV, inv_dv, rank_scale;
+    int n_tab; const double* tab_E; const double* tab_s;
+};
+struct Store { double* a[7]; SpeciesCounters* ctr; u64 cap; };
+
+// evaluateSigmaColl (:541-558): std::map lower_bound + linear interpolation, clamped to the end values
+__host__ __device__ __forceinline__ double sigma_coll(const MccParams& P, double E) {
+    int lo = 0, hi = P.n_tab;                       // first index with tab_E >= E
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (P.tab_E[mid] < E) lo = mid + 1; else hi = mid; }
+    if (lo == 0) return P.tab_s[0];
+    if (lo == P.n_tab) return P.tab_s[P.n_tab - 1];
+    double x1 = P.tab_E[lo - 1], x2 = P.tab_E[lo], y1 = P.tab_s[lo - 1], y2 = P.tab_s[lo];
+    return y1 + (E - x1) * (y2 - y1) / (x2 - x1);
+}
+// evaluateSigmaIon (:559-566)
+__host__ __device__ __forceinline__ double sigma_ion(const MccParams& P, double E) {
+    if (E <= P.E_ion_eV) return 0;
+    return P.c0 * log(E / P.c1) / E * exp(-P.c2 / E);
+}
+// newVelocityElecton, IONIZE_1 / LAB frame (:845-862); note i x u is not normalised
+__device__ __forceinline__ void new_velocity_electron(PhiloxStream& r, const MccParams& P, double E, const double u[3], double out[3]) {
+    double cos_ksi = (2 + E - 2 * pow(1 + E, r.next())) / E;
+    double sin_ksi = sqrt(1 - cos_ksi * cos_ksi);
+    double phi = 2 * 3.141592653 * r.next();
+    double v_mag = sqrt(E * P.two_qe_me);
+    double ixu[3] = {0.0 * u[2] - 0.0 * u[1], 0.0 * u[0] - 1.0 * u[2], 1.0 * u[1] - 0.0 * u[0]};        // (1,0,0) x u
+    double uxi[3] = {u[1] * ixu[2] - u[2] * ixu[1], u[2] * ixu[0] - u[0] * ixu[2], u[0] * ixu[1] - u[1] * ixu[0]};   // u x (i x u)
+    double sp = sin(phi), cp = cos(phi);
+    for (int c = 0; c < 3; c++) out[c] = (cos_ksi * u[c] + ixu[c] * sin_ksi * sp + uxi[c] * sin_ksi * cp) * v_mag;
+}
+// collide (:885-947).  vel_neu is never modified by the reference.  Returns ionised flag.
+__device__ __forceinline__ bool collide(PhiloxStream& r, const MccParams& P, const double vn[3], double ve[3], double vnew[3], double s_coll) {
+    double g[3] = {vn[0] - ve[0], vn[1] - ve[1], vn[2] - ve[2]};
+    double g_mag = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    double m_r = P.m_n * P.m_e / P.sum_mass;
+    double E_rel_J = 0.5 * m_r * g_mag * g_mag;
+    double Pion = sigma_ion(P, E_rel_J / 1.602176565e-19) / s_coll;
+    if (r.next() <= Pion) {
+        double ve_mag = sqrt(ve[0] * ve[0] + ve[1] * ve[1] + ve[2] * ve[2]);
+        double E_inc = ve_mag * ve_mag * P.E_ele_eV;
+        if (E_inc < P.E_ion_eV) return false;                                          // :900-905
+        double E_ej = 10.0 * tan(r.next() * atan((E_inc - P.E_ion_eV) / (2 * P.B_inc)));
+        double E_sc = E_inc - P.E_ion_eV - E_ej;
+        if (E_sc < 0) E_sc = 0.000001;
+        double inv = 1.0 / ve_mag, u[3] = {ve[0] * inv, ve[1] * inv, ve[2] * inv};      // Vec3::unit
+        new_velocity_electron(r, P, E_sc, u, ve);
+        new_velocity_electron(r, P, E_ej, u, vnew);
+        return true;
+    }
+    // elastic, isotropic in the centre of mass; only the electron changes (:933-947)
+    double cm[3];
+    for (int c = 0; c < 3; c++) cm[c] = (P.m_n * vn[c] + P.m_e * ve[c]) * (1.0 / P.sum_mass);
+    double cos_ksi = 2 * r.next() - 1;
+    double sin_ksi = sqrt(1 - cos_ksi * cos_ksi);
+    double eps = 2 * 3.141592653 * r.next();
+    g[0] = g_mag * cos_ksi; g[1] = g_mag * sin_ksi * cos(eps); g[2] = g_mag * sin_ksi * sin(eps);
+    double f = P.m_n / P.sum_mass;
+    for (int c = 0; c < 3; c++) ve[c] = cm[c] - f * g[c];
+    return false;
+}
+
+__device__ __forceinline__ long long append(const Store& s, const double pos[3], const double v[3], double mpw) {
+    u64 dst = atomicAdd(&s.ctr->n, 1ull);
+    if (dst >= s.cap) { atomicAdd(&s.ctr->overflow, 1ull); return -1; }
+    s.a[0][dst] = pos[0]; s.a[1][dst] = pos[1]; s.a[2][dst] = pos[2]; s.a[3][dst] = v[0]; s.a[4][dst] = v[1]; s.a[5][dst] = v[2]; s.a[6][dst] = mpw;
+    return (long long)dst;
+}
+__device__ __forceinline__ void atomic_max_pos_double(double* addr, double v) {     // valid for non-negative doubles
+    atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
+}
+
+// stats: [0] candidates [1] collisions [2] ionisations [3] skipped (electron heavier than neutral)
+__global__ void __launch_bounds__(128) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, const unsigned* __restrict__ cs_n,
+                                             const unsigned* __restrict__ cs_e, double* __restrict__ wsv, u64* __restrict__ stats, double dt,
+                                             uint64_t seed, uint32_t stream, uint32_t call) {
+    const double W_max = wsv[0];
+    u64 n_cand = 0, n_coll = 0, n_ion = 0, n_skip = 0; double step_max = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.nc; c += gridDim.x * blockDim.x) {
+        unsigned e0 = cs_e[c]; int np_e = (int)(cs_e[c + 1] - e0);
+        if (np_e <= 0) continue;
+        unsigned n0 = cs_n[c]; int np_n0 = (int)(cs_n[c + 1] - n0);
+        if (np_n0 <= 0) continue;
+        int np_n = np_n0;
+        double frac = np_n * np_e * W_max * dt * P.inv_dv * P.rank_scale;               // :646 (x G ranks)
+        int n_groups = (int)(frac + 0.5);
+        if (n_groups > np_n) n_groups = np_n - 1;                                         // :649-653
+        if (n_groups <= 0) continue;
+        PhiloxStream r; r.init(seed, stream, (u64)c, call);
+        long long extra[MCC_EXTRA]; int n_extra = 0;
+        for (int t = 0; t < n_groups; t++) {
+            int a = (int)(r.next() * np_n);                                                // rnd(0,np) = 0 + rnd()*(np-0)
+            int b = (int)(r.next() * np_e);
+            u64 pn = a < np_n0 ? (u64)n0 + a : (u64)extra[a - np_n0];
+            u64 pe = (u64)e0 + b;
+            double vn[3] = {neu.a[3][pn], neu.a[4][pn], neu.a[5][pn]}, ve[3] = {ele.a[3][pe], ele.a[4][pe], ele.a[5][pe]};
+            double d[3] = {vn[0] - ve[0], vn[1] - ve[1], vn[2] - ve[2]};
+            double v_rel = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            double E_rel = P.E_rel_eV * v_rel * v_rel;
+            double s_coll = sigma_coll(P, E_rel);
+            double Wn = neu.a[6][pn], We = ele.a[6][pe];
+            double Wg = Wn < We ? We : Wn, Wl = Wn < We ? Wn : We;                         // greaterLesser funkc.h:19-25
+            double Wsv = Wg * s_coll * v_rel;
+            if (Wsv > step_max) step_max = Wsv;
+            n_cand++;
+            if (r.next() < Wsv / W_max) {
+                n_coll++;
+                if (Wn > We) {                                                             // split the neutral (:684-703)
+                    neu.a[6][pn] = Wn - We;
+                    double vnew[3] = {0, 0, 0};
+                    bool ionised = collide(r, P, vn, ve, vnew, s_coll);
+                    ele.a[3][pe] = ve[0]; ele.a[4][pe] = ve[1]; ele.a[5][pe] = ve[2];
+                    double pos[3] = {neu.a[0][pn], neu.a[1][pn], neu.a[2][pn]};
+                    if (ionised) {
+                        n_ion++;
+                        append(ion, pos, vn, Wl);                                          // no half-step rewind (:694-695)
+                        append(ele, pos, vnew, Wl);
+                    } else {
+                        long long idx = append(neu, pos, vn, We);                          // split-off neutral of the electron's weight
+                        if (idx >= 0 && n_extra < MCC_EXTRA) { extra[n_extra++] = idx; np_n++; }
+                    }
+                } else if (Wn < We) {
+                    n_skip++;          // the reference's electron-heavier branch is defective; not reproduced, counted
+                }                      // equal weights: accepted pair does nothing (:727-734)
+            }
+        }
+    }
+    // block-level reduction of the statistics
+    __shared__ u64 sh[4]; __shared__ double sh_max;
+    if (threadIdx.x == 0) { sh[0] = sh[1] = sh[2] = sh[3] = 0; sh_max = 0; }
+    __syncthreads();
+    if (n_cand) { atomicAdd(&sh[0], n_cand); atomicAdd(&sh[1], n_coll); atomicAdd(&sh[2], n_ion); atomicAdd(&sh[3], n_skip); atomic_max_pos_double(&sh_max, step_max); }
+    __syncthreads();
+    if (threadIdx.x == 0 && sh[0]) {
+        atomicAdd(&stats[0], sh[0]); atomicAdd(&stats[1], sh[1]); atomicAdd(&stats[2], sh[2]); atomicAdd(&stats[3], sh[3]);
+        atomic_max_pos_double(&wsv[1], sh_max);
+    }
+}
+// W_sigma_v_rel_max <- max sampled value of this step, only if a collision happened (:751-756)
+__global__ void k_mcc_finish(double* wsv, const u64* stats) { if (stats[1]) wsv[0] = wsv[1]; }
+// upper bound on appended particles: sum over cells of n_groups
+__global__ void __launch_bounds__(256) k_mcc_count(Grid g, const unsigned* __restrict__ cs_n, const unsigned* __restrict__ cs_e, const double* __restrict__ wsv,
+                                                   double dt, double inv_dv, double rank_scale, u64* __restrict__ total) {
+    u64 acc = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.nc; c += gridDim.x * blockDim.x) {
+        int np_e = (int)(cs_e[c + 1] - cs_e[c]), np_n = (int)(cs_n[c + 1] - cs_n[c]);
+        if (np_e <= 0 || np_n <= 0) continue;
+        int n_groups = (int)(np_n * np_e * wsv[0] * dt * inv_dv * rank_scale + 0.5);
+        if (n_groups > np_n) n_groups = np_n - 1;
+        if (n_groups > 0) acc += n_groups;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
+}
+__global__ void k_sigma_eval(MccParams P, int n, const double* __restrict__ E, double* __restrict__ sc, double* __restrict__ si) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) { sc[t] = sigma_coll(P, E[t]); si[t] = sigma_ion(P, E[t]); }
+}
+
+static MccParams make_params(const picg_mcc_s* m) {
+    MccParams P;
+    P.m_n = m->neu->mass; P.m_e = m->ele->mass; P.sum_mass = P.m_n + P.m_e;
+    double m_r = P.m_n * P.m_e / (P.m_n + P.m_e);                                         // :503
+    P.E_rel_eV = 0.5 * m_r / 1.602176565e-19;                                             // :509
+    P.E_ele_eV = 9.10938215e-31 * 0.5 / 1.602176565e-19;                                  // Interactions.h:123 (Const::m_e)
+    P.two_qe_me = 2 * 1.602176565e-19 / 9.10938215e-31;                                   // Interactions.h:124
+    P.c0 = 1.015e-18; P.c1 = 9.793e+00; P.c2 = 6.181e+01; P.B_inc = 10.0;                 // :513-518
+    P.E_ion_eV = m->E_ion_J / 1.602176565e-19;                                            // :499
+    const Grid& g = m->w->g;
+    P.inv_dv = 1 / (g.dx[0] * g.dx[1] * g.dx[2]);                                         // :500-501
+    P.rank_scale = (double)g_world_size;
+    P.n_tab = m->n_table; P.tab_E = m->tab_E; P.tab_s = m->tab_s;
+    return P;
+}
+static Store store_of(picg_species_s* s) { Store st; for (int c = 0; c < 7; c++) st.a[c] = s->a[c]; st.ctr = s->ctr; st.cap = s->cap; return st; }
+
+extern "C" {
+
+int picg_mcc_create(picg_species_t neutrals, picg_species_t ions, picg_species_t electrons, picg_world_t w, const double* table_E,
+                    const double* table_sigma, int n_table, double E_ion_J, picg_mcc_t* out) {
+    REQUIRE_DEVICE(); REQUIRE_ARG(neutrals && ions && electrons && w && out && table_E && table_sigma, "picg_mcc_create: null argument");
+    // constructor preconditions of the reference (:479-489) -> std::invalid_argument in the facade
+    REQUIRE_ARG(!(neutrals->mpw0 < 1e2 * electrons->mpw0), "neutrals species should have mpw0 at least 100 times greater than electrons");
+    REQUIRE_ARG(!(!E_ion_J || E_ion_J < 0), "neutral species must have proper ionization energy E_ion (in Joules)");
+    REQUIRE_ARG(!(neutrals->mpw0 < ions->mpw0), "neutrals.mpw0 must be greater or equal ions.mpw0");
+    REQUIRE_ARG(n_table >= 1, "picg_mcc_create: empty cross-section table (the reference throws when the file cannot be opened, :521)");
+    picg_mcc_s* m = new picg_mcc_s();
+    m->neu = neutrals; m->ion = ions; m->ele = electrons; m->w = w; m->E_ion_J = E_ion_J;
+    // std::map semantics: sorted by energy, a repeated key keeps its last value (:530)
+    std::vector<std::pair<double, double>> tab;
+    for (int i = 0; i < n_table; i++) {
+        bool dup = false;
+        for (auto& t : tab) if (t.first == table_E[i]) { t.second = table_sigma[i]; dup = true; }
+        if (!dup) tab.push_back({table_E[i], table_sigma[i]});
+    }
+    std::sort(tab.begin(), tab.end());
+    m->n_table = (int)tab.size();
+    std::vector<double> E(tab.size()), S(tab.size());
+    for (size_t i = 0; i < tab.size(); i++) { E[i] = tab[i].first; S[i] = tab[i].second; }
+    cudaError_t e;
+    if ((e = cudaMalloc(&m->tab_E, E.size() * 8)) != cudaSuccess || (e = cudaMalloc(&m->tab_s, S.size() * 8)) != cudaSuccess ||
+        (e = cudaMalloc(&m->wsv, 2 * 8)) != cudaSuccess || (e = cudaMalloc(&m->stats, 8 * 8)) != cudaSuccess) {
+        picg_mcc_destroy(m); return cuda_fail(e, "cudaMalloc(mcc)", __FILE__, __LINE__);
+    }
+    CUDA_TRY(cudaMemcpyAsync(m->tab_E, E.data(), E.size() * 8, cudaMemcpyHostToDevice, g_stream));
+    CUDA_TRY(cudaMemcpyAsync(m->tab_s, S.data(), S.size() * 8, cudaMemcpyHostToDevice, g_stream));
+    double wsv[2] = {1e-14 * std::max(electrons->mpw0, neutrals->mpw0), 0.0};             // Interactions.h:129, .cpp:534
+    CUDA_TRY(cudaMemcpyAsync(m->wsv, wsv, 16, cudaMemcpyHostToDevice, g_stream));
+    CUDA_TRY(cudaMemsetAsync(m->stats, 0, 64, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    *out = m;
+    return PICG_OK;
+}
+
+int picg_mcc_destroy(picg_mcc_t m) {
+    if (!m) return PICG_OK;
+    if (g_stream) cudaStreamSynchronize(g_stream);
+    cudaFree(m->tab_E); cudaFree(m->tab_s); cudaFree(m->wsv); cudaFree(m->stats);
+    delete m; return PICG_OK;
+}
+
+int picg_mcc_set_wsv_max(picg_mcc_t m, double v) {
+    REQUIRE_DEVICE(); REQUIRE_ARG(m && v > 0, "picg_mcc_set_wsv_max: bad argument");
+    CUDA_TRY(cudaMemcpyAsync(m->wsv, &v, 8, cudaMemcpyHostToDevice, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return PICG_OK;
+}
+
+int picg_mcc_sigma(picg_mcc_t m, int n, const double* E_eV, double* sc, double* si) {
+    REQUIRE_DEVICE(); REQUIRE_ARG(m && E_eV && sc && si && n >= 0, "picg_mcc_sigma: bad argument");
+    if (n == 0) return PICG_OK;
+    int rc = ensure_scratch(m->w, (size_t)n * 24 + 64); if (rc) return rc;
+    double* d = (double*)m->w->scratch;
+    CUDA_TRY(cudaMemcpyAsync(d, E_eV, (size_t)n * 8, cudaMemcpyHostToDevice, g_stream));
+    LAUNCH(K_MISC, k_sigma_eval, std::min(div_up(n, 256), 1024), 256, 0, make_params(m), n, d, d + n, d + 2 * (size_t)n); CHECK_LAUNCH();
+    CUDA_TRY(cudaMemcpyAsync(sc, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaMemcpyAsync(si, d + 2 * (size_t)n, (size_t)n * 8, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    return PICG_OK;
+}
+
+int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
+    REQUIRE_DEVICE(); REQUIRE_ARG(m, "picg_mcc_apply: null handle");
+    picg_species_s *neu = m->neu, *ele = m->ele, *ion = m->ion;
+    int rc;
+    // both collision partners must be exactly cell-sorted, as in the reference (:602-613)
+    if (!neu->sorted_valid) { rc = sort_species(neu); if (rc) return rc; }
+    if (!ele->sorted_valid) { rc = sort_species(ele); if (rc) return rc; }
+    MccParams P = make_params(m);
+    const Grid& g = m->w->g;
+    // capacity for the appends: one pass over the cells gives the total number of candidates
+    CUDA_TRY(cudaMemsetAsync(m->stats, 0, 64, g_stream));
+    int cgrid = std::max(1, std::min(div_up(g.nc, 256), g_sm_count * 8));
+    LAUNCH(K_MCC, k_mcc_count, cgrid, 256, 0, g, neu->cell_start, ele->cell_start, m->wsv, dt, P.inv_dv, P.rank_scale, m->stats + 4); CHECK_LAUNCH();
+    u64 host_stats[8];
+    CUDA_TRY(cudaMemcpyAsync(host_stats, m->stats, 64, cudaMemcpyDeviceToHost, g_stream));
+    rc = species_refresh_count(neu); if (rc) return rc;        // synchronises
+    rc = species_refresh_count(ele); if (rc) return rc;
+    rc = species_refresh_count(ion); if (rc) return rc;
+    size_t bound = (size_t)host_stats[4];
+    if (bound) {
+        rc = species_ensure_capacity(neu, neu->n_host + bound); if (rc) return rc;
+        rc = species_ensure_capacity(ele, ele->n_host + bound); if (rc) return rc;
+        rc = species_ensure_capacity(ion, ion->n_host + bound); if (rc) return rc;
+        double zero = 0; CUDA_TRY(cudaMemcpyAsync(m->wsv + 1, &zero, 8, cudaMemcpyHostToDevice, g_stream));
+        m->step++;
+        int grid = std::max(1, std::min(div_up(g.nc, 128), g_sm_count * 16));
+        LAUNCH(K_MCC, k_mcc, grid, 128, 0, g, P, store_of(neu), store_of(ele), store_of(ion), neu->cell_start, ele->cell_start, m->wsv, m->stats, dt,
+               g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
+        CHECK_LAUNCH();
+        LAUNCH(K_MCC, k_mcc_finish, 1, 1, 0, m->wsv, m->stats); CHECK_LAUNCH();
+        CUDA_TRY(cudaMemcpyAsync(host_stats, m->stats, 64, cudaMemcpyDeviceToHost, g_stream));
+        for (picg_species_s* s : {neu, ele, ion}) { s->n_host_valid = false; s->n_upper = s->cap; }
+        rc = species_refresh_count(neu); if (rc) return rc;
+        rc = species_refresh_count(ele); if (rc) return rc;
+        rc = species_refresh_count(ion); if (rc) return rc;
+        if (host_stats[1]) { neu->sorted_valid = false; ele->sorted_valid = false; ion->sorted_valid = false; }   // :751-754
+    } else {
+        m->step++;
+        host_stats[0] = host_stats[1] = host_stats[2] = 0;
+    }
+    if (out) {
+        out->candidates = host_stats[0]; out->collisions = host_stats[1]; out->ionizations = host_stats[2];
+        double wmax; CUDA_TRY(cudaMemcpyAsync(&wmax, m->wsv, 8, cudaMemcpyDeviceToHost, g_stream)); CUDA_TRY(cudaStreamSynchronize(g_stream));
+        out->w_sigma_v_max = wmax;
+    }
+    return PICG_OK;
+}
+
+}  // extern "C"

@@ -138,6 +138,18 @@ int species_ensure_capacity(picg_species_s* s, size_t cap) {
 
 static SoA soa_of(picg_species_s* s) { SoA r; for (int c = 0; c < 7; c++) r.a[c] = s->a[c]; return r; }
 
+namespace picg {
+// addParticle for n candidates already staged on the device (AoS).  Capacity must have been ensured.
+int species_add_staged(picg_species_s* s, size_t n, const double* d_aos) {
+    double q_over_m = s->charge / s->mass, half_dt = 0.5 * s->w->dt;
+    LAUNCH(K_ADD_PARTICLES, k_add_particles, std::max(1, std::min(div_up(n, 256), g_sm_count * 8)), 256, 0, s->w->g, n, d_aos,
+           soa_of(s), s->cap, s->ctr, s->w->ef, q_over_m, half_dt);
+    CHECK_LAUNCH();
+    s->n_host_valid = false; s->n_upper = std::min(s->cap, s->n_upper + n); s->sorted_valid = false;
+    return PICG_OK;
+}
+}
+
 extern "C" {
 
 int picg_species_create(picg_world_t w, double mass, double charge, double mpw0, picg_species_t* out) {
@@ -146,6 +158,7 @@ int picg_species_create(picg_world_t w, double mass, double charge, double mpw0,
     REQUIRE_ARG(mass > 0 && mpw0 > 0, "picg_species_create: mass and mpw0 must be positive");
     picg_species_s* s = new picg_species_s();
     s->w = w; s->mass = mass; s->charge = charge; s->mpw0 = mpw0;
+    static uint32_t next_id = 0; s->id = next_id++;
     size_t nv = w->g.nv, nc = w->g.nc;
     cudaError_t e;
     double** nodef[] = {&s->den, &s->den_avg, &s->T, &s->n_sum, &s->nuu, &s->nvv, &s->nww};

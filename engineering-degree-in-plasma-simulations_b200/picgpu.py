@@ -223,6 +223,11 @@ class Species:
         _chk(lib().picg_species_add_particles(self.h, C.c_size_t(a.shape[0]), _dp(a), C.byref(acc)))
         return acc.value
 
+    def loadParticleBoxThermal(self, x0, sides, num_den, T):
+        n = C.c_size_t(0)
+        _chk(lib().picg_species_load_box_thermal(self.h, _d3(x0), _d3(sides), C.c_double(num_den), C.c_double(T), C.byref(n)))
+        return n.value
+
     def advanceElectrons(self, dt):
         _chk(lib().picg_species_push_electrons(self.h, C.c_double(dt)))
 

@@ -110,6 +110,10 @@ PICG_API int picg_species_download(picg_species_t s, size_t capacity, double* ao
 /* Species::addParticle(pos,vel,mpw)  Species.cpp:420-434: reject NaN / out of bounds / in object, then
  * vel -= charge/mass*E(pos)*(0.5*world.dt).  n particles at once; *accepted returns how many were kept. */
 PICG_API int picg_species_add_particles(picg_species_t s, size_t n, const double* aos7, size_t* accepted);
+/* Species::loadParticleBoxThermal(x0, sides, num_den, T)  Species.cpp:560-598, generated on the device:
+ * (size_t)(num_den*volume/mpw0) particles uniform in the box centred at x0, velocities by sampleV3th(T) (:855-869),
+ * each passed through addParticle.  With picg_set_rank(r, G) every rank loads its 1/G share. */
+PICG_API int picg_species_load_box_thermal(picg_species_t s, const double centre[3], const double sides[3], double num_den, double T, size_t* loaded);
 /* Species::advanceElectrons(dt)  Species.cpp:258-399 (gather, kick, drift, absorb on walls/objects, remove) */
 PICG_API int picg_species_push_electrons(picg_species_t s, double dt);
 /* Species::advanceNonElectron(neutrals, spherium, dt)  Species.cpp:47-256 */

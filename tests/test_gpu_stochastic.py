@@ -1,0 +1,218 @@
+"""Stochastic device kernels (Philox streams) against the compiled reference (mt19937): ensemble statistics.
+
+north_star: "Stochastic DSMC ionization must match the reference's ionization-rate and density moments within
+stated ensemble confidence intervals."  Both sides run N_SEEDS independent seeds on identical inputs; for every
+observable the two ensemble means must agree within CI_SIGMA combined standard errors (two-sample z test,
+CI_SIGMA = 4.5 => false-alarm probability < 1e-5 per observable).
+Deterministic sub-cases (no RNG involved) are compared exactly.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = [pytest.mark.gpu, pytest.mark.reference]
+
+N_SEEDS = 32
+CI_SIGMA = 4.5
+
+
+def _agree(a, b, name, rel_floor=1e-9):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+    diff = abs(a.mean() - b.mean())
+    assert diff <= CI_SIGMA * se + rel_floor * abs(b.mean()), f"{name}: gpu {a.mean():.6g} vs ref {b.mean():.6g}, diff {diff:.3g} > {CI_SIGMA} * {se:.3g}"
+
+
+def _mcc_case(seed):
+    ni, nj, nk = 7, 7, 9
+    x0, xm, rects = util.discharge_geometry(ni, nj, nk)
+    rng = np.random.default_rng(1000 + seed)
+    neu = util.random_particles(6000, x0, xm, seed=2000 + seed, vth=600.0, mpw=(5e11, 5e11), lo_frac=(0, 0, 0.15), hi_frac=(1, 1, 0.85))
+    ele = util.random_particles(3000, x0, xm, seed=3000 + seed, vth=2.5e6, mpw=(100.0, 100.0), lo_frac=(0, 0, 0.15), hi_frac=(1, 1, 0.85))
+    ele[:, 3:6] *= rng.uniform(0.5, 2.0, (len(ele), 1))      # 5..150 eV electrons: both elastic and ionising collisions
+    return (ni, nj, nk, x0, xm, rects), neu, ele
+
+
+def _energy_ev(parts):
+    return 0.5 * util.ME * (parts[:, 3:6] ** 2).sum(1) / util.QE
+
+
+def _run_mcc(mod, is_ref, seed, table, dt, wsv):
+    (ni, nj, nk, x0, xm, rects), neu, ele = _mcc_case(0)          # identical inputs for every seed: only the RNG differs
+    w = util.build_world(mod.World, ni, nj, nk, x0, xm, rects, dt=dt)
+    E_ion = 1313.9 * 1000 / util.NA
+    sn = mod.Species("O", 16 * util.AMU, 0.0, w, 5e11, E_ion)
+    si = mod.Species("O+", 16 * util.AMU, util.QE, w, 100.0)
+    se = mod.Species("e-", util.ME, -util.QE, w, 100.0)
+    sn.setParticles(neu); se.setParticles(ele)
+    if is_ref:
+        mod.seed(seed)
+        m = mod.MC_MEX_Ionization(sn, si, se, w, table)
+    else:
+        mod.seed(seed)
+        E, s = util.momentum_transfer_table()
+        m = mod.MC_MEX_Ionization(sn, si, se, w, E, s)
+    m.setWsvMax(wsv)
+    m.apply(dt)
+    pe, pi_, pn = se.getParticles(), si.getParticles(), sn.getParticles()
+    out = dict(n_ion=len(pi_), n_split=len(pn) - len(neu), n_ele=len(pe) - len(ele),
+               e_mean=_energy_ev(pe).mean(), e_new=_energy_ev(pe[len(ele):]).mean() if len(pe) > len(ele) else 0.0,
+               w_neu=pn[:, 6].sum(), w_ion=pi_[:, 6].sum() if len(pi_) else 0.0, w_ele=pe[:, 6].sum(),
+               ez_mean=pe[:, 5].mean(), ion_z=pi_[:, 2].mean() if len(pi_) else 0.0)
+    for o in (m, sn, si, se, w):
+        o.close()
+    return out
+
+
+def test_mc_ionization_ensemble(picgpu, ref):
+    dt = 1e-10
+    wsv = 5e11 * 8e-20 * 8e6          # a realistic ceiling W*sigma*g for these populations
+    with tempfile.TemporaryDirectory() as d:
+        table = util.write_table(os.path.join(d, "Oxygen_momentum_transfer.txt"))
+        G = [_run_mcc(picgpu, False, s, table, dt, wsv) for s in range(N_SEEDS)]
+        R = [_run_mcc(ref, True, 100 + s, table, dt, wsv) for s in range(N_SEEDS)]
+    assert np.mean([r["n_ion"] for r in R]) > 20 and np.mean([r["n_split"] for r in R]) > 20     # the case exercises both branches
+    for key in ("n_ion", "n_split", "n_ele", "e_mean", "e_new", "w_ion", "ez_mean", "ion_z"):
+        _agree([g[key] for g in G], [r[key] for r in R], key)
+    # exact invariants on every run: weight moved from neutrals to ions only by ionisation; electrons gain what ions gain
+    for g in G:
+        assert g["n_ion"] == g["n_ele"]
+        assert abs(g["w_neu"] + g["w_ion"] - 6000 * 5e11) <= 1e-3
+        assert abs(g["w_ele"] - (3000 * 100.0 + g["w_ion"])) <= 1e-6
+
+
+def test_cross_sections_match_reference(picgpu, ref):
+    x0, xm, rects = util.discharge_geometry(7, 7, 9)
+    E, s = util.momentum_transfer_table()
+    with tempfile.TemporaryDirectory() as d:
+        table = util.write_table(os.path.join(d, "t.txt"))
+        wr = util.build_world(ref.World, 7, 7, 9, x0, xm, rects)
+        wg = util.build_world(picgpu.World, 7, 7, 9, x0, xm, rects)
+        E_ion = 1313.9 * 1000 / util.NA
+        sr = [ref.Species("O", 16 * util.AMU, 0.0, wr, 5e11, E_ion), ref.Species("O+", 16 * util.AMU, util.QE, wr, 100.0), ref.Species("e-", util.ME, -util.QE, wr, 100.0)]
+        sg = [picgpu.Species("O", 16 * util.AMU, 0.0, wg, 5e11, E_ion), picgpu.Species("O+", 16 * util.AMU, util.QE, wg, 100.0), picgpu.Species("e-", util.ME, -util.QE, wg, 100.0)]
+        mr = ref.MC_MEX_Ionization(sr[0], sr[1], sr[2], wr, table)
+        mg = picgpu.MC_MEX_Ionization(sg[0], sg[1], sg[2], wg, E, s)
+    q = np.concatenate([np.logspace(-4, 7, 300), E, [13.6, 13.618, 13.62, 0.0]])
+    sc, si = mg.sigma(q)
+    assert np.array_equal(sc, [mr.sigmaColl(e) for e in q])                  # table lookup + lerp: same bits
+    ref_si = np.array([mr.sigmaIon(e) for e in q])
+    assert np.allclose(si, ref_si, rtol=1e-13, atol=0)                       # log/exp differ by ulps between libm and CUDA
+    # constructor preconditions (Interactions.cpp:479-489) surface as argument errors
+    light = picgpu.Species("O", 16 * util.AMU, 0.0, wg, 50.0, E_ion)
+    with pytest.raises(picgpu.PicgError):
+        picgpu.MC_MEX_Ionization(light, sg[1], sg[2], wg, E, s)
+    noion = picgpu.Species("O", 16 * util.AMU, 0.0, wg, 5e11)
+    with pytest.raises(picgpu.PicgError):
+        picgpu.MC_MEX_Ionization(noion, sg[1], sg[2], wg, E, s)
+    for o in [mr, mg, light, noion] + sr + sg + [wr, wg]:
+        o.close()
+
+
+def _heavy_worlds(picgpu, ref, spheres=()):
+    ni, nj, nk = 11, 9, 13
+    x0, xm, rects = util.discharge_geometry(ni, nj, nk)
+    wr = util.build_world(ref.World, ni, nj, nk, x0, xm, rects, spheres, dt=1e-9)
+    wg = util.build_world(picgpu.World, ni, nj, nk, x0, xm, rects, spheres, dt=1e-9)
+    ef = util.smooth_ef((ni, nj, nk), x0, xm, seed=2, amp=2e5)
+    wr.set(3, ef); wg.upload(picgpu.F_EF, ef)
+    return wr, wg, x0, xm
+
+
+def test_heavy_push_ions_deterministic_part(picgpu, ref):
+    """Ions: kick, drift, absorption on electrodes / sphere / walls involve no RNG (the injected-neutral count
+    int(100/5e11 + rnd()) is 0), so the survivors must match the reference bit for bit."""
+    sph = [((0.0, 0.0, 0.0025), -100.0, 0.0007)]
+    wr, wg, x0, xm = _heavy_worlds(picgpu, ref, sph)
+    parts = util.random_particles(40000, x0, xm, seed=5, vth=4e4, mpw=(100.0, 100.0), lo_frac=(0, 0, 0.1), hi_frac=(1, 1, 0.9))
+    out = []
+    for mod, w in ((ref, wr), (picgpu, wg)):
+        mod.seed(7)
+        neu = mod.Species("O", 16 * util.AMU, 0.0, w, 5e11)
+        ion = mod.Species("O+", 16 * util.AMU, util.QE, w, 100.0)
+        ion.setParticles(parts)
+        for _ in range(3):
+            ion.advanceNonElectron(neu, neu, 2e-8)
+        out.append((ion.getParticles(), neu.getNumParticles()))
+        ion.close(); neu.close()
+    (pr, nr), (pg, ng) = out
+    assert 0 < len(pr) < len(parts) and nr == 0 and ng == 0
+    assert np.array_equal(util.sort_rows(pg), util.sort_rows(pr))
+    wr.close(); wg.close()
+
+
+def test_heavy_push_neutral_reflection_statistics(picgpu, ref):
+    """Neutrals are re-emitted diffusely from surfaces (sampleReflectedVelocity, 11 RNG draws per bounce)."""
+    sph = [((0.0, 0.0, 0.0025), -100.0, 0.0009)]
+    wr, wg, x0, xm = _heavy_worlds(picgpu, ref, sph)
+    parts = util.random_particles(8000, x0, xm, seed=9, vth=900.0, mpw=(5e11, 5e11), lo_frac=(0.1, 0.1, 0.12), hi_frac=(0.9, 0.9, 0.88))
+    dt = 4e-7                                  # ~0.4 mm per step: a good fraction reaches a surface
+    res = {"g": [], "r": []}
+    for tag, mod, w in (("r", ref, wr), ("g", picgpu, wg)):
+        for s in range(N_SEEDS):
+            mod.seed(50 + s + (0 if tag == "g" else 500))
+            neu = mod.Species("O", 16 * util.AMU, 0.0, w, 5e11)
+            neu.setParticles(parts)
+            neu.advanceNonElectron(neu, neu, dt)
+            p = neu.getParticles()
+            moved = ~np.isin(p[:, 3], parts[:, 3])        # velocity changed <=> the particle bounced
+            res[tag].append(dict(n=len(p), n_bounced=int(moved.sum()), speed=np.linalg.norm(p[moved, 3:6], axis=1).mean(),
+                                 ke=(p[:, 3:6] ** 2).sum(), z=p[:, 2].mean(), vz_b=p[moved, 5].mean()))
+            neu.close()
+    assert np.mean([r["n_bounced"] for r in res["r"]]) > 300
+    for key in ("n", "n_bounced", "speed", "ke", "z", "vz_b"):
+        _agree([g[key] for g in res["g"]], [r[key] for r in res["r"]], key)
+    wr.close(); wg.close()
+
+
+def test_sources_statistics(picgpu, ref):
+    ni, nj, nk = 11, 9, 13
+    x0, xm = np.array([-0.1, -0.1, 0.0]), np.array([0.1, 0.1, 0.4])
+    for face, T in (("-z", None), ("+x", 1000.0), ("y+", None)):
+        res = {"g": [], "r": []}
+        for tag, mod in (("r", ref), ("g", picgpu)):
+            w = util.build_world(mod.World, ni, nj, nk, x0, xm, dt=1e-7)
+            sp = mod.Species("O+", 16 * util.AMU, util.QE, w, 2e2)
+            mod.seed(11 if tag == "g" else 12)
+            if tag == "r":
+                src = ref.Source(sp, w, 7000.0, 1e10, face, T)
+            else:
+                src = picgpu.WarmBeamSource(sp, w, 7000.0, 1e10, T, face) if T else picgpu.ColdBeamSource(sp, w, 7000.0, 1e10, face)
+            for _ in range(N_SEEDS):
+                before = sp.getNumParticles()
+                src.sample()
+                p = sp.getParticles()[before:]
+                res[tag].append(dict(n=len(p), x=p[:, 0].mean(), y=p[:, 1].mean(), z=p[:, 2].mean(), u=p[:, 3].mean(), v=p[:, 4].mean(), w=p[:, 5].mean(),
+                                     ke=(p[:, 3:6] ** 2).sum(1).mean(), mpw=p[:, 6].mean()))
+            src.close(); sp.close(); w.close()
+        assert res["r"][0]["n"] > 500
+        for key in res["r"][0]:
+            _agree([g[key] for g in res["g"]], [r[key] for r in res["r"]], f"{face}:{key}", rel_floor=1e-12)
+
+
+def test_thermal_loader_statistics(picgpu, ref):
+    ni, nj, nk = 11, 9, 13
+    x0, xm, rects = util.discharge_geometry(ni, nj, nk)
+    xc = 0.5 * (x0 + xm); L = xm - x0
+    out = {}
+    for tag, mod in (("r", ref), ("g", picgpu)):
+        w = util.build_world(mod.World, ni, nj, nk, x0, xm, rects)
+        sp = mod.Species("e-", util.ME, -util.QE, w, 1e5)
+        mod.seed(3)
+        sp.loadParticleBoxThermal(xc, (L[0], L[1], L[2] * 0.9), 1e16, 3000.0)
+        out[tag] = sp.getParticles()
+        sp.close(); w.close()
+    g, r = out["g"], out["r"]
+    assert abs(len(g) - len(r)) < 5 * np.sqrt(len(r) * 0.2) + 5          # same request, same in-electrode rejection fraction
+    for c in range(6):                                                    # position and velocity moments
+        for f, nm in ((np.mean, "mean"), (np.std, "std")):
+            a, b = f(g[:, c]), f(r[:, c])
+            scale = np.std(r[:, c])
+            assert abs(a - b) < 6 * scale / np.sqrt(len(r)), (c, nm, a, b)
+    sg, sr = np.linalg.norm(g[:, 3:6], axis=1), np.linalg.norm(r[:, 3:6], axis=1)
+    assert abs(sg.mean() - sr.mean()) < 6 * sr.std() / np.sqrt(len(sr))
+    assert np.all(g[:, 6] == 1e5)
