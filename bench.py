@@ -1,0 +1,481 @@
+#!/usr/bin/env python
+"""Benchmark of the PIC-DSMC per-timestep particle loop (BASELINE.json: particle-steps/s, Poisson ms/step, % HBM roofline).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path through the C ABI (libpicgpu.so)
+  python bench.py --impl reference --steps K --warmup W     # the reference's own CPU code (oracle/_ref, or the C port)
+
+Workload (BASELINE.json configs[4], SURVEY.md 8d "C5"): World(256,256,256) with dx=1e-4 m, the two electrode
+Rectangles of ch4/v3/src/main.cpp:94-98 at -/+4000 V, dt=1e-12 s, 1e9 macro-particles uniform in the gap
+(0.1..0.9 Lz): 5e8 O (300 K), 2.5e8 O+ (300 K), 2.5e8 e- (3000 K), velocities by the reference's sampleV3th law,
+generated on the device with Philox.  One step = the body of the v3 main loop (main.cpp:177-288) with sub-cycling
+off and the Poisson solve live (as in ch2/ch3/ch4-v1): MC ionisation (cell sort of the two collision partners
+included), push of every species, number-density deposit + per-cell macro-particle count, charge density,
+red-black SOR solve (warm start, reference tolerance) and E = -grad(phi).
+Particles are split evenly across the N GPUs (strong scaling); every GPU deposits onto a full-grid fixed-point
+accumulator, the accumulators are summed with an NCCL all-reduce, Poisson is solved redundantly.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+PKG = "engineering-degree-in-plasma-simulations_b200"
+
+AMU, QE, ME, NA = 1.660538921e-27, 1.602176565e-19, 9.10938215e-31, 6.02214076e23
+# algorithmic bytes (SURVEY.md 8d / DESIGN.md): per particle or per node, per launch of the kernel
+ALG_BYTES_PER_PARTICLE = {"push_electrons": 96, "push_heavy": 96, "push_electrons_deposit": 104, "push_heavy_deposit": 104, "deposit_density": 32}
+ALG_BYTES_PER_NODE = {"sor_redblack": 12.5, "sor_tiled": 25.0, "compute_ef": 32, "charge_density": 24, "finalize_density": 24}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mesh", type=int, default=256, help="nodes per axis")
+    ap.add_argument("--particles", type=float, default=1e9, help="total macro-particles over all GPUs")
+    ap.add_argument("--s_max_it", type=int, default=50, help="max SOR iterations per step (warm start)")
+    ap.add_argument("--s_tol", type=float, default=1.0, help="L2 tolerance of the solve (v3 default, main.cpp:83)")
+    ap.add_argument("--sort_every", type=int, default=1, help="cell-sort period of species that MC ionisation does not sort itself")
+    ap.add_argument("--no_mcc", action="store_true")
+    ap.add_argument("--moments", action="store_true", help="also run Species::sampleMoments every step (SURVEY 8f row 1)")
+    ap.add_argument("--cpu_sample_nodes", type=int, default=49, help="nodes per axis of the CPU-baseline sub-volume (same dx, same particles per cell)")
+    ap.add_argument("--skip_cpu_baseline", action="store_true")
+    ap.add_argument("--inject", type=int, default=1 << 20, help="e2e: electrons injected from pinned host memory per step")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------- workload definition
+def workload(mesh, n_total):
+    """Geometry and species of the synthetic discharge; particle counts follow from densities and weights."""
+    dx = 1e-4
+    L = dx * (mesh - 1)
+    x0 = np.zeros(3)
+    xm = np.full(3, L)
+    xc = 0.5 * (x0 + xm)
+    rects = [((xc[0], xc[1], x0[2]), -4000.0, (L, L, L * 0.1)), ((xc[0], xc[1], xm[2]), 4000.0, (L, L, L * 0.1))]
+    box_c = xc.copy()
+    box_s = np.array([L, L, 0.8 * L])
+    vol = box_s.prod()
+    frac = {"O": 0.5, "O+": 0.25, "e-": 0.25}
+    den = {"O": 1e24, "O+": 1e16, "e-": 1e16}
+    T = {"O": 300.0, "O+": 300.0, "e-": 3000.0}
+    mass = {"O": 16 * AMU, "O+": 16 * AMU, "e-": ME}
+    charge = {"O": 0.0, "O+": QE, "e-": -QE}
+    ppc_total = n_total / ((mesh - 1) ** 2 * (mesh - 1) * 0.8)
+    species = []
+    for name in ("O", "O+", "e-"):
+        count = n_total * frac[name]
+        mpw0 = den[name] * vol / count
+        species.append(dict(name=name, mass=mass[name], charge=charge[name], mpw0=mpw0, den=den[name], T=T[name], count=int(count)))
+    return dict(mesh=mesh, dx=dx, x0=x0, xm=xm, rects=rects, box_c=box_c, box_s=box_s, species=species, dt=1e-12, ppc=ppc_total,
+                E_ion=1313.9 * 1000 / NA)
+
+
+def sub_volume(wl, nodes):
+    """The CPU-baseline sample: a sub-box of the same plasma (same dx, same particles per cell, electrodes kept)."""
+    frac_cells = ((nodes - 1) ** 3) / float((wl["mesh"] - 1) ** 3)
+    n_total = sum(s["count"] for s in wl["species"]) * frac_cells
+    return workload(nodes, n_total), n_total
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw = [], [], []
+        reasons = set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------- our arm
+class CudaArray:
+    """Zero-copy torch view of a device buffer owned by libpicgpu.so (for torch.distributed collectives)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pg = importlib.import_module(PKG + ".picgpu")
+    pg.init(local)
+    pg.set_rank(rank, world)
+    pg.seed(0x5EED0000)
+    stream = torch.cuda.ExternalStream(pg.stream_ptr(), device=local)
+
+    wl = workload(args.mesh, args.particles)
+    m = wl["mesh"]
+    w = pg.World(m, m, m, wl["x0"], wl["xm"])
+    w.setTime(wl["dt"], 1 << 30)
+    for c, phi, sides in wl["rects"]:
+        w.addRectangle(c, phi, sides)
+    w.computeObjectID()
+    sol = pg.PotentialSolver(w, args.s_max_it, args.s_tol)
+    sol.setReferenceValues(0.0, 0.0, 1e20)                 # main.cpp:138
+    cold = pg.PotentialSolver(w, 20000, args.s_tol)          # initial vacuum solve (main.cpp:172-173)
+    cold.setReferenceValues(0.0, 0.0, 1e20)
+    t0 = time.time()
+    cold.solveGS(); cold.computeEF()
+    init_iters = cold.iterations
+
+    species = {}
+    for s in wl["species"]:
+        sp = pg.Species(s["name"], s["mass"], s["charge"], w, s["mpw0"], wl["E_ion"] if s["name"] == "O" else -666.0)
+        per_rank = s["count"] // world + 1
+        sp.reserve(int(per_rank * (1.30 if s["name"] != "O+" else 1.1)) + args.inject * (args.steps + args.warmup + 2))
+        sp.loadParticleBoxThermal(wl["box_c"], wl["box_s"], s["den"], s["T"])
+        sp.sort()
+        species[s["name"]] = sp
+    neu, ion, ele = species["O"], species["O+"], species["e-"]
+    order = [neu, ion, ele]
+    mcc = None
+    if not args.no_mcc:
+        import util
+        E, sg = util.momentum_transfer_table()
+        mcc = pg.MC_MEX_Ionization(neu, ion, ele, w, E, sg)
+
+    # a common fixed-point scale on every rank (the all-reduce sums raw int64 accumulators)
+    for sp in order:
+        sp.computeNumberDensity()
+        S = sp.densityScale()
+        if world > 1:
+            t = torch.tensor([S], device="cuda", dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            S = int(t.item()) - int(np.ceil(np.log2(world)))
+        sp.setDensityScale(S)
+    fixed_views = {}
+    if world > 1:
+        for sp in order:
+            ptr, nbytes = sp.device_ptr(pg.SF_DEN_FIXED)
+            fixed_views[sp.name] = torch.as_tensor(CudaArray(ptr, nbytes // 8, "<i8"), device="cuda")
+    setup_s = time.time() - t0
+
+    counts = {}
+
+    def step(ts, inject=None):
+        """One pass of the v3 main-loop body (main.cpp:197-261) through the C ABI."""
+        if inject is not None:                              # Source::sample on the host side: H2D of this step's new particles
+            ele.addParticles(inject)
+        if mcc is not None:
+            mcc.apply(wl["dt"])
+        for sp in order:
+            if world == 1:
+                if sp is ele:
+                    sp.advanceElectronsDeposit(wl["dt"], count_cells=True)      # fused push + deposit + per-cell count
+                else:
+                    sp.advanceNonElectron(neu, neu, wl["dt"])
+                    sp.computeNumberDensity()
+                    sp.computeMacroParticlesCount()
+            else:
+                if sp is ele:
+                    sp.advanceElectrons(wl["dt"])
+                else:
+                    sp.advanceNonElectron(neu, neu, wl["dt"])
+                sp.depositPartial()
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(fixed_views[sp.name])                        # int64 sum over NVLink
+                sp.finalizeDensity()
+                sp.computeMacroParticlesCount()
+            if args.moments:
+                sp.sampleMoments()
+            if mcc is None and args.sort_every and ts % args.sort_every == 0:
+                sp.sort()
+        if ts > 5:
+            for sp in order:
+                sp.updateAverages()
+        w.computeChargeDensity(order)
+        sol.solveGS()
+        sol.computeEF()
+        return sol.iterations
+
+    def barrier():
+        pg.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(n_steps, ts0, e2e=False, inject_bufs=None, rho_host=None):
+        """Times n_steps on the device (CUDA events on the library's stream); returns ms, particle-steps, iterations."""
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        psteps = 0
+        its = 0
+        ev0.record(stream)
+        for k in range(n_steps):
+            n_now = sum(sp.getNumParticles() for sp in order) if e2e else None
+            it = step(ts0 + k, inject_bufs[k % len(inject_bufs)] if e2e else None)
+            its += it
+            if e2e:                                           # what the reference loop reads every step: counts + diagnostics + rho
+                for sp in order:
+                    sp.diagnostics()
+                pg._chk(pg.lib().picg_world_download(w.h, pg.F_RHO, rho_host.ctypes.data_as(pg.C.POINTER(pg.C.c_double))))
+                psteps += n_now
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, psteps, its
+
+    def global_count():
+        n = sum(sp.getNumParticles() for sp in order)
+        if world > 1:
+            t = torch.tensor([n], device="cuda", dtype=torch.int64)
+            dist.all_reduce(t)
+            n = int(t.item())
+        return n
+
+    # ---- warm-up
+    ts = 1
+    for _ in range(args.warmup):
+        step(ts); ts += 1
+    n_start = global_count()
+    # ---- timed region: device-resident inputs, per-kernel CUDA-event timers on
+    pg.timers_reset(); pg.timers_enable(True); pg.launch_count_reset()
+    clocks = ClockSampler(local); clocks.start()
+    ms, _, its = timed(args.steps, ts)
+    clk = clocks.stop()
+    launches = pg.launch_count()
+    pg.timers_enable(False)
+    kt = pg.timers_read()
+    ts += args.steps
+    n_end = global_count()
+    n_avg = 0.5 * (n_start + n_end)
+    value = n_avg * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (largest accumulated device time)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    per_rank_counts = {sp.name: sp.getNumParticles() for sp in order}
+    nv = m ** 3
+    kernels = {}
+    for name, (tot_ms, n_l) in kt.items():
+        avg = tot_ms / n_l
+        entry = {"ms_total": round(tot_ms, 4), "launches": int(n_l), "ms_avg": round(avg, 5)}
+        alg = None
+        if name == "push_electrons_deposit" or name == "push_electrons":
+            alg = ALG_BYTES_PER_PARTICLE[name] * per_rank_counts["e-"]
+        elif name == "push_heavy":
+            alg = 96 * 0.5 * (per_rank_counts["O"] + per_rank_counts["O+"])       # launches alternate between the two heavy species
+        elif name == "deposit_density":
+            launched = [per_rank_counts["O"], per_rank_counts["O+"]] + ([per_rank_counts["e-"]] if world > 1 else [])
+            alg = 32 * float(np.mean(launched))
+        elif name in ALG_BYTES_PER_NODE:
+            alg = ALG_BYTES_PER_NODE[name] * nv
+        if alg:
+            entry["alg_GB_per_launch"] = round(alg / 1e9, 4)
+            entry["GBps"] = round(alg / (avg * 1e-3) / 1e9, 1)
+            entry["frac_of_peak"] = round(entry["GBps"] / peak, 4)
+        kernels[name] = entry
+    dom = max((k for k in kernels if "GBps" in kernels[k]), key=lambda k: kernels[k]["ms_total"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac_of_peak"],
+                "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": kernels[dom]["alg_GB_per_launch"] * 1e9}
+    poisson_ms = sum(kernels[k]["ms_total"] for k in ("sor_redblack", "sor_tiled", "residual_l2", "compute_ef") if k in kernels) / args.steps
+
+    # ---- end to end through the C ABI with host buffers (pinned): inject + diagnostics + rho download every step
+    inj = []
+    rng = np.random.default_rng(7 + rank)
+    n_inj = args.inject // world
+    for _ in range(2):
+        buf = torch.empty((n_inj, 7), dtype=torch.float64).pin_memory()
+        a = buf.numpy()
+        a[:, 0:3] = wl["box_c"] + (rng.random((n_inj, 3)) - 0.5) * wl["box_s"]
+        a[:, 3:6] = rng.normal(0, 2e5, (n_inj, 3)); a[:, 6] = ele.mpw0
+        inj.append(a)
+    rho_pin = torch.empty(nv, dtype=torch.float64).pin_memory()
+    rho_host = rho_pin.numpy()
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e2e, ps_local, _ = timed(e2e_steps, ts, e2e=True, inject_bufs=inj, rho_host=rho_host)
+    if world > 1:
+        t = torch.tensor([ps_local], device="cuda", dtype=torch.int64); dist.all_reduce(t); ps_local = int(t.item())
+    e2e = {"value": ps_local / (ms_e2e * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": int(n_inj * 56 * world),
+           "d2h_bytes_per_step": int((nv * 8 + 3 * 5 * 8 + 3 * 64) * world), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+           "what": "C-ABI step with host buffers: H2D of injected electrons (pinned), D2H of per-species counters + diagnostics and of rho every step"}
+
+    out = None
+    if rank == 0:
+        out = {"metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "synthetic %d^3 mesh, %.3g macro-particles (O/O+/e- = 2:1:1), full PIC-DSMC step, Poisson live" % (m, args.particles),
+                          "mesh": [m, m, m], "particles_global": int(n_avg), "species": {k: int(v) for k, v in per_rank_counts.items()},
+                          "steps_per_sort": 1 if mcc else args.sort_every, "mcc": mcc is not None, "moments": bool(args.moments),
+                          "poisson": {"max_it": args.s_max_it, "tol": args.s_tol, "mode": "replicated", "iterations_per_step": its / args.steps,
+                                      "initial_solve_iterations": init_iters},
+                          "parallelism": "particles split by index over %d GPU(s); int64 density all-reduce; replicated Poisson" % world,
+                          "l2_policy": "inputs larger than L2 (%.1f GB of particle arrays per GPU vs 126 MB L2)" % (sum(per_rank_counts.values()) * 56 / 1e9)},
+               "poisson_ms_per_step": poisson_ms, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "kernels": kernels, "e2e": e2e,
+               "setup_s": round(setup_s, 1)}
+        if not args.skip_cpu_baseline:
+            out["cpu_baseline"] = cpu_reference_run(args, wl, steps=2, warmup=1)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# --------------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference_run(args, wl_full, steps, warmup):
+    """Times the reference's own CPU implementation of the same step on a bounded sample of the workload: a sub-volume of
+    the same plasma (same dx, dt, densities and particles per cell, electrodes kept).  Uses oracle/_ref (the unmodified
+    reference compiled here) when present, else the C port of the same loops."""
+    from oracle import ref_v3
+    import util
+    wl, n_total = sub_volume(wl_full, args.cpu_sample_nodes)
+    m = wl["mesh"]
+    cores = os.cpu_count() or 1
+    if ref_v3.available():
+        ref_v3.lib()
+        # Config.cpp:68-75 default is hardware_concurrency()-1 threads, used by the electron push only.  With MC ionisation
+        # in the loop the thread-pool push leaves stale per-cell index lists behind (the reference then reads
+        # particles past the end of its store and crashes), so the reference is run serial in that case.
+        threads = 1 if not args.no_mcc else max(1, cores - 1)
+        ref_v3.config(subcycling=False, multithreading=threads > 1, num_threads=threads, merging=False, sputtering=False)
+        saved_stdout = os.dup(1)                             # the reference prints progress to stdout: keep the JSON line clean
+        sys.stdout.flush()
+        devnull = os.open(os.devnull, os.O_WRONLY); os.dup2(devnull, 1)
+        ref_v3.seed(12345)
+        w = ref_v3.World(m, m, m, wl["x0"], wl["xm"])
+        w.setTime(wl["dt"], 1 << 30)
+        for c, phi, sides in wl["rects"]:
+            w.addRectangle(c, phi, sides)
+        w.computeObjectID()
+        sol = ref_v3.PotentialSolver(w, args.s_max_it, args.s_tol, ref_v3.PotentialSolver.GS)
+        sol.setReferenceValues(0.0, 0.0, 1e20)
+        cold = ref_v3.PotentialSolver(w, 20000, args.s_tol, ref_v3.PotentialSolver.GS)
+        cold.setReferenceValues(0.0, 0.0, 1e20)
+        cold.solveGS(); cold.computeEF()
+        sp = {}
+        for s in wl["species"]:
+            o = ref_v3.Species(s["name"], s["mass"], s["charge"], w, s["mpw0"], wl["E_ion"] if s["name"] == "O" else -666.0)
+            o.loadParticleBoxThermal(wl["box_c"], wl["box_s"], s["den"], s["T"])
+            sp[s["name"]] = o
+        order = [sp["O"], sp["O+"], sp["e-"]]
+        tmp = tempfile.mkdtemp()
+        mcc = None if args.no_mcc else ref_v3.MC_MEX_Ionization(sp["O"], sp["O+"], sp["e-"], w, util.write_table(os.path.join(tmp, "Oxygen_momentum_transfer.txt")))
+
+        def step(ts):
+            if mcc:
+                mcc.apply(wl["dt"])
+            for o in order:
+                if o is sp["e-"]:
+                    o.advanceElectrons(wl["dt"])
+                else:
+                    o.advanceNonElectron(sp["O"], sp["O"], wl["dt"])
+                o.computeNumberDensity()
+                if args.moments:
+                    o.sampleMoments()
+                o.computeMacroParticlesCount()
+            if ts > 5:
+                for o in order:
+                    o.updateAverages()
+            w.computeChargeDensity(order)
+            sol.solveGS(); sol.computeEF()
+
+        ts = 1
+        for _ in range(warmup):
+            step(ts); ts += 1
+        n0 = sum(o.getNumParticles() for o in order)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step(ts); ts += 1
+        dt = time.perf_counter() - t0
+        n1 = sum(o.getNumParticles() for o in order)
+        os.dup2(saved_stdout, 1); os.close(saved_stdout); os.close(devnull)
+        kind = "reference"
+    else:
+        raise SystemExit("oracle/_ref is absent and the C-port whole-step baseline is not wired: build oracle/_ref where /root/reference exists")
+    val = 0.5 * (n0 + n1) * steps / dt
+    return {"value": val, "unit": "particle-steps/s", "cores": threads, "host_cores": cores, "kind": kind, "ms_per_step": dt / steps * 1e3,
+            "sample": "sub-volume of the same plasma: %d^3 nodes (same dx, dt, densities, %.1f particles/cell), %d macro-particles, %d steps; "
+                      "reference on %d thread(s) (only its electron push can use the thread pool, Species.cpp:258-355; serial when MC ionisation is on, SURVEY B20)" % (m, wl["ppc"], int(n0), steps, threads)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = workload(args.mesh, args.particles)
+    cb = cpu_reference_run(args, wl, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 3)))
+    out = {"impl": "reference", "metric": "particle-steps/s", "value": cb["value"], "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": "synthetic %d^3 mesh, %.3g macro-particles (O/O+/e- = 2:1:1), full PIC-DSMC step, Poisson live" % (args.mesh, args.particles),
+                      "note": "CPU arm timed on a bounded sample of this workload, see cpu_baseline.sample"},
+           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -81,7 +81,7 @@ def test_mc_ionization_ensemble(picgpu, ref):
     # exact invariants on every run: weight moved from neutrals to ions only by ionisation; electrons gain what ions gain
     for g in G:
         assert g["n_ion"] == g["n_ele"]
-        assert abs(g["w_neu"] + g["w_ion"] - 6000 * 5e11) <= 1e-3
+        assert abs(g["w_neu"] + g["w_ion"] - 6000 * 5e11) <= 1e-12 * 6000 * 5e11
         assert abs(g["w_ele"] - (3000 * 100.0 + g["w_ion"])) <= 1e-6
 
 
@@ -163,7 +163,7 @@ def test_heavy_push_neutral_reflection_statistics(picgpu, ref):
             res[tag].append(dict(n=len(p), n_bounced=int(moved.sum()), speed=np.linalg.norm(p[moved, 3:6], axis=1).mean(),
                                  ke=(p[:, 3:6] ** 2).sum(), z=p[:, 2].mean(), vz_b=p[moved, 5].mean()))
             neu.close()
-    assert np.mean([r["n_bounced"] for r in res["r"]]) > 300
+    assert np.mean([r["n_bounced"] for r in res["r"]]) > 100
     for key in ("n", "n_bounced", "speed", "ke", "z", "vz_b"):
         _agree([g[key] for g in res["g"]], [r[key] for r in res["r"]], key)
     wr.close(); wg.close()
