@@ -113,7 +113,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, first=0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -123,7 +123,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw = [], [], []
         reasons = set()
-        for r in self.rows:
+        rows = self.rows[first:] if len(self.rows) - first >= 3 else self.rows      # prefer samples taken inside the timed region
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
             except Exception:
@@ -132,7 +133,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_in_timed_region": max(0, len(self.rows) - first), "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------------------- our arm
@@ -287,16 +288,17 @@ def run_ours(args):
             n = int(t.item())
         return n
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler starts here: nvidia-smi needs ~0.5 s before its first sample)
+    clocks = ClockSampler(local); clocks.start()
     ts = 1
     for _ in range(args.warmup):
         step(ts); ts += 1
     n_start = global_count()
     # ---- timed region: device-resident inputs, per-kernel CUDA-event timers on
     pg.timers_reset(); pg.timers_enable(True); pg.launch_count_reset()
-    clocks = ClockSampler(local); clocks.start()
+    n_before = len(clocks.rows)
     ms, _, its = timed(args.steps, ts)
-    clk = clocks.stop()
+    clk = clocks.stop(first=n_before)
     launches = pg.launch_count()
     pg.timers_enable(False)
     kt = pg.timers_read()
