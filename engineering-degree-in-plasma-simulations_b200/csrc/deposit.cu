@@ -1,7 +1,6 @@
 // Number-density deposition (deterministic, fixed point) and the node passes that follow it.
-//   k_deposit        : Species::computeNumberDensity loop     ch4/v3/src/Species.cpp:401-413 + Field::scatter Field.h:157-199
+//   (the particle pass itself -- computeNumberDensity's loop, Species.cpp:401-413 -- is k_step in step.cu)
 //   k_finalize_den   : den /= node_vol (zero-divisor guard)   Species.cpp:415, Field.h:563-583
-//   k_count_cells    : Species::computeMacroParticlesCount    Species.cpp:813-819
 //   k_moments        : Species::sampleMoments                 Species.cpp:767-776
 // Algorithmic bytes per particle: deposit 24 B (pos) + 8 B (mpw) = 32 B.
 #include "common.cuh"
@@ -10,45 +9,6 @@
 #include <cmath>
 
 using namespace picg;
-
-template <bool COUNT>
-__global__ void __launch_bounds__(DEP_THREADS) k_deposit(Grid g, const double* __restrict__ px, const double* __restrict__ py,
-                                                         const double* __restrict__ pz, const double* __restrict__ pm,
-                                                         const SpeciesCounters* ctr, u64* __restrict__ den_fixed, double scale,
-                                                         double* __restrict__ macro_count) {
-    __shared__ i64 win[DEP_WINDOW * 8];
-    __shared__ int s_c0;
-    const u64 n = ctr->n;
-    const int lane = threadIdx.x & 31;
-    for (int t = threadIdx.x; t < DEP_WINDOW * 8; t += blockDim.x) win[t] = 0;
-    for (u64 chunk = (u64)blockIdx.x * DEP_CHUNK; chunk < n; chunk += (u64)gridDim.x * DEP_CHUNK) {
-        if (threadIdx.x == 0) {       // place the window at the chunk's first particle (2 cells of slack below)
-            int i = min((int)x_to_l(px[chunk], g.x0[0], g.inv_dx[0]), g.ci - 1);
-            int j = min((int)x_to_l(py[chunk], g.x0[1], g.inv_dx[1]), g.cj - 1);
-            int k = min((int)x_to_l(pz[chunk], g.x0[2], g.inv_dx[2]), g.ck - 1);
-            s_c0 = cell_of(g, i, j, k) - 2;
-        }
-        __syncthreads();
-        const int c0 = s_c0;
-        const u64 end = min(chunk + DEP_CHUNK, n);
-        for (u64 p0 = chunk + (threadIdx.x - lane); p0 < end; p0 += DEP_THREADS) {
-            u64 p = p0 + lane;
-            bool active = p < end;
-            int cell = -1; i64 q[8];
-            if (active) {
-                int i, j, k;
-                scatter_weights_fixed(g, x_to_l(px[p], g.x0[0], g.inv_dx[0]), x_to_l(py[p], g.x0[1], g.inv_dx[1]),
-                                      x_to_l(pz[p], g.x0[2], g.inv_dx[2]), pm[p], scale, i, j, k, q);
-                cell = cell_of(g, i, j, k);
-                if (COUNT) atomicAdd(&macro_count[cell], 1.0);      // integer-valued: exact, order independent
-            }
-            warp_accumulate(g, active, cell, q, win, c0, den_fixed, lane);
-        }
-        __syncthreads();
-        window_flush(g, win, c0, den_fixed);
-        __syncthreads();
-    }
-}
 
 // den = (fixed * 2^-S) / node_vol, 0 where node_vol == 0; tracks max and overflow (negative) nodes.
 __global__ void __launch_bounds__(256) k_finalize_den(int nv, const i64* __restrict__ fixed, const double* __restrict__ vol,
@@ -68,26 +28,6 @@ __global__ void __launch_bounds__(256) k_finalize_den(int nv, const i64* __restr
     }
 }
 __global__ void k_reset_den_stats(SpeciesCounters* ctr) { ctr->den_max = 0; ctr->den_neg = 0; }
-
-// Species::computeMacroParticlesCount (Species.cpp:813-819): cells in Field order (i*(nj-1)+j)*(nk-1)+k == cell_of()
-__global__ void __launch_bounds__(256) k_count_cells(Grid g, const double* __restrict__ px, const double* __restrict__ py,
-                                                     const double* __restrict__ pz, const SpeciesCounters* ctr, double* __restrict__ macro_count) {
-    const u64 n = ctr->n;
-    const int lane = threadIdx.x & 31;
-    for (u64 p0 = (blockIdx.x * (u64)blockDim.x + threadIdx.x) - lane; p0 < n; p0 += (u64)gridDim.x * blockDim.x) {
-        u64 p = p0 + lane;
-        int cell = -1;
-        if (p < n) {
-            int i = min((int)x_to_l(px[p], g.x0[0], g.inv_dx[0]), g.ci - 1);
-            int j = min((int)x_to_l(py[p], g.x0[1], g.inv_dx[1]), g.cj - 1);
-            int k = min((int)x_to_l(pz[p], g.x0[2], g.inv_dx[2]), g.ck - 1);
-            cell = cell_of(g, i, j, k);
-        }
-        // run-length aggregation: sorted particles form runs of equal cells inside the warp
-        unsigned peers = __match_any_sync(0xffffffffu, cell);
-        if (cell >= 0 && lane == __ffs(peers) - 1) atomicAdd(&macro_count[cell], (double)__popc(peers));
-    }
-}
 
 // Species::sampleMoments (Species.cpp:767-776): five scatters per particle (n, n*v (3), n*u^2, n*v^2, n*w^2) with the
 // reference's weights; these diagnostics accumulate in fp64 (order-dependent in the reference as well).
@@ -130,21 +70,8 @@ __global__ void k_gas_properties(int nv, const double* __restrict__ n_sum, const
 }
 
 namespace picg {
-int deposit_grid(size_t n_upper) { return std::max(1, std::min(div_up(std::max<size_t>(n_upper, 1), DEP_CHUNK), g_sm_count * 6)); }
-
+int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals, picg_species_s* spherium, int sputtering, size_t n_snapshot);   // step.cu
 static int pow2_floor_log(i64 v) { int l = -1; while (v > 0) { v >>= 1; l++; } return l; }
-
-int launch_deposit(picg_species_s* s, bool count_cells) {
-    const Grid& g = s->w->g;
-    double scale = std::ldexp(1.0, s->S);
-    cudaMemsetAsync(s->den_fixed, 0, (size_t)g.nv * 8, g_stream);
-    if (count_cells) cudaMemsetAsync(s->macro_count, 0, (size_t)g.nc * 8, g_stream);
-    int grid = deposit_grid(s->n_upper);
-    if (count_cells) LAUNCH(K_DEPOSIT, k_deposit<true>, grid, DEP_THREADS, 0, g, s->a[0], s->a[1], s->a[2], s->a[6], s->ctr, (u64*)s->den_fixed, scale, s->macro_count);
-    else LAUNCH(K_DEPOSIT, k_deposit<false>, grid, DEP_THREADS, 0, g, s->a[0], s->a[1], s->a[2], s->a[6], s->ctr, (u64*)s->den_fixed, scale, s->macro_count);
-    CHECK_LAUNCH();
-    return PICG_OK;
-}
 
 int launch_finalize(picg_species_s* s) {
     const Grid& g = s->w->g;
@@ -168,7 +95,7 @@ int calibrate_scale(picg_species_s* s, bool count_cells) {
         rc = picg_species_diagnostics(s, &total, nullptr, nullptr); if (rc) return rc;
         int e = 0; if (total > 0) std::frexp(total, &e);          // total < 2^e
         s->S = 61 - e;
-        rc = launch_deposit(s, count_cells); if (rc) return rc;
+        rc = launch_step(s, 4, 0.0, nullptr, nullptr, 0, 0); if (rc) return rc;
         rc = launch_finalize(s); if (rc) return rc;
         s->n_host_valid = false; rc = species_refresh_count(s); if (rc) return rc;   // reads den_max
         i64 mx = s->ctr_host->den_max;
@@ -202,36 +129,9 @@ int picg_species_set_density_scale(picg_species_t s, int S) {
 }
 int picg_species_density_scale(picg_species_t s, int* S) { REQUIRE_ARG(s && S, "picg_species_density_scale: null argument"); *S = s->S; return PICG_OK; }
 
-int picg_species_deposit_density_partial(picg_species_t s) {
-    REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_species_deposit_density_partial: null species");
-    REQUIRE_ARG(s->S_pinned, "picg_species_deposit_density_partial: pin a common scale with picg_species_set_density_scale first (all ranks must share S)");
-    return launch_deposit(s, false);
-}
 int picg_species_finalize_density(picg_species_t s) {
     REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_species_finalize_density: null species");
     return launch_finalize(s);
-}
-
-int picg_species_deposit_density(picg_species_t s) {
-    REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_species_deposit_density: null species");
-    int rc = calibrate_scale(s, false); if (rc < 0) return rc;
-    rc = launch_deposit(s, false); if (rc) return rc;
-    rc = launch_finalize(s); if (rc) return rc;
-    if (s->S_pinned) return PICG_OK;          // overflow is then reported by the next count refresh
-    // automatic scale: read back max / overflow counters (one small synchronising copy per deposit)
-    s->n_host_valid = false;
-    rc = species_refresh_count(s); if (rc) return rc;
-    return check_scale_after(s);
-}
-
-int picg_species_count_per_cell(picg_species_t s) {
-    REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_species_count_per_cell: null species");
-    const Grid& g = s->w->g;
-    cudaMemsetAsync(s->macro_count, 0, (size_t)g.nc * 8, g_stream);
-    LAUNCH(K_COUNT_CELLS, k_count_cells, std::max(1, std::min(div_up(std::max<size_t>(s->n_upper, 1), 256), g_sm_count * 8)), 256, 0,
-           g, s->a[0], s->a[1], s->a[2], s->ctr, s->macro_count);
-    CHECK_LAUNCH();
-    return PICG_OK;
 }
 
 int picg_species_sample_moments(picg_species_t s) {

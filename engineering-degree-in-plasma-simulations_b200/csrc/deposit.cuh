@@ -5,17 +5,14 @@
 // associative, so ANY aggregation order (warp shuffles, shared-memory staging, global atomics,
 // NCCL all-reduce across GPUs) yields the same bits.
 //
-// Staging: a block owns a contiguous chunk of the (cell-sorted) particle array and a shared-memory
-// window of DEP_WINDOW consecutive cells x 8 corner accumulators.  Within a warp, lanes that fall in
-// the same cell are first combined with a transposed butterfly (9 64-bit shuffles for all eight
-// corners instead of 40), then one lane per corner issues the atomic: to shared memory when the
+// Staging (used by step.cu): a block owns a contiguous chunk of the (cell-sorted) particle array and a
+// shared-memory window of WINDOW consecutive cells x 8 corner accumulators.  Lanes of a warp whose run
+// totals fall in the same cell are first combined with a transposed butterfly (9 64-bit shuffles for all
+// eight corners instead of 40), then one lane per corner issues the atomic: to shared memory when the
 // cell is inside the window, straight to global memory otherwise (unsorted / straggler particles).
 #pragma once
 #include "common.cuh"
 
-#define DEP_WINDOW 512            // cells per block window  (512*8*8 B = 32 KB shared)
-#define DEP_THREADS 256
-#define DEP_CHUNK 4096            // particles per block chunk
 
 #ifdef __CUDACC__
 // node index of corner c (0..7: dk = c&1, dj = (c>>1)&1, di = c>>2) of the cell whose low node is (i,j,k)
@@ -28,8 +25,9 @@ __device__ __forceinline__ void cell_to_ijk(const Grid& g, int cell, int& i, int
 
 // Adds the warp's contributions.  `active` lanes carry (cell, q[8]); all 32 lanes must call.
 // win: shared window accumulators [DEP_WINDOW*8], c0: first cell of the window.
-__device__ __forceinline__ void warp_accumulate(const Grid& g, bool active, int cell, const i64 q[8], i64* win, int c0,
-                                                u64* __restrict__ den_fixed, int lane) {
+template <int WINDOW>
+__device__ __forceinline__ void warp_accumulate_w(const Grid& g, bool active, int cell, const i64 q[8], i64* win, int c0,
+                                                  u64* __restrict__ den_fixed, int lane) {
     unsigned todo = __ballot_sync(0xffffffffu, active);
     while (todo) {
         int leader = __ffs(todo) - 1;
@@ -38,7 +36,7 @@ __device__ __forceinline__ void warp_accumulate(const Grid& g, bool active, int 
         unsigned m = __ballot_sync(0xffffffffu, mine);
         todo &= ~m;
         int rel = lcell - c0;
-        bool in_win = rel >= 0 && rel < DEP_WINDOW;
+        bool in_win = rel >= 0 && rel < WINDOW;
         if (__popc(m) >= 3) {
             // transposed butterfly: after the three halving steps lane L holds corner (L>>2)'s partial
             // sum over 8 lanes; two more plain steps finish it.
@@ -74,15 +72,4 @@ __device__ __forceinline__ void warp_accumulate(const Grid& g, bool active, int 
     }
 }
 
-// Flush the non-zero window accumulators to the global fixed-point grid and clear them.
-__device__ __forceinline__ void window_flush(const Grid& g, i64* win, int c0, u64* __restrict__ den_fixed) {
-    for (int slot = threadIdx.x; slot < DEP_WINDOW * 8; slot += blockDim.x) {
-        i64 v = win[slot];
-        if (v != 0) {
-            int i, j, k; cell_to_ijk(g, c0 + (slot >> 3), i, j, k);
-            atomicAdd(&den_fixed[corner_node(g, i, j, k, slot & 7)], (u64)v);
-            win[slot] = 0;
-        }
-    }
-}
 #endif

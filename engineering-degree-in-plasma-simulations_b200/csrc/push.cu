@@ -1,5 +1,5 @@
 // Particle push kernels + in-place removal of dead particles.
-//   k_push_electrons : Species::advanceElectronsSerial           ch4/v3/src/Species.cpp:356-399
+//   (the electron / heavy pushes are k_step in step.cu)
 //   k_push_reflect   : ch2 Species::advance (specular walls)     ch2/v2/Species.cpp:18-55
 //   compaction       : the swap-with-last removal :378-398 done as hole filling: survivors from the
 //                      tail [n_alive,n) move into the holes left below n_alive, so the traffic is
@@ -10,25 +10,6 @@
 #include <algorithm>
 
 using namespace picg;
-
-// ---------------------------------------------------------------- electron push
-__global__ void __launch_bounds__(256) k_push_electrons(Grid g, PushArrays s, SpeciesCounters* ctr, const double* __restrict__ ef,
-                                                        double qm_dt, double dt, unsigned* __restrict__ dead_list) {
-    const u64 n = ctr->n;
-    const int lane = threadIdx.x & 31;
-    // every warp walks whole 32-particle groups so that the ballots below are convergent
-    for (u64 p0 = (blockIdx.x * (u64)blockDim.x + threadIdx.x) - lane; p0 < n; p0 += (u64)gridDim.x * blockDim.x) {
-        u64 p = p0 + lane;
-        bool dead = false;
-        if (p < n) {
-            double x = s.x[p], y = s.y[p], z = s.z[p], u = s.u[p], v = s.v[p], w = s.w[p];
-            push_kick_drift(g, ef, qm_dt, dt, x, y, z, u, v, w);
-            dead = !in_bounds(g, x, y, z) || in_object(g, x, y, z) != 0;          // Species.cpp:375-388
-            if (!dead) { s.x[p] = x; s.y[p] = y; s.z[p] = z; s.u[p] = u; s.v[p] = v; s.w[p] = w; }
-        }
-        record_dead(dead, lane, p, ctr, dead_list);
-    }
-}
 
 // ---------------------------------------------------------------- ch2 reflective push
 __global__ void __launch_bounds__(256) k_push_reflect(Grid g, PushArrays s, const SpeciesCounters* ctr, const double* __restrict__ ef,
@@ -103,18 +84,6 @@ int push_grid(size_t n_upper) { return std::max(1, std::min(div_up(std::max<size
 }  // namespace picg
 
 extern "C" {
-
-int picg_species_push_electrons(picg_species_t s, double dt) {
-    REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_species_push_electrons: null species");
-    size_t cap = std::max<size_t>(s->n_upper, 1);
-    REQUIRE_ARG(cap < 0xffffffffull, "picg_species_push_electrons: more than 2^32-1 particles per GPU are not supported");
-    int rc = ensure_scratch(s->w, compact_scratch_bytes(cap)); if (rc) return rc;
-    double qm_dt = dt * s->charge / s->mass;                                       // Species.cpp:372 `dt*charge/mass`
-    PushArrays a = {s->a[0], s->a[1], s->a[2], s->a[3], s->a[4], s->a[5]};
-    LAUNCH(K_PUSH_ELECTRONS, k_push_electrons, push_grid(cap), 256, 0, s->w->g, a, s->ctr, s->w->ef, qm_dt, dt, (unsigned*)s->w->scratch);
-    CHECK_LAUNCH();
-    return compact_dead(s, cap);
-}
 
 int picg_species_push_reflect(picg_species_t s, double dt) {
     REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_species_push_reflect: null species");

@@ -240,6 +240,13 @@ class Species:
     def advanceElectronsDeposit(self, dt, count_cells=False):
         _chk(lib().picg_species_push_electrons_deposit(self.h, C.c_double(dt), int(count_cells)))
 
+    def advanceNonElectronDeposit(self, neutrals, spherium, dt, sputtering=False, count_cells=False):
+        _chk(lib().picg_species_push_heavy_deposit(self.h, neutrals.h, spherium.h, C.c_double(dt), int(sputtering), int(count_cells)))
+
+    def advanceDepositPartial(self, dt, neutrals=None, spherium=None, heavy=False, sputtering=False, count_cells=False):
+        _chk(lib().picg_species_push_deposit_partial(self.h, neutrals.h if neutrals else None, spherium.h if spherium else None, C.c_double(dt),
+                                                     int(heavy), int(sputtering), int(count_cells)))
+
     def computeNumberDensity(self):
         _chk(lib().picg_species_deposit_density(self.h))
 

@@ -126,6 +126,11 @@ PICG_API int picg_species_push_reflect(picg_species_t s, double dt);
 PICG_API int picg_species_deposit_density(picg_species_t s);
 /* fused Species::advanceElectrons + computeNumberDensity (+ computeMacroParticlesCount): one pass over the particles */
 PICG_API int picg_species_push_electrons_deposit(picg_species_t s, double dt, int count_cells);
+/* fused Species::advanceNonElectron + computeNumberDensity (+ computeMacroParticlesCount) */
+PICG_API int picg_species_push_heavy_deposit(picg_species_t s, picg_species_t neutrals, picg_species_t spherium, double dt, int sputtering, int count_cells);
+/* multi-GPU: fused push + deposit into the raw int64 accumulator only (scale pinned on every rank); all-reduce
+ * PICG_SF_DEN_FIXED across ranks, then picg_species_finalize_density.  heavy != 0 selects advanceNonElectron. */
+PICG_API int picg_species_push_deposit_partial(picg_species_t s, picg_species_t neutrals, picg_species_t spherium, double dt, int heavy, int sputtering, int count_cells);
 PICG_API int picg_species_density_scale(picg_species_t s, int* S);           /* the S of the last deposit */
 PICG_API int picg_species_set_density_scale(picg_species_t s, int S);        /* pin S (tests); <-1000 = automatic */
 /* Species::sampleMoments :767-776, computeGasProperties :777-804, clearSamples :805-812 */

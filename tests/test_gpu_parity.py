@@ -173,6 +173,35 @@ def test_fused_push_deposit_equals_separate(picgpu, orc):
     a.close(); b.close(); w.close()
 
 
+def test_fused_heavy_push_deposit_equals_separate(picgpu, orc):
+    sph = [((0.0, 0.0, 0.0025), -100.0, 0.0007)]
+    w, g, x0, xm = _setup(picgpu, orc, spheres=sph, dt=1e-9)
+    ef = util.smooth_ef((w.ni, w.nj, w.nk), x0, xm, seed=3, amp=2e5)
+    w.upload(picgpu.F_EF, ef)
+    parts = util.random_particles(90000, x0, xm, seed=23, vth=4e4, mpw=(100.0, 100.0), lo_frac=(0, 0, 0.1), hi_frac=(1, 1, 0.9))
+    neu = picgpu.Species("O", 16 * util.AMU, 0.0, w, 5e11)
+    a = picgpu.Species("O+", 16 * util.AMU, util.QE, w, 100.0)
+    b = picgpu.Species("O+", 16 * util.AMU, util.QE, w, 100.0)
+    for sp in (a, b):
+        sp.setParticles(parts); sp.sort(); sp.setDensityScale(30)
+    a.advanceNonElectron(neu, neu, 2e-8); a.computeNumberDensity(); a.computeMacroParticlesCount()
+    b.advanceNonElectronDeposit(neu, neu, 2e-8, count_cells=True)
+    assert 0 < a.getNumParticles() < len(parts) and a.getNumParticles() == b.getNumParticles()
+    assert np.array_equal(a.den_fixed, b.den_fixed)
+    assert np.array_equal(a.macro_part_count, b.macro_part_count)
+    assert np.array_equal(util.sort_rows(a.getParticles()), util.sort_rows(b.getParticles()))
+    assert np.array_equal(a.den_fixed, g.deposit_fixed(a.getParticles(), 30))
+    # partial (multi-GPU) path: raw accumulator, finalised separately
+    c = picgpu.Species("O+", 16 * util.AMU, util.QE, w, 100.0)
+    c.setParticles(parts); c.sort(); c.setDensityScale(30)
+    c.advanceDepositPartial(2e-8, neu, neu, heavy=True)
+    assert np.array_equal(c.den_fixed, a.den_fixed)
+    c.finalizeDensity()
+    assert np.array_equal(c.den, a.den)
+    for o in (a, b, c, neu, w):
+        o.close()
+
+
 def test_count_per_cell_and_sort(picgpu, orc):
     w, g, x0, xm = _setup(picgpu, orc)
     parts = util.random_particles(123457, x0, xm, seed=8)
