@@ -74,7 +74,8 @@ struct picg_species_s {
     // cell-sorted layout
     unsigned* cell_start = nullptr;    // nc+1 entries, valid when sorted_valid
     bool sorted_valid = false;         // cell_start describes the current particle order exactly
-    size_t sorted_n = 0;               // particle count covered by cell_start
+    bool part_valid = false;           // cell_start is a partition of [0, part_n) (possibly stale: particles may have drifted)
+    size_t part_n = 0;                 // upper bound of the particle count at the last sort
 };
 
 struct picg_solver_s {

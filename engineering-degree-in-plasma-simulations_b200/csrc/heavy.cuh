@@ -1,0 +1,56 @@
+// Surface interaction of the heavy-species push (ions / neutrals hitting an object), shared by step.cu and cellstep.cu.
+//   Species::advanceNoSputteringSerial / advanceSputteringSerial   ch4/v3/src/Species.cpp:213-238, :136-145
+#pragma once
+#include "common.cuh"
+#include "samplers.cuh"
+
+struct Emit { double* a[7]; SpeciesCounters* ctr; u64 cap; double mpw0, q_over_m; };
+struct HeavyArgs { Emit neutrals, spherium; int sputtering; double charge, mass, half_world_dt; uint64_t seed; uint32_t stream, call; };
+
+#ifdef __CUDACC__
+// Species::addParticle(pos, vel) for one particle created on a surface (Species.cpp:420-437)
+static __device__ __noinline__ void emit_particle(const Grid& g, const Emit& e, const double* __restrict__ ef, double half_dt, const double pos[3], const double v[3]) {
+    if (isnan(pos[0]) || isnan(pos[1]) || isnan(pos[2]) || isnan(v[0]) || isnan(v[1]) || isnan(v[2])) return;
+    if (!in_bounds(g, pos[0], pos[1], pos[2]) || in_object(g, pos[0], pos[1], pos[2])) return;
+    double ex, ey, ez;
+    gather_ef(g, ef, x_to_l(pos[0], g.x0[0], g.inv_dx[0]), x_to_l(pos[1], g.x0[1], g.inv_dx[1]), x_to_l(pos[2], g.x0[2], g.inv_dx[2]), ex, ey, ez);
+    double u = __dsub_rn(v[0], __dmul_rn(__dmul_rn(ex, e.q_over_m), half_dt));
+    double vv = __dsub_rn(v[1], __dmul_rn(__dmul_rn(ey, e.q_over_m), half_dt));
+    double w = __dsub_rn(v[2], __dmul_rn(__dmul_rn(ez, e.q_over_m), half_dt));
+    u64 dst = atomicAdd(&e.ctr->n, 1ull);
+    if (dst >= e.cap) { atomicAdd(&e.ctr->overflow, 1ull); return; }
+    e.a[0][dst] = pos[0]; e.a[1][dst] = pos[1]; e.a[2][dst] = pos[2]; e.a[3][dst] = u; e.a[4][dst] = vv; e.a[5][dst] = w; e.a[6][dst] = e.mpw0;
+}
+
+// The part of the heavy push that follows an impact (Species.cpp:213-238): rare, kept out of line.
+// Returns true when the particle is absorbed; otherwise x, v, t_rem are updated for the next sub-move.
+static __device__ __noinline__ bool surface_interaction(const Grid& g, const HeavyArgs& h, const double* __restrict__ ef, PhiloxStream& r, int obj,
+                                                 const double old[3], double x[3], double v[3], double mpw, double& t_rem) {
+    double tp, hit[3], nrm[3];
+    const ObjShape& o = g.obj[obj - 1];
+    if (o.type == 0) rect_line_intersect(o, old, x, &tp, hit, nrm); else sphere_line_intersect(o, old, x, &tp, hit, nrm);
+    x[0] = hit[0]; x[1] = hit[1]; x[2] = hit[2];
+    double v_mag = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (h.charge == 0) {                                                    // neutrals: diffuse re-emission
+        double nv[3]; sample_reflected(r, v_mag, nrm, h.mass, nv);
+        v[0] = nv[0]; v[1] = nv[1]; v[2] = nv[2];
+        t_rem *= (1 - tp);
+        return false;
+    }
+    int mp_create = (int)(mpw / h.neutrals.mpw0 + r.next());                // ions: neutralise on the surface (:225-232)
+    for (int c = 0; c < mp_create; c++) { double nv[3]; sample_reflected(r, v_mag, nrm, h.mass, nv); emit_particle(g, h.neutrals, ef, h.half_world_dt, x, nv); }
+    if (h.sputtering) {                                                     // :136-145
+        double yield = (v_mag > 5e3) ? 0.1 : 0;
+        int sp_create = (int)(yield * mpw / h.spherium.mpw0 + r.next());
+        for (int c = 0; c < sp_create; c++) { double nv[3]; sample_reflected(r, v_mag, nrm, h.mass, nv); emit_particle(g, h.spherium, ef, h.half_world_dt, x, nv); }
+    }
+    return true;
+}
+
+#endif
+
+static inline Emit emit_of(picg_species_s* t) {
+    Emit e; for (int c = 0; c < 7; c++) e.a[c] = t->a[c];
+    e.ctr = t->ctr; e.cap = t->cap; e.mpw0 = t->mpw0; e.q_over_m = t->charge / t->mass;
+    return e;
+}

@@ -179,7 +179,7 @@ int sort_species(picg_species_s* s) {
         std::swap(s->a[c], s->spare);
     }
     LAUNCH(K_CELL_START, k_cell_start, pgrid, 256, 0, s->ctr, keysA, g.nc, s->cell_start); CHECK_LAUNCH();
-    s->sorted_valid = true;
+    s->sorted_valid = true; s->part_valid = true; s->part_n = cap;
     return PICG_OK;
 }
 }  // namespace picg

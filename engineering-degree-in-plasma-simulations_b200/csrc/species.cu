@@ -220,7 +220,7 @@ int picg_species_upload(picg_species_t s, size_t n, const double* aos7) {
     *s->ctr_host = z;
     CUDA_TRY(cudaMemcpyAsync(s->ctr, s->ctr_host, sizeof(z), cudaMemcpyHostToDevice, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));
-    s->n_host = n; s->n_host_valid = true; s->n_upper = n; s->sorted_valid = false;
+    s->n_host = n; s->n_host_valid = true; s->n_upper = n; s->sorted_valid = false; s->part_valid = false;
     return PICG_OK;
 }
 

@@ -24,6 +24,7 @@
 #include "push.cuh"
 #include "deposit.cuh"
 #include "samplers.cuh"
+#include "heavy.cuh"
 #include <algorithm>
 #include <cmath>
 
@@ -35,54 +36,14 @@ using namespace picg;
 #define STEP_PITCH (STEP_CHUNK + STEP_CHUNK / STEP_RUN)      // one pad double per run: conflict-free run-wise reads
 #define STEP_WINDOW 256                                      // cells staged in shared memory (x 8 corners x 8 B = 16 KB)
 
-struct Emit { double* a[7]; SpeciesCounters* ctr; u64 cap; double mpw0, q_over_m; };
-struct HeavyArgs { Emit neutrals, spherium; int sputtering; double charge, mass, half_world_dt; uint64_t seed; uint32_t stream, call; };
 struct StepArgs {
     double* a[7]; SpeciesCounters* ctr; u64 n_fixed; int use_fixed_n;      // heavy pushes walk a snapshot of the count (Species.cpp:176)
+    const unsigned* tail_from;                                              // non-null: only particles [*tail_from, n) (the part beyond the cell partition)
     const double* ef; double qm_dt, dt;
     unsigned* dead_list; u64* den_fixed; double scale; double* macro_count;
 };
 
 __device__ __forceinline__ int spos(int i) { return i + (i / STEP_RUN); }
-
-// Species::addParticle(pos, vel) for one particle created on a surface (Species.cpp:420-437)
-__device__ __noinline__ void emit_particle(const Grid& g, const Emit& e, const double* __restrict__ ef, double half_dt, const double pos[3], const double v[3]) {
-    if (isnan(pos[0]) || isnan(pos[1]) || isnan(pos[2]) || isnan(v[0]) || isnan(v[1]) || isnan(v[2])) return;
-    if (!in_bounds(g, pos[0], pos[1], pos[2]) || in_object(g, pos[0], pos[1], pos[2])) return;
-    double ex, ey, ez;
-    gather_ef(g, ef, x_to_l(pos[0], g.x0[0], g.inv_dx[0]), x_to_l(pos[1], g.x0[1], g.inv_dx[1]), x_to_l(pos[2], g.x0[2], g.inv_dx[2]), ex, ey, ez);
-    double u = __dsub_rn(v[0], __dmul_rn(__dmul_rn(ex, e.q_over_m), half_dt));
-    double vv = __dsub_rn(v[1], __dmul_rn(__dmul_rn(ey, e.q_over_m), half_dt));
-    double w = __dsub_rn(v[2], __dmul_rn(__dmul_rn(ez, e.q_over_m), half_dt));
-    u64 dst = atomicAdd(&e.ctr->n, 1ull);
-    if (dst >= e.cap) { atomicAdd(&e.ctr->overflow, 1ull); return; }
-    e.a[0][dst] = pos[0]; e.a[1][dst] = pos[1]; e.a[2][dst] = pos[2]; e.a[3][dst] = u; e.a[4][dst] = vv; e.a[5][dst] = w; e.a[6][dst] = e.mpw0;
-}
-
-// The part of the heavy push that follows an impact (Species.cpp:213-238): rare, kept out of line.
-// Returns true when the particle is absorbed; otherwise x, v, t_rem are updated for the next sub-move.
-__device__ __noinline__ bool surface_interaction(const Grid& g, const HeavyArgs& h, const double* __restrict__ ef, PhiloxStream& r, int obj,
-                                                 const double old[3], double x[3], double v[3], double mpw, double& t_rem) {
-    double tp, hit[3], nrm[3];
-    const ObjShape& o = g.obj[obj - 1];
-    if (o.type == 0) rect_line_intersect(o, old, x, &tp, hit, nrm); else sphere_line_intersect(o, old, x, &tp, hit, nrm);
-    x[0] = hit[0]; x[1] = hit[1]; x[2] = hit[2];
-    double v_mag = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-    if (h.charge == 0) {                                                    // neutrals: diffuse re-emission
-        double nv[3]; sample_reflected(r, v_mag, nrm, h.mass, nv);
-        v[0] = nv[0]; v[1] = nv[1]; v[2] = nv[2];
-        t_rem *= (1 - tp);
-        return false;
-    }
-    int mp_create = (int)(mpw / h.neutrals.mpw0 + r.next());                // ions: neutralise on the surface (:225-232)
-    for (int c = 0; c < mp_create; c++) { double nv[3]; sample_reflected(r, v_mag, nrm, h.mass, nv); emit_particle(g, h.neutrals, ef, h.half_world_dt, x, nv); }
-    if (h.sputtering) {                                                     // :136-145
-        double yield = (v_mag > 5e3) ? 0.1 : 0;
-        int sp_create = (int)(yield * mpw / h.spherium.mpw0 + r.next());
-        for (int c = 0; c < sp_create; c++) { double nv[3]; sample_reflected(r, v_mag, nrm, h.mass, nv); emit_particle(g, h.spherium, ef, h.half_world_dt, x, nv); }
-    }
-    return true;
-}
 
 template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT>
 __global__ void __launch_bounds__(STEP_THREADS, 2) k_step(Grid g, StepArgs A, HeavyArgs H) {
@@ -97,7 +58,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 2) k_step(Grid g, StepArgs A, He
     const int tid = threadIdx.x, lane = tid & 31;
     if (DEPOSIT) { for (int t = tid; t < STEP_WINDOW * 8; t += STEP_THREADS) win[t] = 0; }
 
-    for (u64 chunk = (u64)blockIdx.x * STEP_CHUNK; chunk < n; chunk += (u64)gridDim.x * STEP_CHUNK) {
+    const u64 first = A.tail_from ? (u64)*A.tail_from : 0;
+    for (u64 chunk = first + (u64)blockIdx.x * STEP_CHUNK; chunk < n; chunk += (u64)gridDim.x * STEP_CHUNK) {
         const int cnt = (int)min((u64)STEP_CHUNK, n - chunk);
         // ---- load phase (coalesced; every load of the thread is independent of every other)
 #pragma unroll
@@ -237,11 +199,6 @@ int launch_finalize(picg_species_s* s);
 int calibrate_scale(picg_species_s* s, bool count_cells);
 int check_scale_after(picg_species_s* s);
 
-static Emit emit_of(picg_species_s* t) {
-    Emit e; for (int c = 0; c < 7; c++) e.a[c] = t->a[c];
-    e.ctr = t->ctr; e.cap = t->cap; e.mpw0 = t->mpw0; e.q_over_m = t->charge / t->mass;
-    return e;
-}
 template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT>
 static int launch_variant(const Grid& g, const StepArgs& A, const HeavyArgs& H, size_t n_upper, int kid) {
     size_t smem = (size_t)((PUSH ? 7 : 4) * STEP_PITCH) * 8 + (DEPOSIT ? STEP_WINDOW * 64 : 0);
@@ -256,9 +213,12 @@ static int launch_variant(const Grid& g, const StepArgs& A, const HeavyArgs& H, 
 }
 
 // mode bits: 1 push, 2 heavy, 4 deposit, 8 count
+int launch_cell_step(picg_species_s* s, int mode, double dt, const HeavyArgs& H, size_t n_limit);     // cellstep.cu
+
 int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals, picg_species_s* spherium, int sputtering, size_t n_snapshot) {
     const Grid& g = s->w->g;
     StepArgs A;
+    A.tail_from = nullptr;
     for (int c = 0; c < 7; c++) A.a[c] = s->a[c];
     A.ctr = s->ctr; A.use_fixed_n = (mode & 2) ? 1 : 0; A.n_fixed = n_snapshot;
     A.ef = s->w->ef; A.qm_dt = dt * s->charge / s->mass; A.dt = dt;                 // Species.cpp:372 `dt*charge/mass`
@@ -272,6 +232,13 @@ int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals
     if (mode & 4) cudaMemsetAsync(s->den_fixed, 0, (size_t)g.nv * 8, g_stream);
     if (mode & 8) cudaMemsetAsync(s->macro_count, 0, (size_t)g.nc * 8, g_stream);
     size_t nu = (mode & 2) ? n_snapshot : s->n_upper;
+    // fast path: the store carries a cell partition (cell_start[] of the last sort) and is dense enough for a warp per cell
+    if (s->part_valid && nu >= (size_t)4 * g.nc) {
+        int rc = launch_cell_step(s, mode, dt, H, (mode & 2) ? n_snapshot : (size_t)-1); if (rc) return rc;
+        if (nu <= s->part_n) return PICG_OK;              // nothing was appended since the sort
+        A.tail_from = s->cell_start + g.nc;               // the appended tail goes through the generic kernel
+        nu = nu - s->part_n;
+    }
     switch (mode) {
         case 1:  return launch_variant<true, false, false, false>(g, A, H, nu, K_PUSH_ELECTRONS);
         case 3:  return launch_variant<true, true, false, false>(g, A, H, nu, K_PUSH_HEAVY);

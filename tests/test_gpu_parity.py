@@ -202,6 +202,36 @@ def test_fused_heavy_push_deposit_equals_separate(picgpu, orc):
         o.close()
 
 
+def test_cell_partition_path_with_stragglers_holes_and_appended_tail(picgpu, orc):
+    """The warp-per-cell fast path must not depend on how stale the partition is: after the sort particles drift out of
+    their cells, die (holes are filled from the tail) and new ones are appended beyond the partition."""
+    w, g, x0, xm = _setup(picgpu, orc)
+    ef = util.smooth_ef((w.ni, w.nj, w.nk), x0, xm, seed=3, amp=3e6)
+    w.upload(picgpu.F_EF, ef)
+    parts = util.random_particles(70000, x0, xm, seed=31, vth=1.5e6)
+    sp = picgpu.Species("e-", util.ME, -util.QE, w, 100.0)
+    sp.setParticles(parts); sp.sort(); sp.setDensityScale(28)
+    cur = sp.getParticles()
+    for it in range(4):                                   # several pushes on one (increasingly stale) partition
+        sp.advanceElectronsDeposit(6e-11, count_cells=True)
+        want, alive = g.push_electrons(ef, -util.QE, util.ME, 6e-11, cur)
+        cur = want[alive]
+        assert sp.getNumParticles() == len(cur)
+        assert np.array_equal(sp.den_fixed, g.deposit_fixed(cur, 28))
+        assert np.array_equal(sp.macro_part_count, g.count_per_cell(cur))
+        got = sp.getParticles()
+        assert np.array_equal(util.sort_rows(got), util.sort_rows(cur))
+        cur = got                                         # follow the device order (compaction permutes)
+        if it == 1:                                       # append beyond the partition
+            extra = util.random_particles(9000, x0, xm, seed=32, vth=1.5e6, lo_frac=(0, 0, 0.2), hi_frac=(1, 1, 0.8))
+            sp.addParticles(extra)
+            cur = sp.getParticles()
+    assert len(cur) < 70000 + 9000
+    sp.computeNumberDensity()                             # deposit-only through the same path
+    assert np.array_equal(sp.den_fixed, g.deposit_fixed(cur, 28))
+    sp.close(); w.close()
+
+
 def test_count_per_cell_and_sort(picgpu, orc):
     w, g, x0, xm = _setup(picgpu, orc)
     parts = util.random_particles(123457, x0, xm, seed=8)
