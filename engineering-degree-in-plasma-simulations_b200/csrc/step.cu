@@ -1,23 +1,23 @@
 // The particle-loop kernel: push (+ wall interaction) and/or fixed-point deposit (+ per-cell count) in one pass.
 //
-//   k_step<PUSH, HEAVY, DEPOSIT, COUNT>
+//   k_run<PUSH, HEAVY, DEPOSIT, COUNT>
 //     PUSH            Species::advanceElectronsSerial              ch4/v3/src/Species.cpp:356-399
 //     PUSH + HEAVY    Species::advanceNoSputteringSerial / ...SputteringSerial   :170-256 / :81-169
 //     DEPOSIT         Species::computeNumberDensity                :401-413 (+ Field::scatter Field.h:157-199)
 //     COUNT           Species::computeMacroParticlesCount          :813-819
 //
-// Data movement (the design point of this kernel; every stage is HBM-bound):
-//   * a block owns a contiguous chunk of STEP_CHUNK particles of the (cell-sorted) SoA store;
-//   * load phase: the chunk's arrays are copied global -> shared with fully coalesced accesses, all loads of a thread
-//     issued before the first use (deep memory-level parallelism; no dependent gather sits between two particle loads);
-//   * compute phase: thread t processes the R = STEP_RUN CONSECUTIVE particles t*R..t*R+R-1 from shared memory.  In a
-//     cell-sorted store a run stays inside one cell almost always, so the eight fixed-point corner sums are accumulated
-//     in registers and leave the thread once per run, not once per particle.  Run totals of the lanes of a warp that end
-//     in the same cell are combined with a transposed butterfly (deposit.cuh) and go to a shared-memory window of
-//     STEP_WINDOW cells x 8 corners with 64-bit integer atomics; cells outside the window (unsorted input, stragglers)
-//     go straight to global memory.  Integer sums are associative: any order gives the same bits.
-//   * store phase: updated positions / velocities go shared -> global, coalesced; the window is flushed with one
-//     global atomic per touched (cell, corner).
+// Data movement (every stage is HBM-bound; the design point is bytes in flight and instructions per particle):
+//   * a thread owns a RUN of 4 CONSECUTIVE particles.  Each SoA array is read with one 256-bit load per run
+//     (ld.global.cs.v4.f64 -> LDG.E.256, evict-first so the streamed particles do not push the field out of L2): a warp
+//     covers 128 consecutive particles with 7 fully coalesced, mutually independent loads, i.e. 7 KB in flight per warp
+//     before the first dependent instruction.  Results go back with 256-bit stores (full sectors).
+//   * the four particles of a run are independent, so their E-field gathers (24 L1/L2 loads each) overlap.
+//   * in a cell-sorted store a run stays inside one cell almost always: the eight fixed-point corner sums are
+//     accumulated in registers and leave the thread once per run, not once per particle.  Run totals of lanes that end
+//     in the same cell are combined with a transposed butterfly (deposit.cuh) and go to a per-warp shared-memory window
+//     of RUN_WINDOW cells x 8 corners with 64-bit integer atomics; cells outside the window (unsorted input,
+//     stragglers) go straight to global memory.  Integer sums are associative: any order gives the same bits.
+//   * warps are independent (no block-level barrier): a persistent grid strides over 128-particle warp chunks.
 // Algorithmic bytes per particle: push 96 B, deposit 32 B, fused 104 B (E-field and grid traffic are amortised over
 // the ~60 particles of a cell and served by L1/L2).
 #include "common.cuh"
@@ -27,14 +27,15 @@
 #include "heavy.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 using namespace picg;
 
-#define STEP_THREADS 256
-#define STEP_RUN 4
-#define STEP_CHUNK (STEP_THREADS * STEP_RUN)                 // 1024 particles per block iteration
-#define STEP_PITCH (STEP_CHUNK + STEP_CHUNK / STEP_RUN)      // one pad double per run: conflict-free run-wise reads
-#define STEP_WINDOW 256                                      // cells staged in shared memory (x 8 corners x 8 B = 16 KB)
+#define RUN_THREADS 256
+#define RUN_WARPS (RUN_THREADS / 32)
+#define RUN_LEN 4
+#define RUN_WARP_CHUNK (32 * RUN_LEN)                        // 128 particles per warp iteration
+#define RUN_WINDOW 16                                        // cells in the per-warp window (x 8 corners x 8 B = 1 KB)
 
 struct StepArgs {
     double* a[7]; SpeciesCounters* ctr; u64 n_fixed; int use_fixed_n;      // heavy pushes walk a snapshot of the count (Species.cpp:176)
@@ -43,154 +44,151 @@ struct StepArgs {
     unsigned* dead_list; u64* den_fixed; double scale; double* macro_count;
 };
 
-__device__ __forceinline__ int spos(int i) { return i + (i / STEP_RUN); }
+__device__ __forceinline__ void ld4_stream(const double* p, double v[4]) {
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void st4_stream(double* p, const double v[4]) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+__device__ __forceinline__ void load_run(const double* base, u64 p0, bool full, u64 lo, u64 n, double v[4]) {
+    if (full) ld4_stream(base + p0, v);
+    else {
+#pragma unroll
+        for (int r = 0; r < RUN_LEN; r++) v[r] = (p0 + r >= lo && p0 + r < n) ? __ldcs(base + p0 + r) : 0.0;
+    }
+}
+__device__ __forceinline__ void store_run(double* base, u64 p0, bool full, u64 lo, u64 n, const double v[4]) {
+    if (full) st4_stream(base + p0, v);
+    else {
+#pragma unroll
+        for (int r = 0; r < RUN_LEN; r++) if (p0 + r >= lo && p0 + r < n) __stcs(base + p0 + r, v[r]);
+    }
+}
 
 template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT>
-__global__ void __launch_bounds__(STEP_THREADS, 2) k_step(Grid g, StepArgs A, HeavyArgs H) {
-    extern __shared__ double smem[];
-    constexpr int NARR = PUSH ? 7 : 4;                       // staged arrays: x y z [u v w] mpw
-    double* sx = smem; double* sy = sx + STEP_PITCH; double* sz = sy + STEP_PITCH;
-    double* su = PUSH ? sz + STEP_PITCH : nullptr; double* sv = PUSH ? su + STEP_PITCH : nullptr; double* sw = PUSH ? sv + STEP_PITCH : nullptr;
-    double* sm = smem + (NARR - 1) * STEP_PITCH;
-    i64* win = (i64*)(smem + NARR * STEP_PITCH);
-    __shared__ int s_c0;
+__global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, HeavyArgs H) {
+    __shared__ i64 s_win[DEPOSIT ? RUN_WARPS : 1][RUN_WINDOW * 8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    i64* win = s_win[DEPOSIT ? wib : 0];
+    if (DEPOSIT) { for (int t = lane; t < RUN_WINDOW * 8; t += 32) win[t] = 0; __syncwarp(); }
     const u64 n = A.use_fixed_n ? A.n_fixed : A.ctr->n;
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (DEPOSIT) { for (int t = tid; t < STEP_WINDOW * 8; t += STEP_THREADS) win[t] = 0; }
+    const u64 lo = A.tail_from ? (u64)*A.tail_from : 0;
+    const u64 warp = (u64)blockIdx.x * RUN_WARPS + wib, nwarps = (u64)gridDim.x * RUN_WARPS;
 
-    const u64 first = A.tail_from ? (u64)*A.tail_from : 0;
-    for (u64 chunk = first + (u64)blockIdx.x * STEP_CHUNK; chunk < n; chunk += (u64)gridDim.x * STEP_CHUNK) {
-        const int cnt = (int)min((u64)STEP_CHUNK, n - chunk);
-        // ---- load phase (coalesced; every load of the thread is independent of every other)
-#pragma unroll
-        for (int r = 0; r < STEP_RUN; r++) {
-            int i = r * STEP_THREADS + tid;
-            bool ok = i < cnt; u64 p = chunk + i; int d = spos(i);
-            sx[d] = ok ? A.a[0][p] : 0.0; sy[d] = ok ? A.a[1][p] : 0.0; sz[d] = ok ? A.a[2][p] : 0.0;
-            if (PUSH) { su[d] = ok ? A.a[3][p] : 0.0; sv[d] = ok ? A.a[4][p] : 0.0; sw[d] = ok ? A.a[5][p] : 0.0; }
-            if (DEPOSIT || HEAVY) sm[d] = ok ? A.a[6][p] : 0.0;
+    for (u64 chunk = (lo & ~(u64)3) + warp * RUN_WARP_CHUNK; chunk < n; chunk += nwarps * RUN_WARP_CHUNK) {
+        const u64 p0 = chunk + (u64)lane * RUN_LEN;
+        const bool full = p0 >= lo && p0 + RUN_LEN <= n;
+        double x[4], y[4], z[4], u[4], v[4], w[4], m[4];
+        load_run(A.a[0], p0, full, lo, n, x); load_run(A.a[1], p0, full, lo, n, y); load_run(A.a[2], p0, full, lo, n, z);
+        if (PUSH) { load_run(A.a[3], p0, full, lo, n, u); load_run(A.a[4], p0, full, lo, n, v); load_run(A.a[5], p0, full, lo, n, w); }
+        if (DEPOSIT || HEAVY) load_run(A.a[6], p0, full, lo, n, m);
+        int c0 = 0;
+        if (DEPOSIT) {                  // window placed at the warp's first particle (2 cells of slack below)
+            int i = min(max((int)x_to_l(x[0], g.x0[0], g.inv_dx[0]), 0), g.ci - 1);
+            int j = min(max((int)x_to_l(y[0], g.x0[1], g.inv_dx[1]), 0), g.cj - 1);
+            int k = min(max((int)x_to_l(z[0], g.x0[2], g.inv_dx[2]), 0), g.ck - 1);
+            c0 = __shfl_sync(0xffffffffu, cell_of(g, i, j, k), 0) - 2;
         }
-        __syncthreads();
-        if (DEPOSIT && tid == 0) {            // window placed at the chunk's first particle (2 cells of slack below)
-            int i = min(max((int)x_to_l(sx[0], g.x0[0], g.inv_dx[0]), 0), g.ci - 1);
-            int j = min(max((int)x_to_l(sy[0], g.x0[1], g.inv_dx[1]), 0), g.cj - 1);
-            int k = min(max((int)x_to_l(sz[0], g.x0[2], g.inv_dx[2]), 0), g.ck - 1);
-            s_c0 = cell_of(g, i, j, k) - 2;
-        }
-        if (DEPOSIT) __syncthreads();
-        const int c0 = DEPOSIT ? s_c0 : 0;
-
-        // ---- compute phase: a run of STEP_RUN consecutive particles per thread
         int cur = -1; i64 acc[8]; double cur_count = 0;
 #pragma unroll
         for (int c = 0; c < 8; c++) acc[c] = 0;
 #pragma unroll
-        for (int r = 0; r < STEP_RUN; r++) {
-            const int i = tid * STEP_RUN + r, d = spos(i);
-            const u64 p = chunk + i;
-            const bool ok = i < cnt;
+        for (int r = 0; r < RUN_LEN; r++) {
+            const u64 p = p0 + r;
+            const bool ok = p >= lo && p < n;
             bool dead = false;
-            double x = sx[d], y = sy[d], z = sz[d];
             if (PUSH && ok) {
-                double u = su[d], v = sv[d], w = sw[d];
+                double ex, ey, ez;
+                gather_ef(g, A.ef, x_to_l(x[r], g.x0[0], g.inv_dx[0]), x_to_l(y[r], g.x0[1], g.inv_dx[1]), x_to_l(z[r], g.x0[2], g.inv_dx[2]), ex, ey, ez);
+                double un = __dadd_rn(u[r], __dmul_rn(ex, A.qm_dt)), vn = __dadd_rn(v[r], __dmul_rn(ey, A.qm_dt)), wn = __dadd_rn(w[r], __dmul_rn(ez, A.qm_dt));
+                double xn = x[r], yn = y[r], zn = z[r];
                 if (!HEAVY) {
-                    push_kick_drift(g, A.ef, A.qm_dt, A.dt, x, y, z, u, v, w);
-                    dead = !in_bounds(g, x, y, z) || in_object(g, x, y, z) != 0;            // Species.cpp:375-388
+                    xn = __dadd_rn(xn, __dmul_rn(un, A.dt)); yn = __dadd_rn(yn, __dmul_rn(vn, A.dt)); zn = __dadd_rn(zn, __dmul_rn(wn, A.dt));
+                    dead = !in_bounds(g, xn, yn, zn) || in_object(g, xn, yn, zn) != 0;        // Species.cpp:375-388
                 } else {
-                    double ex, ey, ez;
-                    gather_ef(g, A.ef, x_to_l(x, g.x0[0], g.inv_dx[0]), x_to_l(y, g.x0[1], g.inv_dx[1]), x_to_l(z, g.x0[2], g.inv_dx[2]), ex, ey, ez);
-                    u = __dadd_rn(u, __dmul_rn(ex, A.qm_dt)); v = __dadd_rn(v, __dmul_rn(ey, A.qm_dt)); w = __dadd_rn(w, __dmul_rn(ez, A.qm_dt));
                     double t_rem = 1; int n_b = 0; bool rng_ready = false; PhiloxStream rs;
                     while (t_rem > 0) {
                         if (++n_b > 20) { dead = true; break; }                                // :198-203
-                        double old[3] = {x, y, z};
-                        x = __dadd_rn(x, __dmul_rn(__dmul_rn(u, t_rem), A.dt));               // pos += vel*t_rem*dt
-                        y = __dadd_rn(y, __dmul_rn(__dmul_rn(v, t_rem), A.dt));
-                        z = __dadd_rn(z, __dmul_rn(__dmul_rn(w, t_rem), A.dt));
-                        int obj = in_object(g, x, y, z);
-                        if (!in_bounds(g, x, y, z)) { dead = true; break; }
+                        double old[3] = {xn, yn, zn};
+                        xn = __dadd_rn(xn, __dmul_rn(__dmul_rn(un, t_rem), A.dt));            // pos += vel*t_rem*dt
+                        yn = __dadd_rn(yn, __dmul_rn(__dmul_rn(vn, t_rem), A.dt));
+                        zn = __dadd_rn(zn, __dmul_rn(__dmul_rn(wn, t_rem), A.dt));
+                        int obj = in_object(g, xn, yn, zn);
+                        if (!in_bounds(g, xn, yn, zn)) { dead = true; break; }
                         if (obj) {
                             if (!rng_ready) { rs.init(H.seed, H.stream, p, H.call); rng_ready = true; }
-                            double xx[3] = {x, y, z}, vv[3] = {u, v, w};
-                            bool absorbed = surface_interaction(g, H, A.ef, rs, obj, old, xx, vv, sm[d], t_rem);
-                            x = xx[0]; y = xx[1]; z = xx[2]; u = vv[0]; v = vv[1]; w = vv[2];
+                            double xx[3] = {xn, yn, zn}, vv[3] = {un, vn, wn};
+                            bool absorbed = surface_interaction(g, H, A.ef, rs, obj, old, xx, vv, m[r], t_rem);
+                            xn = xx[0]; yn = xx[1]; zn = xx[2]; un = vv[0]; vn = vv[1]; wn = vv[2];
                             if (absorbed) { dead = true; break; }
                             continue;
                         }
                         t_rem = 0;
                     }
                 }
-                if (!dead) { sx[d] = x; sy[d] = y; sz[d] = z; su[d] = u; sv[d] = v; sw[d] = w; }
+                if (!dead) { x[r] = xn; y[r] = yn; z[r] = zn; u[r] = un; v[r] = vn; w[r] = wn; }
             }
             if (PUSH) record_dead(dead, lane, p, A.ctr, A.dead_list);
-            if (DEPOSIT || COUNT) {
-                if (ok && !dead) {
-                    int ci, cj, ck; i64 q[8];
-                    if (DEPOSIT) scatter_weights_fixed(g, x_to_l(x, g.x0[0], g.inv_dx[0]), x_to_l(y, g.x0[1], g.inv_dx[1]), x_to_l(z, g.x0[2], g.inv_dx[2]),
-                                                       sm[d], A.scale, ci, cj, ck, q);
-                    else {
-                        ci = min((int)x_to_l(x, g.x0[0], g.inv_dx[0]), g.ci - 1); cj = min((int)x_to_l(y, g.x0[1], g.inv_dx[1]), g.cj - 1);
-                        ck = min((int)x_to_l(z, g.x0[2], g.inv_dx[2]), g.ck - 1);
-                    }
-                    int cell = cell_of(g, ci, cj, ck);
-                    if (cell != cur) {
-                        if (cur >= 0) {                                  // the run left its cell: hand the partial sums over
-                            if (DEPOSIT) {
-                                int rel = cur - c0;
-                                if (rel >= 0 && rel < STEP_WINDOW) {
-#pragma unroll
-                                    for (int c = 0; c < 8; c++) if (acc[c]) atomicAdd((u64*)&win[rel * 8 + c], (u64)acc[c]);
-                                } else {
-                                    int i2, j2, k2; cell_to_ijk(g, cur, i2, j2, k2);
-#pragma unroll
-                                    for (int c = 0; c < 8; c++) if (acc[c]) atomicAdd(&A.den_fixed[corner_node(g, i2, j2, k2, c)], (u64)acc[c]);
-                                }
-                            }
-                            if (COUNT) atomicAdd(&A.macro_count[cur], cur_count);
-                        }
-                        cur = cell; cur_count = 0;
-#pragma unroll
-                        for (int c = 0; c < 8; c++) acc[c] = 0;
-                    }
-                    if (DEPOSIT) {
-#pragma unroll
-                        for (int c = 0; c < 8; c++) acc[c] += q[c];
-                    }
-                    cur_count += 1.0;
+            if ((DEPOSIT || COUNT) && ok && !dead) {
+                int ci, cj, ck; i64 q[8];
+                if (DEPOSIT) scatter_weights_fixed(g, x_to_l(x[r], g.x0[0], g.inv_dx[0]), x_to_l(y[r], g.x0[1], g.inv_dx[1]), x_to_l(z[r], g.x0[2], g.inv_dx[2]),
+                                                   m[r], A.scale, ci, cj, ck, q);
+                else {
+                    ci = min((int)x_to_l(x[r], g.x0[0], g.inv_dx[0]), g.ci - 1); cj = min((int)x_to_l(y[r], g.x0[1], g.inv_dx[1]), g.cj - 1);
+                    ck = min((int)x_to_l(z[r], g.x0[2], g.inv_dx[2]), g.ck - 1);
                 }
+                int cell = cell_of(g, ci, cj, ck);
+                if (cell != cur) {
+                    if (cur >= 0) {                                      // the run left its cell: hand the partial sums over
+                        if (DEPOSIT) {
+                            int rel = cur - c0;
+                            if (rel >= 0 && rel < RUN_WINDOW) {
+#pragma unroll
+                                for (int c = 0; c < 8; c++) if (acc[c]) atomicAdd((u64*)&win[rel * 8 + c], (u64)acc[c]);
+                            } else {
+                                int i2, j2, k2; cell_to_ijk(g, cur, i2, j2, k2);
+#pragma unroll
+                                for (int c = 0; c < 8; c++) if (acc[c]) atomicAdd(&A.den_fixed[corner_node(g, i2, j2, k2, c)], (u64)acc[c]);
+                            }
+                        }
+                        if (COUNT) atomicAdd(&A.macro_count[cur], cur_count);
+                    }
+                    cur = cell; cur_count = 0;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) acc[c] = 0;
+                }
+                if (DEPOSIT) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) acc[c] += q[c];
+                }
+                cur_count += 1.0;
             }
+        }
+        // results back to the store (dead slots keep their old contents; the compaction fills them)
+        if (PUSH) {
+            store_run(A.a[0], p0, full, lo, n, x); store_run(A.a[1], p0, full, lo, n, y); store_run(A.a[2], p0, full, lo, n, z);
+            store_run(A.a[3], p0, full, lo, n, u); store_run(A.a[4], p0, full, lo, n, v); store_run(A.a[5], p0, full, lo, n, w);
         }
         // run totals: lanes ending in the same cell are combined before they touch shared / global memory
-        if (DEPOSIT) warp_accumulate_w<STEP_WINDOW>(g, cur >= 0, cur, acc, win, c0, A.den_fixed, lane);
-        if (COUNT) {
-            unsigned peers = __match_any_sync(0xffffffffu, cur);
-            double s = 0; unsigned m = peers;                            // integer-valued counts: exact in any order
-            while (m) { int src = __ffs(m) - 1; m &= m - 1; s += __shfl_sync(peers, cur_count, src); }
-            if (cur >= 0 && lane == __ffs(peers) - 1) atomicAdd(&A.macro_count[cur], s);
-        }
-        __syncthreads();
-        // ---- store phase
-        if (PUSH) {
-#pragma unroll
-            for (int r = 0; r < STEP_RUN; r++) {
-                int i = r * STEP_THREADS + tid;
-                if (i < cnt) {
-                    u64 p = chunk + i; int d = spos(i);
-                    A.a[0][p] = sx[d]; A.a[1][p] = sy[d]; A.a[2][p] = sz[d]; A.a[3][p] = su[d]; A.a[4][p] = sv[d]; A.a[5][p] = sw[d];
-                }
-            }
-        }
         if (DEPOSIT) {
-            for (int slot = tid; slot < STEP_WINDOW * 8; slot += STEP_THREADS) {
-                i64 v = win[slot];
-                if (v != 0) {
+            warp_accumulate_w<RUN_WINDOW>(g, cur >= 0, cur, acc, win, c0, A.den_fixed, lane);
+            __syncwarp();
+            for (int slot = lane; slot < RUN_WINDOW * 8; slot += 32) {
+                i64 t = win[slot];
+                if (t != 0) {
                     int i2, j2, k2; cell_to_ijk(g, c0 + (slot >> 3), i2, j2, k2);
-                    atomicAdd(&A.den_fixed[corner_node(g, i2, j2, k2, slot & 7)], (u64)v);
+                    atomicAdd(&A.den_fixed[corner_node(g, i2, j2, k2, slot & 7)], (u64)t);
                     win[slot] = 0;
                 }
             }
+            __syncwarp();
         }
-        __syncthreads();
+        if (COUNT) {
+            unsigned peers = __match_any_sync(0xffffffffu, cur);
+            double s = 0; unsigned mm = peers;                          // integer-valued counts: exact in any order
+            while (mm) { int src = __ffs(mm) - 1; mm &= mm - 1; s += __shfl_sync(peers, cur_count, src); }
+            if (cur >= 0 && lane == __ffs(peers) - 1) atomicAdd(&A.macro_count[cur], s);
+        }
     }
 }
 
@@ -201,13 +199,8 @@ int check_scale_after(picg_species_s* s);
 
 template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT>
 static int launch_variant(const Grid& g, const StepArgs& A, const HeavyArgs& H, size_t n_upper, int kid) {
-    size_t smem = (size_t)((PUSH ? 7 : 4) * STEP_PITCH) * 8 + (DEPOSIT ? STEP_WINDOW * 64 : 0);
-    static bool attr_set = false;
-    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_step<PUSH, HEAVY, DEPOSIT, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-    int per_sm = std::max(1, (int)((size_t)227 * 1024 / (smem + 1024)));
-    per_sm = std::min(per_sm, 2048 / STEP_THREADS);
-    int grid = std::max(1, std::min(div_up(std::max<size_t>(n_upper, 1), STEP_CHUNK), g_sm_count * per_sm));
-    LAUNCH(kid, (k_step<PUSH, HEAVY, DEPOSIT, COUNT>), grid, STEP_THREADS, smem, g, A, H);
+    int grid = std::max(1, std::min(div_up(std::max<size_t>(n_upper, 1), RUN_WARP_CHUNK * RUN_WARPS), g_sm_count * 2 * 4));
+    LAUNCH(kid, (k_run<PUSH, HEAVY, DEPOSIT, COUNT>), grid, RUN_THREADS, 0, g, A, H);
     CHECK_LAUNCH();
     return PICG_OK;
 }
@@ -233,7 +226,8 @@ int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals
     if (mode & 8) cudaMemsetAsync(s->macro_count, 0, (size_t)g.nc * 8, g_stream);
     size_t nu = (mode & 2) ? n_snapshot : s->n_upper;
     // fast path: the store carries a cell partition (cell_start[] of the last sort) and is dense enough for a warp per cell
-    if (s->part_valid && nu >= (size_t)4 * g.nc) {
+    static const bool cell_path = getenv("PICG_CELL_PATH") && atoi(getenv("PICG_CELL_PATH")) != 0;      // A/B switch, see DESIGN.md
+    if (cell_path && s->part_valid && nu >= (size_t)4 * g.nc) {
         int rc = launch_cell_step(s, mode, dt, H, (mode & 2) ? n_snapshot : (size_t)-1); if (rc) return rc;
         if (nu <= s->part_n) return PICG_OK;              // nothing was appended since the sort
         A.tail_from = s->cell_start + g.nc;               // the appended tail goes through the generic kernel
