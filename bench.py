@@ -221,11 +221,11 @@ def run_ours(args):
         for sp in order:
             if world == 1:
                 if sp is ele:
-                    sp.advanceElectronsDeposit(wl["dt"], count_cells=True)      # fused push + deposit + per-cell count
+                    sp.advanceElectrons(wl["dt"])
                 else:
                     sp.advanceNonElectron(neu, neu, wl["dt"])
-                    sp.computeNumberDensity()
-                    sp.computeMacroParticlesCount()
+                sp.computeNumberDensity()
+                sp.computeMacroParticlesCount()
             else:
                 if sp is ele:
                     sp.advanceElectrons(wl["dt"])
@@ -327,8 +327,9 @@ def run_ours(args):
         elif name == "push_heavy":
             alg = 96 * 0.5 * (per_rank_counts["O"] + per_rank_counts["O+"])       # launches alternate between the two heavy species
         elif name == "deposit_density":
-            launched = [per_rank_counts["O"], per_rank_counts["O+"]] + ([per_rank_counts["e-"]] if world > 1 else [])
-            alg = 32 * float(np.mean(launched))
+            alg = 32 * float(np.mean(list(per_rank_counts.values())))             # one launch per species per step
+        elif name == "count_per_cell":
+            alg = 24 * float(np.mean(list(per_rank_counts.values())))
         elif name in ALG_BYTES_PER_NODE:
             alg = ALG_BYTES_PER_NODE[name] * nv
         if alg:

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(CS_THREADS, 3) k_cell_step(Grid g, CellArgs A,
                     double t_rem = 1; int n_b = 0; bool rng_ready = false; PhiloxStream rs;
                     while (t_rem > 0) {
                         if (++n_b > 20) { dead = true; break; }                                // :198-203
-                        double old[3] = {x, y, z};
+                        const double ox = x, oy = y, oz = z;
                         x = __dadd_rn(x, __dmul_rn(__dmul_rn(u, t_rem), A.dt));
                         y = __dadd_rn(y, __dmul_rn(__dmul_rn(v, t_rem), A.dt));
                         z = __dadd_rn(z, __dmul_rn(__dmul_rn(w, t_rem), A.dt));
@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(CS_THREADS, 3) k_cell_step(Grid g, CellArgs A,
                         if (!in_bounds(g, x, y, z)) { dead = true; break; }
                         if (obj) {
                             if (!rng_ready) { rs.init(H.seed, H.stream, p, H.call); rng_ready = true; }
-                            double xx[3] = {x, y, z}, vv[3] = {u, v, w};
-                            bool absorbed = surface_interaction(g, H, A.ef, rs, obj, old, xx, vv, m, t_rem);
+                            double xx[3] = {x, y, z}, vv[3] = {u, v, w}, oo[3] = {ox, oy, oz};
+                            bool absorbed = surface_interaction(g, H, A.ef, rs, obj, oo, xx, vv, m, t_rem);
                             x = xx[0]; y = xx[1]; z = xx[2]; u = vv[0]; v = vv[1]; w = vv[2];
                             if (absorbed) { dead = true; break; }
                             continue;
@@ -160,18 +160,7 @@ __global__ void __launch_bounds__(CS_THREADS, 3) k_cell_step(Grid g, CellArgs A,
         }
         // once per cell: combine the 32 lanes (transposed butterfly, deposit.cuh) and hand the 8 corner sums over
         if (DEPOSIT) {
-            bool h = lane & 16;
-            i64 a0 = (h ? acc[4] : acc[0]) + __shfl_xor_sync(0xffffffffu, h ? acc[0] : acc[4], 16);
-            i64 a1 = (h ? acc[5] : acc[1]) + __shfl_xor_sync(0xffffffffu, h ? acc[1] : acc[5], 16);
-            i64 a2 = (h ? acc[6] : acc[2]) + __shfl_xor_sync(0xffffffffu, h ? acc[2] : acc[6], 16);
-            i64 a3 = (h ? acc[7] : acc[3]) + __shfl_xor_sync(0xffffffffu, h ? acc[3] : acc[7], 16);
-            bool b = lane & 8;
-            i64 b0 = (b ? a2 : a0) + __shfl_xor_sync(0xffffffffu, b ? a0 : a2, 8);
-            i64 b1 = (b ? a3 : a1) + __shfl_xor_sync(0xffffffffu, b ? a1 : a3, 8);
-            bool c4 = lane & 4;
-            i64 t = (c4 ? b1 : b0) + __shfl_xor_sync(0xffffffffu, c4 ? b0 : b1, 4);
-            t += __shfl_xor_sync(0xffffffffu, t, 2);
-            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            i64 t = butterfly8(acc, lane);
             if ((lane & 3) == 0 && t != 0) atomicAdd(&A.den_fixed[corner_node(g, ci, cj, ck, lane >> 2)], (u64)t);
         }
         if (COUNT) {

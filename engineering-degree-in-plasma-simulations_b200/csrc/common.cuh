@@ -27,6 +27,7 @@ struct ObjShape {           // Object.h: Sphere / Rectangle
 struct Grid {               // passed by value to kernels (World.cpp:63-77)
     int ni, nj, nk, nv;
     int ci, cj, ck, nc;     // cells per axis (ni-1 ..), num_cells
+    unsigned div_ck_mul, div_ck_shift, div_cj_mul, div_cj_shift;   // multiply-shift division by ck / cj (exact for numerators < 2^31)
     double x0[3], xm[3], dx[3], inv_dx[3];
     int n_obj;
     ObjShape obj[PICG_MAX_OBJECTS];

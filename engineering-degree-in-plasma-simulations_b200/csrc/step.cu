@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
         int cur = -1; i64 acc[8]; double cur_count = 0;
 #pragma unroll
         for (int c = 0; c < 8; c++) acc[c] = 0;
-#pragma unroll
+        constexpr int kUnroll = DEPOSIT ? 1 : 4;
+#pragma unroll kUnroll
         for (int r = 0; r < RUN_LEN; r++) {
             const u64 p = p0 + r;
             const bool ok = p >= lo && p < n;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
                     double t_rem = 1; int n_b = 0; bool rng_ready = false; PhiloxStream rs;
                     while (t_rem > 0) {
                         if (++n_b > 20) { dead = true; break; }                                // :198-203
-                        double old[3] = {xn, yn, zn};
+                        const double ox = xn, oy = yn, oz = zn;
                         xn = __dadd_rn(xn, __dmul_rn(__dmul_rn(un, t_rem), A.dt));            // pos += vel*t_rem*dt
                         yn = __dadd_rn(yn, __dmul_rn(__dmul_rn(vn, t_rem), A.dt));
                         zn = __dadd_rn(zn, __dmul_rn(__dmul_rn(wn, t_rem), A.dt));
@@ -117,8 +118,8 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
                         if (!in_bounds(g, xn, yn, zn)) { dead = true; break; }
                         if (obj) {
                             if (!rng_ready) { rs.init(H.seed, H.stream, p, H.call); rng_ready = true; }
-                            double xx[3] = {xn, yn, zn}, vv[3] = {un, vn, wn};
-                            bool absorbed = surface_interaction(g, H, A.ef, rs, obj, old, xx, vv, m[r], t_rem);
+                            double xx[3] = {xn, yn, zn}, vv[3] = {un, vn, wn}, oo[3] = {ox, oy, oz};
+                            bool absorbed = surface_interaction(g, H, A.ef, rs, obj, oo, xx, vv, m[r], t_rem);
                             xn = xx[0]; yn = xx[1]; zn = xx[2]; un = vv[0]; vn = vv[1]; wn = vv[2];
                             if (absorbed) { dead = true; break; }
                             continue;
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
                 if (!dead) { x[r] = xn; y[r] = yn; z[r] = zn; u[r] = un; v[r] = vn; w[r] = wn; }
             }
             if (PUSH) record_dead(dead, lane, p, A.ctr, A.dead_list);
+            int newcell = -1; bool have = false; i64 qq[8];
             if ((DEPOSIT || COUNT) && ok && !dead) {
                 int ci, cj, ck; i64 q[8];
                 if (DEPOSIT) scatter_weights_fixed(g, x_to_l(x[r], g.x0[0], g.inv_dx[0]), x_to_l(y[r], g.x0[1], g.inv_dx[1]), x_to_l(z[r], g.x0[2], g.inv_dx[2]),
@@ -138,30 +140,31 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
                     ck = min((int)x_to_l(z[r], g.x0[2], g.inv_dx[2]), g.ck - 1);
                 }
                 int cell = cell_of(g, ci, cj, ck);
-                if (cell != cur) {
-                    if (cur >= 0) {                                      // the run left its cell: hand the partial sums over
-                        if (DEPOSIT) {
-                            int rel = cur - c0;
-                            if (rel >= 0 && rel < RUN_WINDOW) {
-#pragma unroll
-                                for (int c = 0; c < 8; c++) if (acc[c]) atomicAdd((u64*)&win[rel * 8 + c], (u64)acc[c]);
-                            } else {
-                                int i2, j2, k2; cell_to_ijk(g, cur, i2, j2, k2);
-#pragma unroll
-                                for (int c = 0; c < 8; c++) if (acc[c]) atomicAdd(&A.den_fixed[corner_node(g, i2, j2, k2, c)], (u64)acc[c]);
-                            }
-                        }
-                        if (COUNT) atomicAdd(&A.macro_count[cur], cur_count);
-                    }
-                    cur = cell; cur_count = 0;
-#pragma unroll
-                    for (int c = 0; c < 8; c++) acc[c] = 0;
-                }
+                newcell = cell; have = true;
                 if (DEPOSIT) {
 #pragma unroll
-                    for (int c = 0; c < 8; c++) acc[c] += q[c];
+                    for (int c = 0; c < 8; c++) qq[c] = q[c];
                 }
-                cur_count += 1.0;
+            }
+            // a run that leaves its cell hands its partial sums over (warp-collective, rare in a sorted store)
+            {
+                bool leave = have && cur >= 0 && newcell != cur;
+                if (__any_sync(0xffffffffu, leave)) {
+                    if (DEPOSIT) warp_accumulate_w<RUN_WINDOW>(g, leave, cur, acc, win, c0, A.den_fixed, lane);
+                    if (COUNT && leave) atomicAdd(&A.macro_count[cur], cur_count);
+                }
+                if (have) {
+                    if (newcell != cur) {
+                        cur = newcell; cur_count = 0;
+#pragma unroll
+                        for (int c = 0; c < 8; c++) acc[c] = 0;
+                    }
+                    if (DEPOSIT) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) acc[c] += qq[c];
+                    }
+                    cur_count += 1.0;
+                }
             }
         }
         // results back to the store (dead slots keep their old contents; the compaction fills them)

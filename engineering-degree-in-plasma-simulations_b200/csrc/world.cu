@@ -59,6 +59,11 @@ int picg_world_create(int ni, int nj, int nk, const double x0[3], const double x
     memset(&g, 0, sizeof(g));
     g.ni = ni; g.nj = nj; g.nk = nk; g.nv = ni * nj * nk;
     g.ci = ni - 1; g.cj = nj - 1; g.ck = nk - 1; g.nc = g.ci * g.cj * g.ck;
+    auto magic = [](unsigned d, unsigned& mul, unsigned& shift) {      // n / d == (n * mul) >> shift for 0 <= n < 2^31
+        unsigned l = 0; while ((1u << l) < d) l++;
+        shift = 31 + l; mul = (unsigned)(((1ull << shift) / d) + 1);
+    };
+    magic((unsigned)g.ck, g.div_ck_mul, g.div_ck_shift); magic((unsigned)g.cj, g.div_cj_mul, g.div_cj_shift);
     int nn[3] = {ni, nj, nk};
     for (int a = 0; a < 3; a++) {                                // World::setExtents World.cpp:63-77
         g.x0[a] = x0[a]; g.xm[a] = xm[a];
