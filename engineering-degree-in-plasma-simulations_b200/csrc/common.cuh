@@ -47,6 +47,7 @@ struct SpeciesCounters {    // lives in device memory, one per species
 struct picg_world_s {
     Grid g;
     double dt = 1e-4; int num_ts = 0;
+    uint32_t n_species = 0;
     double *phi = nullptr, *rho = nullptr, *node_vol = nullptr, *ef = nullptr;   // ef: 3*nv interleaved
     int *object_id = nullptr, *node_type = nullptr;
     // scratch arena shared by sort / compaction (never live at the same time)
@@ -58,7 +59,8 @@ struct picg_world_s {
 struct picg_species_s {
     picg_world_s* w;
     double mass, charge, mpw0;
-    uint32_t id = 0;                   // creation order; decorrelates the species' RNG streams
+    uint32_t id = 0;                   // index within its world; decorrelates the species' RNG streams
+    uint32_t n_load_calls = 0, n_heavy_calls = 0;   // call counters that address the Philox streams (reproducible per species)
     size_t cap = 0;                   // allocated particles per array
     size_t n_host = 0;                 // last count known to the host
     bool n_host_valid = true;

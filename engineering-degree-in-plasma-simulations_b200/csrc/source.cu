@@ -81,7 +81,7 @@ int picg_species_load_box_thermal(picg_species_t s, const double centre[3], cons
     rc = species_ensure_capacity(s, before + num_macro); if (rc) return rc;
     double lo[3], hi[3];
     for (int a = 0; a < 3; a++) { lo[a] = centre[a] - sides[a] / 2; hi[a] = centre[a] + sides[a] / 2; }   // x0 -/+ sides/2 (:580-581)
-    static uint32_t call = 0; call++;
+    uint32_t call = ++s->n_load_calls;
     uint32_t stream = rng_stream_id(RNG_LOADER, s->id, g_rank);
     rc = ensure_scratch(s->w, std::min(num_macro, kGenChunk) * 56 + 64); if (rc) return rc;
     for (size_t off = 0; off < num_macro; off += kGenChunk) {

@@ -158,7 +158,7 @@ int picg_species_create(picg_world_t w, double mass, double charge, double mpw0,
     REQUIRE_ARG(mass > 0 && mpw0 > 0, "picg_species_create: mass and mpw0 must be positive");
     picg_species_s* s = new picg_species_s();
     s->w = w; s->mass = mass; s->charge = charge; s->mpw0 = mpw0;
-    static uint32_t next_id = 0; s->id = next_id++;
+    s->id = w->n_species++;
     size_t nv = w->g.nv, nc = w->g.nc;
     cudaError_t e;
     double** nodef[] = {&s->den, &s->den_avg, &s->T, &s->n_sum, &s->nuu, &s->nvv, &s->nww};

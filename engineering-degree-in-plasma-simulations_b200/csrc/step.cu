@@ -221,7 +221,7 @@ int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals
     A.dead_list = (unsigned*)s->w->scratch; A.den_fixed = (u64*)s->den_fixed; A.scale = std::ldexp(1.0, s->S); A.macro_count = s->macro_count;
     HeavyArgs H; memset(&H, 0, sizeof(H));
     if (mode & 2) {
-        static uint32_t call = 0; call++;
+        uint32_t call = ++s->n_heavy_calls;
         H.neutrals = emit_of(neutrals); H.spherium = emit_of(spherium); H.sputtering = (sputtering && s->charge != 0) ? 1 : 0;
         H.charge = s->charge; H.mass = s->mass; H.half_world_dt = 0.5 * s->w->dt; H.seed = g_seed; H.stream = rng_stream_id(RNG_HEAVY, s->id, g_rank); H.call = call;
     }
