@@ -99,8 +99,7 @@ int calibrate_scale(picg_species_s* s, bool count_cells) {
         rc = launch_finalize(s); if (rc) return rc;
         s->n_host_valid = false; rc = species_refresh_count(s); if (rc) return rc;   // reads den_max
         i64 mx = s->ctr_host->den_max;
-        if (mx > 0) s->S += 54 - pow2_floor_log(mx);
-        s->S_calibrated = true;
+        if (mx > 0) { s->S += 54 - pow2_floor_log(mx); s->S_calibrated = true; }      // an empty store stays uncalibrated
         return 1;   // caller must deposit again with the calibrated S
     }
     return PICG_OK;

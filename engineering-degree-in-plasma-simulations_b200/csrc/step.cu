@@ -278,7 +278,17 @@ int species_step(picg_species_s* s, bool push, bool heavy, bool deposit, bool fi
     if (push) { rc = compact_dead(s, cap); if (rc) return rc; }
     if (deposit && finalize) {
         rc = launch_finalize(s); if (rc) return rc;
-        if (!s->S_pinned) { s->n_host_valid = false; rc = species_refresh_count(s); if (rc) return rc; return check_scale_after(s); }
+        if (!s->S_pinned) {
+            s->n_host_valid = false; rc = species_refresh_count(s); if (rc) return rc;
+            if (s->ctr_host->den_neg) {                     // overflow (the population grew by orders of magnitude): re-calibrate, deposit once more
+                s->S_calibrated = false;
+                rc = calibrate_scale(s, false); if (rc < 0) return rc;
+                rc = launch_step(s, 4, 0.0, nullptr, nullptr, 0, 0); if (rc) return rc;
+                rc = launch_finalize(s); if (rc) return rc;
+                s->n_host_valid = false; rc = species_refresh_count(s); if (rc) return rc;
+            }
+            return check_scale_after(s);
+        }
     }
     return PICG_OK;
 }

@@ -50,11 +50,16 @@ def _parse_steps(text):
 
 
 @pytest.mark.gpu
-def test_example_matches_ctypes_binding(picgpu):
+@pytest.mark.parametrize("collisions", [False, True])
+def test_example_matches_ctypes_binding(picgpu, collisions):
+    """Without collisions every printed quantity is order-independent and must agree to rounding; with Monte-Carlo
+    collisions the particle order inside a cell (which depends on atomic append order) selects the pairs, so the two
+    runs are two samples of the same process and are compared loosely."""
     num_ts, n_ele, seed = 8, 20000, 777
+    table = os.path.join(HOST, "examples", "data", "Oxygen_momentum_transfer.txt") if collisions else "/nonexistent/table.txt"
     with tempfile.TemporaryDirectory() as d:
         out = subprocess.run([EXAMPLE, "--num_ts", str(num_ts), "--electrons", str(n_ele), "--seed", str(seed), "--dt", "2e-11",
-                              "--table", os.path.join(HOST, "examples", "data", "Oxygen_momentum_transfer.txt")], cwd=d, capture_output=True, text=True, timeout=300)
+                              "--table", table], cwd=d, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     cpp = _parse_steps(out.stdout)
     assert len(cpp) == num_ts + 1                      # World::advanceTime runs num_ts+1 iterations (SURVEY B12)
@@ -75,7 +80,7 @@ def test_example_matches_ctypes_binding(picgpu):
     O.loadParticleBoxThermal(xc, (L[0], L[1], L[2] * 0.8), 2e5 * 5e11 / gap_vol, 300)
     e.loadParticleBoxThermal(xc, (L[0], L[1], L[2] * 0.8), n_ele * 100.0 / gap_vol, 3000)
     tE, tS = np.loadtxt(os.path.join(HOST, "examples", "data", "Oxygen_momentum_transfer.txt"), unpack=True)
-    mcc = pg.MC_MEX_Ionization(O, Op, e, w, tE, tS)
+    mcc = pg.MC_MEX_Ionization(O, Op, e, w, tE, tS) if collisions else None
     sol = pg.PotentialSolver(w, 200, 1.0)
     sol.setReferenceValues(0, 0, 1e20)
     species = [O, Op, e]
@@ -84,7 +89,8 @@ def test_example_matches_ctypes_binding(picgpu):
     sol.solveGS(); sol.computeEF()
     rows = []
     for ts in range(num_ts + 1):
-        mcc.apply(dt)
+        if mcc:
+            mcc.apply(dt)
         for sp in species:
             if sp is e:
                 sp.advanceElectrons(dt)
@@ -99,13 +105,22 @@ def test_example_matches_ctypes_binding(picgpu):
         rows.append(dict(ts=ts, nO=O.getNumParticles(), keO=O.diagnostics()[2], nOp=Op.getNumParticles(), keOp=Op.diagnostics()[2], ne=e.getNumParticles(),
                          kee=e.diagnostics()[2], pe=w.getPE(), phi=w.phi[10, 10, 15], rho=w.rho[10, 10, 15], it=sol.iterations))
     for a, b in zip(cpp, rows):
-        for k in ("ts", "nO", "nOp", "ne", "it"):
-            assert a[k] == b[k], (k, a, b)
-        for k in ("keO", "keOp", "kee", "pe", "phi", "rho"):
-            assert a[k] == pytest.approx(b[k], rel=1e-12, abs=1e-300), (k, a, b)      # reductions use atomics-free fixed trees: equal up to print precision
-    assert rows[-1]["ne"] != rows[0]["ne"] or rows[-1]["nOp"] > 0                      # the plasma actually evolved
+        assert a["ts"] == b["ts"]
+        if not collisions:
+            for k in ("nO", "nOp", "ne", "it"):
+                assert a[k] == b[k], (k, a, b)
+            for k in ("keO", "kee", "pe", "phi", "rho"):
+                assert a[k] == pytest.approx(b[k], rel=1e-10, abs=1e-300), (k, a, b)
+        else:
+            # two samples of a stochastic process whose acceptance ceiling is itself a sampled maximum (Interactions.cpp:670-672,756)
+            assert abs(a["nO"] - b["nO"]) <= 0.02 * b["nO"] and abs(a["ne"] - b["ne"]) <= 0.1 * b["ne"], (a, b)
+            assert a["kee"] == pytest.approx(b["kee"], rel=0.25), (a, b)
+    if collisions:
+        assert cpp[-1]["nOp"] > 0 and rows[-1]["nOp"] > 0 and 1 / 3 < cpp[-1]["nOp"] / rows[-1]["nOp"] < 3
+    assert rows[-1]["ne"] < rows[0]["ne"] or rows[-1]["nOp"] > 0                       # the plasma evolved (absorption / ionisation)
     for o in (mcc, sol, O, Op, e, w):
-        o.close()
+        if o:
+            o.close()
 
 
 @pytest.mark.gpu
