@@ -137,13 +137,6 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- our arm
-class CudaArray:
-    """Zero-copy torch view of a device buffer owned by libpicgpu.so (for torch.distributed collectives)."""
-
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -195,19 +188,17 @@ def run_ours(args):
         mcc = pg.MC_MEX_Ionization(neu, ion, ele, w, E, sg)
 
     # a common fixed-point scale on every rank (the all-reduce sums raw int64 accumulators)
+    mg = importlib.import_module(PKG + ".multigpu")
+
+    def reduce_min(v):
+        t = torch.tensor([v], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item())
+
     for sp in order:
         sp.computeNumberDensity()
-        S = sp.densityScale()
-        if world > 1:
-            t = torch.tensor([S], device="cuda", dtype=torch.int32)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            S = int(t.item()) - int(np.ceil(np.log2(world)))
-        sp.setDensityScale(S)
-    fixed_views = {}
-    if world > 1:
-        for sp in order:
-            ptr, nbytes = sp.device_ptr(pg.SF_DEN_FIXED)
-            fixed_views[sp.name] = torch.as_tensor(CudaArray(ptr, nbytes // 8, "<i8"), device="cuda")
+        sp.setDensityScale(mg.common_scale(sp.densityScale(), world, reduce_min))
+    fixed_views = {sp.name: mg.fixed_view(torch, sp, pg.SF_DEN_FIXED) for sp in order} if world > 1 else {}
     setup_s = time.time() - t0
 
     counts = {}
