@@ -77,6 +77,10 @@ struct picg_species_s {
     // cell-sorted layout
     unsigned* cell_start = nullptr;    // nc+1 entries, valid when sorted_valid
     bool sorted_valid = false;         // cell_start describes the current particle order exactly
+    // exact per-cell lists on top of a stale partition (sort.cu: movers)
+    unsigned *home = nullptr, *in_start = nullptr, *out_start = nullptr, *mv_in = nullptr;
+    size_t home_cap = 0, lists_cap = 0, mv_cap = 0, mv_stride = 0;
+    bool lists_valid = false;          // cell_start + in/out mover lists describe the current cell membership exactly
     bool part_valid = false;           // cell_start is a partition of [0, part_n) (possibly stale: particles may have drifted)
     size_t part_n = 0;                 // upper bound of the particle count at the last sort
 };

@@ -14,7 +14,7 @@
 
 using namespace picg;
 
-namespace picg { int sort_species(picg_species_s* s); }
+namespace picg { int sort_species(picg_species_s* s); int species_exact_lists(picg_species_s* s); }
 
 #define MCC_EXTRA 16          // split-off neutrals created in this call that remain selectable within the cell (:699-701)
 
@@ -23,6 +23,32 @@ struct MccParams {
     int n_tab; const double* tab_E; const double* tab_s;
 };
 struct Store { double* a[7]; SpeciesCounters* ctr; u64 cap; };
+// Exact per-cell particle lists on top of a (possibly stale) partition, see sort.cu:
+//   list(c) = slots [cs[c], cs[c+1]) minus the out-movers of c, followed by the in-movers of c.
+struct CellLists { const unsigned* cs; const unsigned* in_start; const unsigned* out_start; const unsigned* mv_in; const unsigned* mv_out; };
+struct CellView { unsigned h0, n_stay, o0, o1, i0; int np; };
+__device__ __forceinline__ CellView cell_view(const CellLists& L, int c) {
+    CellView v;
+    v.h0 = L.cs[c]; unsigned h1 = L.cs[c + 1];
+    v.o0 = L.out_start[c]; v.o1 = L.out_start[c + 1];
+    v.i0 = L.in_start[c]; unsigned i1 = L.in_start[c + 1];
+    v.n_stay = (h1 - v.h0) - (v.o1 - v.o0);
+    v.np = (int)(v.n_stay + (i1 - v.i0));
+    return v;
+}
+// slot of the a-th particle of the list (0 <= a < np)
+__device__ __forceinline__ unsigned cell_pick(const CellLists& L, const CellView& v, int a) {
+    if ((unsigned)a >= v.n_stay) return L.mv_in[v.i0 + ((unsigned)a - v.n_stay)];
+    unsigned slot = v.h0 + (unsigned)a;
+    if (v.o1 == v.o0) return slot;
+    for (;;) {                                        // a-th slot of the home range that is not an out-mover (the out list is tiny and unordered)
+        unsigned k = 0;
+        for (unsigned o = v.o0; o < v.o1; o++) k += (L.mv_out[o] <= slot);
+        unsigned nxt = v.h0 + (unsigned)a + k;
+        if (nxt == slot) return slot;
+        slot = nxt;
+    }
+}
 
 // evaluateSigmaColl (:541-558): std::map lower_bound + linear interpolation, clamped to the end values
 __host__ __device__ __forceinline__ double sigma_coll(const MccParams& P, double E) {
@@ -91,15 +117,15 @@ __device__ __forceinline__ void atomic_max_pos_double(double* addr, double v) { 
 }
 
 // stats: [0] candidates [1] collisions [2] ionisations [3] skipped (electron heavier than neutral)
-__global__ void __launch_bounds__(128) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, const unsigned* __restrict__ cs_n,
-                                             const unsigned* __restrict__ cs_e, double* __restrict__ wsv, u64* __restrict__ stats, double dt,
+__global__ void __launch_bounds__(128) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, CellLists Ln,
+                                             CellLists Le, double* __restrict__ wsv, u64* __restrict__ stats, double dt,
                                              uint64_t seed, uint32_t stream, uint32_t call) {
     const double W_max = wsv[0];
     u64 n_cand = 0, n_coll = 0, n_ion = 0, n_skip = 0; double step_max = 0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.nc; c += gridDim.x * blockDim.x) {
-        unsigned e0 = cs_e[c]; int np_e = (int)(cs_e[c + 1] - e0);
+        CellView ve = cell_view(Le, c); int np_e = ve.np;
         if (np_e <= 0) continue;
-        unsigned n0 = cs_n[c]; int np_n0 = (int)(cs_n[c + 1] - n0);
+        CellView vn = cell_view(Ln, c); int np_n0 = vn.np;
         if (np_n0 <= 0) continue;
         int np_n = np_n0;
         double frac = np_n * np_e * W_max * dt * P.inv_dv * P.rank_scale;               // :646 (x G ranks)
@@ -111,10 +137,10 @@ __global__ void __launch_bounds__(128) k_mcc(Grid g, MccParams P, Store neu, Sto
         for (int t = 0; t < n_groups; t++) {
             int a = (int)(r.next() * np_n);                                                // rnd(0,np) = 0 + rnd()*(np-0)
             int b = (int)(r.next() * np_e);
-            u64 pn = a < np_n0 ? (u64)n0 + a : (u64)extra[a - np_n0];
-            u64 pe = (u64)e0 + b;
-            double vn[3] = {neu.a[3][pn], neu.a[4][pn], neu.a[5][pn]}, ve[3] = {ele.a[3][pe], ele.a[4][pe], ele.a[5][pe]};
-            double d[3] = {vn[0] - ve[0], vn[1] - ve[1], vn[2] - ve[2]};
+            u64 pn = a < np_n0 ? (u64)cell_pick(Ln, vn, a) : (u64)extra[a - np_n0];
+            u64 pe = (u64)cell_pick(Le, ve, b);
+            double vn_[3] = {neu.a[3][pn], neu.a[4][pn], neu.a[5][pn]}, ve_[3] = {ele.a[3][pe], ele.a[4][pe], ele.a[5][pe]};
+            double d[3] = {vn_[0] - ve_[0], vn_[1] - ve_[1], vn_[2] - ve_[2]};
             double v_rel = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
             double E_rel = P.E_rel_eV * v_rel * v_rel;
             double s_coll = sigma_coll(P, E_rel);
@@ -128,15 +154,15 @@ __global__ void __launch_bounds__(128) k_mcc(Grid g, MccParams P, Store neu, Sto
                 if (Wn > We) {                                                             // split the neutral (:684-703)
                     neu.a[6][pn] = Wn - We;
                     double vnew[3] = {0, 0, 0};
-                    bool ionised = collide(r, P, vn, ve, vnew, s_coll);
-                    ele.a[3][pe] = ve[0]; ele.a[4][pe] = ve[1]; ele.a[5][pe] = ve[2];
+                    bool ionised = collide(r, P, vn_, ve_, vnew, s_coll);
+                    ele.a[3][pe] = ve_[0]; ele.a[4][pe] = ve_[1]; ele.a[5][pe] = ve_[2];
                     double pos[3] = {neu.a[0][pn], neu.a[1][pn], neu.a[2][pn]};
                     if (ionised) {
                         n_ion++;
-                        append(ion, pos, vn, Wl);                                          // no half-step rewind (:694-695)
+                        append(ion, pos, vn_, Wl);                                         // no half-step rewind (:694-695)
                         append(ele, pos, vnew, Wl);
                     } else {
-                        long long idx = append(neu, pos, vn, We);                          // split-off neutral of the electron's weight
+                        long long idx = append(neu, pos, vn_, We);                         // split-off neutral of the electron's weight
                         if (idx >= 0 && n_extra < MCC_EXTRA) { extra[n_extra++] = idx; np_n++; }
                     }
                 } else if (Wn < We) {
@@ -159,11 +185,11 @@ __global__ void __launch_bounds__(128) k_mcc(Grid g, MccParams P, Store neu, Sto
 // W_sigma_v_rel_max <- max sampled value of this step, only if a collision happened (:751-756)
 __global__ void k_mcc_finish(double* wsv, const u64* stats) { if (stats[1]) wsv[0] = wsv[1]; }
 // upper bound on appended particles: sum over cells of n_groups
-__global__ void __launch_bounds__(256) k_mcc_count(Grid g, const unsigned* __restrict__ cs_n, const unsigned* __restrict__ cs_e, const double* __restrict__ wsv,
+__global__ void __launch_bounds__(256) k_mcc_count(Grid g, CellLists Ln, CellLists Le, const double* __restrict__ wsv,
                                                    double dt, double inv_dv, double rank_scale, u64* __restrict__ total) {
     u64 acc = 0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.nc; c += gridDim.x * blockDim.x) {
-        int np_e = (int)(cs_e[c + 1] - cs_e[c]), np_n = (int)(cs_n[c + 1] - cs_n[c]);
+        int np_e = cell_view(Le, c).np, np_n = cell_view(Ln, c).np;
         if (np_e <= 0 || np_n <= 0) continue;
         int n_groups = (int)(np_n * np_e * wsv[0] * dt * inv_dv * rank_scale + 0.5);
         if (n_groups > np_n) n_groups = np_n - 1;
@@ -190,6 +216,14 @@ static MccParams make_params(const picg_mcc_s* m) {
     P.rank_scale = (double)g_world_size;
     P.n_tab = m->n_table; P.tab_E = m->tab_E; P.tab_s = m->tab_s;
     return P;
+}
+static CellLists lists_of(picg_species_s* s) {
+    CellLists L; L.cs = s->cell_start; L.in_start = s->in_start; L.out_start = s->out_start; L.mv_in = s->mv_in; L.mv_out = s->mv_in ? s->mv_in + s->mv_stride : nullptr;
+    return L;
+}
+// per-cell list lengths as the collision kernel sees them (debug / tests): must equal computeMacroParticlesCount
+__global__ void k_list_counts(Grid g, CellLists L, double* __restrict__ out) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.nc; c += gridDim.x * blockDim.x) out[c] = (double)cell_view(L, c).np;
 }
 static Store store_of(picg_species_s* s) { Store st; for (int c = 0; c < 7; c++) st.a[c] = s->a[c]; st.ctr = s->ctr; st.cap = s->cap; return st; }
 
@@ -263,14 +297,14 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     picg_species_s *neu = m->neu, *ele = m->ele, *ion = m->ion;
     int rc;
     // both collision partners must be exactly cell-sorted, as in the reference (:602-613)
-    if (!neu->sorted_valid) { rc = sort_species(neu); if (rc) return rc; }
-    if (!ele->sorted_valid) { rc = sort_species(ele); if (rc) return rc; }
+    rc = species_exact_lists(neu); if (rc) return rc;          // no-op when sorted; mover pass on a stale partition; full sort otherwise
+    rc = species_exact_lists(ele); if (rc) return rc;
     MccParams P = make_params(m);
     const Grid& g = m->w->g;
     // capacity for the appends: one pass over the cells gives the total number of candidates
     CUDA_TRY(cudaMemsetAsync(m->stats, 0, 64, g_stream));
     int cgrid = std::max(1, std::min(div_up(g.nc, 256), g_sm_count * 8));
-    LAUNCH(K_MCC, k_mcc_count, cgrid, 256, 0, g, neu->cell_start, ele->cell_start, m->wsv, dt, P.inv_dv, P.rank_scale, m->stats + 4); CHECK_LAUNCH();
+    LAUNCH(K_MCC, k_mcc_count, cgrid, 256, 0, g, lists_of(neu), lists_of(ele), m->wsv, dt, P.inv_dv, P.rank_scale, m->stats + 4); CHECK_LAUNCH();
     u64 host_stats[8];
     CUDA_TRY(cudaMemcpyAsync(host_stats, m->stats, 64, cudaMemcpyDeviceToHost, g_stream));
     rc = species_refresh_count(neu); if (rc) return rc;        // synchronises
@@ -284,7 +318,7 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
         double zero = 0; CUDA_TRY(cudaMemcpyAsync(m->wsv + 1, &zero, 8, cudaMemcpyHostToDevice, g_stream));
         m->step++;
         int grid = std::max(1, std::min(div_up(g.nc, 128), g_sm_count * 16));
-        LAUNCH(K_MCC, k_mcc, grid, 128, 0, g, P, store_of(neu), store_of(ele), store_of(ion), neu->cell_start, ele->cell_start, m->wsv, m->stats, dt,
+        LAUNCH(K_MCC, k_mcc, grid, 128, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), m->wsv, m->stats, dt,
                g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
         CHECK_LAUNCH();
         LAUNCH(K_MCC, k_mcc_finish, 1, 1, 0, m->wsv, m->stats); CHECK_LAUNCH();
@@ -293,7 +327,7 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
         rc = species_refresh_count(neu); if (rc) return rc;
         rc = species_refresh_count(ele); if (rc) return rc;
         rc = species_refresh_count(ion); if (rc) return rc;
-        if (host_stats[1]) { neu->sorted_valid = false; ele->sorted_valid = false; ion->sorted_valid = false; }   // :751-754
+        if (host_stats[1]) { neu->sorted_valid = false; neu->lists_valid = false; ele->sorted_valid = false; ele->lists_valid = false; ion->sorted_valid = false; ion->lists_valid = false; }   // :751-754
     } else {
         m->step++;
         host_stats[0] = host_stats[1] = host_stats[2] = 0;
@@ -303,6 +337,20 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
         double wmax; CUDA_TRY(cudaMemcpyAsync(&wmax, m->wsv, 8, cudaMemcpyDeviceToHost, g_stream)); CUDA_TRY(cudaStreamSynchronize(g_stream));
         out->w_sigma_v_max = wmax;
     }
+    return PICG_OK;
+}
+
+// debug / tests: lengths of the exact per-cell lists of `which` (0 neutrals, 1 electrons), cells in Field order
+int picg_mcc_list_counts(picg_mcc_t m, int which, double* host) {
+    REQUIRE_DEVICE(); REQUIRE_ARG(m && host && (which == 0 || which == 1), "picg_mcc_list_counts: bad argument");
+    picg_species_s* s = which ? m->ele : m->neu;
+    int rc = species_exact_lists(s); if (rc) return rc;
+    const Grid& g = m->w->g;
+    rc = ensure_scratch(m->w, (size_t)g.nc * 8 + 64); if (rc) return rc;
+    // the mover arrays live in species-owned buffers, not in the scratch arena, so the arena is free here
+    LAUNCH(K_MISC, k_list_counts, std::min(div_up(g.nc, 256), 2048), 256, 0, g, lists_of(s), (double*)m->w->scratch); CHECK_LAUNCH();
+    CUDA_TRY(cudaMemcpyAsync(host, m->w->scratch, (size_t)g.nc * 8, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
     return PICG_OK;
 }
 

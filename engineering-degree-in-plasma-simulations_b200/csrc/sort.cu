@@ -39,12 +39,12 @@ __device__ __forceinline__ void block_range(u64 n, int nblocks, u64& begin, u64&
     end = min(n, begin + per * SORT_TILE);
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_upsweep(const SpeciesCounters* ctr, const unsigned* __restrict__ keys, int shift,
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_upsweep(const u64* __restrict__ n_ptr, const unsigned* __restrict__ keys, int shift,
                                                                unsigned* __restrict__ counts /*[256][gridDim.x]*/) {
     __shared__ unsigned hist[SORT_WARPS][256];
     for (int t = threadIdx.x; t < SORT_WARPS * 256; t += SORT_THREADS) (&hist[0][0])[t] = 0;
     __syncthreads();
-    u64 begin, end; block_range(ctr->n, gridDim.x, begin, end);
+    u64 begin, end; block_range(*n_ptr, gridDim.x, begin, end);
     const int warp = threadIdx.x >> 5;
     for (u64 p = begin + threadIdx.x; p < end; p += SORT_THREADS) atomicAdd(&hist[warp][(keys[p] >> shift) & 255u], 1u);
     __syncthreads();
@@ -82,14 +82,14 @@ __global__ void __launch_bounds__(1024) k_sort_scan(unsigned* __restrict__ count
     }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_downsweep(const SpeciesCounters* ctr, const unsigned* __restrict__ keys_in,
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_downsweep(const u64* __restrict__ n_ptr, const unsigned* __restrict__ keys_in,
                                                                  const unsigned* __restrict__ idx_in, unsigned* __restrict__ keys_out,
                                                                  unsigned* __restrict__ idx_out, int shift, const unsigned* __restrict__ counts) {
     __shared__ unsigned wcount[SORT_WARPS][256];     // per-warp digit counts of the current tile, then exclusive warp offsets
     __shared__ unsigned running[256];                // block's running global offset per digit
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int d = threadIdx.x; d < 256; d += SORT_THREADS) running[d] = counts[(size_t)d * gridDim.x + blockIdx.x];
-    u64 begin, end; block_range(ctr->n, gridDim.x, begin, end);
+    u64 begin, end; block_range(*n_ptr, gridDim.x, begin, end);
     for (u64 tile = begin; tile < end; tile += SORT_TILE) {
         for (int t = threadIdx.x; t < SORT_WARPS * 256; t += SORT_THREADS) (&wcount[0][0])[t] = 0;
         __syncthreads();
@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(256) k_sort_permute(const SpeciesCounters* ctr
 }
 
 // cell_start[c] = first sorted position whose key >= c ; cell_start[nc] = n
-__global__ void __launch_bounds__(256) k_cell_start(const SpeciesCounters* ctr, const unsigned* __restrict__ keys, int nc, unsigned* __restrict__ cell_start) {
-    const u64 n = ctr->n;
+__global__ void __launch_bounds__(256) k_cell_start(const u64* __restrict__ n_ptr, const unsigned* __restrict__ keys, int nc, unsigned* __restrict__ cell_start) {
+    const u64 n = *n_ptr;
     for (u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x; p <= n; p += (u64)gridDim.x * blockDim.x) {
         int lo = (p == 0) ? 0 : (int)keys[p - 1] + 1;
         int hi = (p == n) ? nc : (int)keys[p];
@@ -149,7 +149,86 @@ __global__ void __launch_bounds__(256) k_cell_start(const SpeciesCounters* ctr, 
     }
 }
 
+// ---------------------------------------------------------------- movers (exact cell lists from a stale partition)
+// After a sort every slot has a home cell (home[p]).  Later pushes / appends / hole filling make some slots hold a
+// particle whose current cell differs from the slot's home: the movers.  k_find_movers lists them; sorted once by their
+// current cell and once by their home cell they turn the stale partition into exact per-cell lists for MC collisions:
+//   list(c) = home range of c  minus  movers whose home is c  plus  movers whose current cell is c.
+__global__ void __launch_bounds__(256) k_find_movers(Grid g, const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pz,
+                                                     const unsigned* __restrict__ home, const u64* __restrict__ n_ptr, const unsigned* __restrict__ part_n_ptr,
+                                                     u64* __restrict__ count, u64 cap, unsigned* __restrict__ m_slot, unsigned* __restrict__ m_cell,
+                                                     unsigned* __restrict__ m_home) {
+    const u64 n = *n_ptr, part_n = *part_n_ptr;
+    const int lane = threadIdx.x & 31;
+    for (u64 p0 = (blockIdx.x * (u64)blockDim.x + threadIdx.x) - lane; p0 < n; p0 += (u64)gridDim.x * blockDim.x) {
+        u64 p = p0 + lane;
+        bool mover = false; unsigned cell = 0, hm = (unsigned)g.nc;          // home == nc: no home (appended after the sort)
+        if (p < n) {
+            int i = min(max((int)x_to_l(px[p], g.x0[0], g.inv_dx[0]), 0), g.ci - 1);
+            int j = min(max((int)x_to_l(py[p], g.x0[1], g.inv_dx[1]), 0), g.cj - 1);
+            int k = min(max((int)x_to_l(pz[p], g.x0[2], g.inv_dx[2]), 0), g.ck - 1);
+            cell = (unsigned)cell_of(g, i, j, k);
+            if (p < part_n) { hm = home[p]; mover = hm != cell; } else mover = true;       // appended after the sort: no home
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, mover);
+        if (mask) {
+            u64 base = 0; int leader = __ffs(mask) - 1;
+            if (lane == leader) base = atomicAdd(count, (u64)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            u64 dst = base + __popc(mask & ((1u << lane) - 1));
+            if (mover && dst < cap) { m_slot[dst] = (unsigned)p; m_cell[dst] = cell; m_home[dst] = hm; }
+        }
+    }
+}
+// slots of the partition that lie beyond the live count (particles died since the sort) also leave their home lists
+__global__ void __launch_bounds__(256) k_find_vacated(const unsigned* __restrict__ home, const u64* __restrict__ n_ptr, const unsigned* __restrict__ part_n_ptr,
+                                                      u64* __restrict__ count, u64 cap, unsigned* __restrict__ m_slot, unsigned* __restrict__ m_home) {
+    const u64 n = *n_ptr, part_n = *part_n_ptr;
+    for (u64 p = n + blockIdx.x * (u64)blockDim.x + threadIdx.x; p < part_n; p += (u64)gridDim.x * blockDim.x) {
+        u64 dst = atomicAdd(count, 1ull);
+        if (dst < cap) { m_slot[dst] = (unsigned)p; m_home[dst] = home[p]; }
+    }
+}
+__global__ void k_copy_u32(const u64* __restrict__ n_ptr, const unsigned* __restrict__ in, unsigned* __restrict__ out) {
+    const u64 n = *n_ptr;
+    for (u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x; p < n; p += (u64)gridDim.x * blockDim.x) out[p] = in[p];
+}
+__global__ void k_iota_u32(const u64* __restrict__ n_ptr, unsigned* __restrict__ out) {
+    const u64 n = *n_ptr;
+    for (u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x; p < n; p += (u64)gridDim.x * blockDim.x) out[p] = (unsigned)p;
+}
+__global__ void k_gather_u32(const u64* __restrict__ n_ptr, const unsigned* __restrict__ idx, const unsigned* __restrict__ in, unsigned* __restrict__ out) {
+    const u64 n = *n_ptr;
+    for (u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x; p < n; p += (u64)gridDim.x * blockDim.x) out[p] = in[idx[p]];
+}
+__global__ void k_clamp_u64(u64* v, u64 cap) { if (*v > cap) *v = cap; }
+
 namespace picg {
+double g_mover_fraction = 0.10;     // above this fraction of movers the store is re-sorted instead of patched
+// Stable LSD radix sort of (keys, vals) pairs; n is read on the device.  Returns the buffers that hold the result.
+static int radix_sort_pairs(const u64* n_ptr, size_t n_upper, int key_bits, unsigned*& keysA, unsigned*& valsA, unsigned*& keysB, unsigned*& valsB,
+                            unsigned* counts, int nblocks) {
+    int passes = (key_bits + 7) / 8;
+    for (int pass = 0; pass < passes; pass++) {
+        int shift = pass * 8;
+        LAUNCH(K_SORT_HIST, k_sort_upsweep, nblocks, SORT_THREADS, 0, n_ptr, keysA, shift, counts); CHECK_LAUNCH();
+        LAUNCH(K_SORT_SCAN, k_sort_scan, 1, 1024, 0, counts, 256 * nblocks); CHECK_LAUNCH();
+        LAUNCH(K_SORT_SCATTER, k_sort_downsweep, nblocks, SORT_THREADS, 0, n_ptr, keysA, valsA, keysB, valsB, shift, counts); CHECK_LAUNCH();
+        std::swap(keysA, keysB); std::swap(valsA, valsB);
+    }
+    (void)n_upper;
+    return PICG_OK;
+}
+static int key_bits_of(const Grid& g) { int bits = 1; while ((1ull << bits) < (u64)g.nc) bits++; return bits; }
+
+static int ensure_u32(unsigned*& p, size_t& cap, size_t want) {
+    if (cap >= want) return PICG_OK;
+    if (p) { cudaStreamSynchronize(g_stream); cudaFree(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaMalloc(&p, want * 4);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(u32)", __FILE__, __LINE__);
+    cap = want; return PICG_OK;
+}
+
 // Sorts species s by cell.  Scratch: keysA | keysB | idxA | idxB | counts.
 int sort_species(picg_species_s* s) {
     const Grid& g = s->w->g;
@@ -159,32 +238,91 @@ int sort_species(picg_species_s* s) {
     size_t capa = (cap + 63) & ~(size_t)63;
     size_t bytes = capa * 16 + (size_t)256 * nblocks * 4 + 256;
     int rc = ensure_scratch(s->w, bytes); if (rc) return rc;
+    rc = ensure_u32(s->home, s->home_cap, s->cap); if (rc) return rc;
+    rc = ensure_u32(s->in_start, s->lists_cap, (size_t)g.nc + 1); if (rc) return rc;
+    { size_t c2 = 0; if (!s->out_start) { rc = ensure_u32(s->out_start, c2, (size_t)g.nc + 1); if (rc) return rc; } }
     unsigned* keysA = (unsigned*)s->w->scratch; unsigned* keysB = keysA + capa;
     unsigned* idxA = keysB + capa; unsigned* idxB = idxA + capa;
     unsigned* counts = idxB + capa;
+    const u64* n_ptr = &s->ctr->n;
     int pgrid = std::max(1, std::min(div_up(cap, 256), g_sm_count * 8));
     LAUNCH(K_SORT_KEYS, k_sort_keys, pgrid, 256, 0, g, s->a[0], s->a[1], s->a[2], s->ctr, keysA, idxA); CHECK_LAUNCH();
-    int bits = 1; while ((1ull << bits) < (u64)g.nc) bits++;
-    int passes = (bits + 7) / 8;
-    for (int pass = 0; pass < passes; pass++) {
-        int shift = pass * 8;
-        LAUNCH(K_SORT_HIST, k_sort_upsweep, nblocks, SORT_THREADS, 0, s->ctr, keysA, shift, counts); CHECK_LAUNCH();
-        LAUNCH(K_SORT_SCAN, k_sort_scan, 1, 1024, 0, counts, 256 * nblocks); CHECK_LAUNCH();
-        LAUNCH(K_SORT_SCATTER, k_sort_downsweep, nblocks, SORT_THREADS, 0, s->ctr, keysA, idxA, keysB, idxB, shift, counts); CHECK_LAUNCH();
-        std::swap(keysA, keysB); std::swap(idxA, idxB);
-    }
+    rc = radix_sort_pairs(n_ptr, cap, key_bits_of(g), keysA, idxA, keysB, idxB, counts, nblocks); if (rc) return rc;
     // gather every particle array through the index list into the spare array, then rotate pointers
     for (int c = 0; c < 7; c++) {
         LAUNCH(K_SORT_PERMUTE, k_sort_permute, pgrid, 256, 0, s->ctr, idxA, s->a[c], s->spare); CHECK_LAUNCH();
         std::swap(s->a[c], s->spare);
     }
-    LAUNCH(K_CELL_START, k_cell_start, pgrid, 256, 0, s->ctr, keysA, g.nc, s->cell_start); CHECK_LAUNCH();
-    s->sorted_valid = true; s->part_valid = true; s->part_n = cap;
+    LAUNCH(K_CELL_START, k_cell_start, pgrid, 256, 0, n_ptr, keysA, g.nc, s->cell_start); CHECK_LAUNCH();
+    LAUNCH(K_CELL_START, k_copy_u32, pgrid, 256, 0, n_ptr, keysA, s->home); CHECK_LAUNCH();                 // home cell of every slot
+    CUDA_TRY(cudaMemsetAsync(s->in_start, 0, ((size_t)g.nc + 1) * 4, g_stream));                           // no movers right after a sort
+    CUDA_TRY(cudaMemsetAsync(s->out_start, 0, ((size_t)g.nc + 1) * 4, g_stream));
+    s->sorted_valid = true; s->part_valid = true; s->part_n = cap; s->lists_valid = true;
+    return PICG_OK;
+}
+
+// Makes the per-cell lists of s exact for its current particle positions: nothing to do if the store is exactly sorted,
+// a mover pass over a stale partition when few particles changed cell, a full sort otherwise.
+int species_exact_lists(picg_species_s* s) {
+    if (s->sorted_valid || s->lists_valid) return PICG_OK;
+    int rc = species_refresh_count(s); if (rc) return rc;
+    size_t n = s->n_host;
+    const double max_frac = g_mover_fraction;
+    if (!s->part_valid || n < 4096 || max_frac <= 0) return sort_species(s);
+    const Grid& g = s->w->g;
+    size_t mcap = (size_t)(max_frac * (double)n) + 1024;
+    // mover arrays: slot/cell/home triples plus radix ping-pong buffers, all in the scratch arena
+    size_t mcapa = (mcap + 63) & ~(size_t)63;
+    int nblocks = std::max(1, std::min(div_up(mcap, SORT_TILE), g_sm_count * 4));
+    size_t bytes = mcapa * 4 * 7 + (size_t)256 * nblocks * 4 + 256;
+    rc = ensure_scratch(s->w, bytes); if (rc) return rc;
+    rc = ensure_u32(s->mv_in, s->mv_cap, mcapa * 2); if (rc) return rc;     // [0,mcapa): slots ordered by current cell, [mcapa, 2 mcapa): slots ordered by home cell
+    s->mv_stride = mcapa;
+    unsigned* m_slot = (unsigned*)s->w->scratch; unsigned* m_cell = m_slot + mcapa; unsigned* m_home = m_cell + mcapa;
+    unsigned* kB = m_home + mcapa; unsigned* vA = kB + mcapa; unsigned* vB = vA + mcapa; unsigned* tmp = vB + mcapa;
+    unsigned* counts = tmp + mcapa;
+    u64* cnt = (u64*)&s->ctr->pad;                                           // device-side mover count
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 8, g_stream));
+    int pgrid = std::max(1, std::min(div_up(std::max<size_t>(n, 1), 256), g_sm_count * 8));
+    LAUNCH(K_SORT_KEYS, k_find_movers, pgrid, 256, 0, g, s->a[0], s->a[1], s->a[2], s->home, &s->ctr->n, s->cell_start + g.nc, cnt, (u64)mcap, m_slot, m_cell, m_home);
+    CHECK_LAUNCH();
+    u64 n_live_movers = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n_live_movers, cnt, 8, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    if (n_live_movers > mcap) return sort_species(s);                        // too stale: periodic full radix sort
+    int mgrid = std::max(1, std::min(div_up(std::max<size_t>((size_t)n_live_movers, 1), 256), g_sm_count * 4));
+    int bits = key_bits_of(g);
+    // (1) in-lists: live movers ordered by their current cell
+    {
+        unsigned *ka = m_cell, *kb = kB, *va = vA, *vb = vB;
+        LAUNCH(K_SORT_KEYS, k_iota_u32, mgrid, 256, 0, cnt, va); CHECK_LAUNCH();
+        LAUNCH(K_SORT_KEYS, k_copy_u32, mgrid, 256, 0, cnt, m_cell, tmp); CHECK_LAUNCH();          // keep m_cell intact? (not needed later) -> sort a copy
+        ka = tmp;
+        rc = radix_sort_pairs(cnt, mcap, bits, ka, va, kb, vb, counts, nblocks); if (rc) return rc;
+        LAUNCH(K_CELL_START, k_cell_start, mgrid, 256, 0, cnt, ka, g.nc, s->in_start); CHECK_LAUNCH();
+        LAUNCH(K_SORT_PERMUTE, k_gather_u32, mgrid, 256, 0, cnt, va, m_slot, s->mv_in); CHECK_LAUNCH();
+    }
+    // (2) out-lists: every slot whose particle left its home cell (live movers with a home + slots vacated beyond n), ordered by home
+    {
+        // movers without a home (appended) carry home = nc; they sort to the end and fall outside every cell's range
+        size_t vac_upper = s->part_n > n ? s->part_n - n : 0;
+        if (n_live_movers + vac_upper > mcap) return sort_species(s);
+        if (vac_upper) { LAUNCH(K_SORT_KEYS, k_find_vacated, std::max(1, std::min(div_up(vac_upper, 256), g_sm_count * 4)), 256, 0, s->home, &s->ctr->n, s->cell_start + g.nc, cnt, (u64)mcap, m_slot, m_home); CHECK_LAUNCH(); }
+        unsigned *ka = m_home, *kb = kB, *va = vA, *vb = vB;
+        int mgrid2 = std::max(1, std::min(div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), 256), g_sm_count * 4));
+        LAUNCH(K_SORT_KEYS, k_iota_u32, mgrid2, 256, 0, cnt, va); CHECK_LAUNCH();
+        int hbits = 1; while ((1ull << hbits) < (u64)g.nc + 1) hbits++;
+        rc = radix_sort_pairs(cnt, mcap, hbits, ka, va, kb, vb, counts, nblocks); if (rc) return rc;
+        LAUNCH(K_CELL_START, k_cell_start, mgrid2, 256, 0, cnt, ka, g.nc, s->out_start); CHECK_LAUNCH();
+        LAUNCH(K_SORT_PERMUTE, k_gather_u32, mgrid2, 256, 0, cnt, va, m_slot, s->mv_in + mcapa); CHECK_LAUNCH();
+    }
+    s->lists_valid = true;
     return PICG_OK;
 }
 }  // namespace picg
 
 extern "C" {
+int picg_set_mover_fraction(double f) { REQUIRE_ARG(f >= 0 && f <= 0.5, "picg_set_mover_fraction: 0 <= f <= 0.5"); g_mover_fraction = f; return PICG_OK; }
 int picg_species_sort(picg_species_t s) {
     REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_species_sort: null species");
     return sort_species(s);

@@ -71,6 +71,10 @@ def set_rank(rank, world_size):
     _chk(lib().picg_set_rank(int(rank), int(world_size)))
 
 
+def set_mover_fraction(f):
+    _chk(lib().picg_set_mover_fraction(C.c_double(f)))
+
+
 def synchronize():
     _chk(lib().picg_synchronize())
 
@@ -381,6 +385,11 @@ class MC_MEX_Ionization:
 
     def setWsvMax(self, v):
         _chk(lib().picg_mcc_set_wsv_max(self.h, C.c_double(v)))
+
+    def listCounts(self, which, world):
+        out = np.empty((world.ni - 1, world.nj - 1, world.nk - 1), dtype=np.float64)
+        _chk(lib().picg_mcc_list_counts(self.h, int(which), _dp(out)))
+        return out
 
     def sigma(self, E_eV):
         e = np.ascontiguousarray(E_eV, dtype=np.float64)

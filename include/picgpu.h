@@ -141,7 +141,11 @@ PICG_API int picg_species_clear_samples(picg_species_t s);
 PICG_API int picg_species_update_averages(picg_species_t s);
 /* Species::computeMacroParticlesCount  Species.cpp:813-819 */
 PICG_API int picg_species_count_per_cell(picg_species_t s);
-/* Species::sortIndexes  Species.cpp:905-929 -> device: cell-sorted SoA layout + cell_start[] */
+/* Species::sortIndexes  Species.cpp:905-929 -> device: cell-sorted SoA layout + cell_start[].
+ * Between sorts the exact per-cell lists that MC collisions need are kept up to date by listing the particles that
+ * changed cell ("movers"); when more than `f` of a species moved, it is re-sorted (periodic radix sort).  f = 0 forces a
+ * full sort whenever the order is stale (the reference re-sorts every step). */
+PICG_API int picg_set_mover_fraction(double f);
 PICG_API int picg_species_sort(picg_species_t s);
 /* diagnostics: getMicroCount, getMomentum, getKE  Species.cpp:726-755 */
 PICG_API int picg_species_diagnostics(picg_species_t s, double* micro_count, double momentum[3], double* ke);
@@ -186,6 +190,8 @@ typedef struct { uint64_t candidates, collisions, ionizations; double w_sigma_v_
 /* Interaction::apply(dt) -> MC_MEX_Ionization::apply_vector_indexes  Interactions.cpp:567-762 */
 PICG_API int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* stats /*may be NULL*/);
 PICG_API int picg_mcc_set_wsv_max(picg_mcc_t m, double v);
+/* debug / tests: lengths of the exact per-cell particle lists the collision kernel uses (0 neutrals, 1 electrons) */
+PICG_API int picg_mcc_list_counts(picg_mcc_t m, int which, double* cells);
 PICG_API int picg_mcc_sigma(picg_mcc_t m, int n, const double* E_eV, double* sigma_coll, double* sigma_ion); /* evaluateSigmaColl/Ion :541-566 */
 
 /* ------------------------------------------------------------------- Source */

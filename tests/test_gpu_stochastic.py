@@ -85,6 +85,48 @@ def test_mc_ionization_ensemble(picgpu, ref):
         assert abs(g["w_ele"] - (3000 * 100.0 + g["w_ion"])) <= 1e-6
 
 
+def test_mover_lists_are_exact_and_equivalent_to_resorting(picgpu, orc=None):
+    """Between sorts the collision kernel works on a stale partition patched with mover lists.  (1) The per-cell list
+    lengths must equal the per-cell particle counts exactly after pushes, deaths (hole filling) and appends.  (2) An MC
+    ensemble run on patched lists must agree with the same ensemble run after a forced full sort."""
+    pg = picgpu
+    ni, nj, nk = 9, 9, 13
+    x0, xm, rects = util.discharge_geometry(ni, nj, nk)
+    E, sg = util.momentum_transfer_table()
+    E_ion = 1313.9 * 1000 / util.NA
+    neu0 = util.random_particles(40000, x0, xm, seed=71, vth=600.0, mpw=(5e11, 5e11), lo_frac=(0, 0, 0.15), hi_frac=(1, 1, 0.85))
+    ele0 = util.random_particles(20000, x0, xm, seed=72, vth=2.5e6, mpw=(100.0, 100.0), lo_frac=(0, 0, 0.15), hi_frac=(1, 1, 0.85))
+    extra = util.random_particles(1500, x0, xm, seed=73, vth=2.5e6, mpw=(100.0, 100.0), lo_frac=(0, 0, 0.2), hi_frac=(1, 1, 0.8))
+
+    def run(seed, frac):
+        pg.set_mover_fraction(frac); pg.seed(seed)
+        w = util.build_world(pg.World, ni, nj, nk, x0, xm, rects, dt=1e-10)
+        w.upload(pg.F_EF, util.smooth_ef((ni, nj, nk), x0, xm, seed=3, amp=2e6))
+        sn = pg.Species("O", 16 * util.AMU, 0.0, w, 5e11, E_ion); si = pg.Species("O+", 16 * util.AMU, util.QE, w, 100.0); se = pg.Species("e-", util.ME, -util.QE, w, 100.0)
+        sn.setParticles(neu0); se.setParticles(ele0)
+        sn.sort(); se.sort()
+        se.advanceElectrons(1.5e-11)                      # ~5 % of the electrons change cell, some are absorbed (holes filled from the tail)
+        sn.advanceNonElectron(sn, sn, 2e-8)
+        se.addParticles(extra)                            # appended beyond the partition
+        m = pg.MC_MEX_Ionization(sn, si, se, w, E, sg)
+        m.setWsvMax(5e11 * 8e-20 * 8e6)
+        if frac > 0:
+            se.computeMacroParticlesCount(); sn.computeMacroParticlesCount()
+            assert np.array_equal(m.listCounts(1, w), se.macro_part_count)
+            assert np.array_equal(m.listCounts(0, w), sn.macro_part_count)
+        st = m.apply(1e-10)
+        out = dict(coll=st.collisions, ion=st.ionizations, ne=se.getNumParticles(), nn=sn.getNumParticles(), ke=se.diagnostics()[2])
+        for o in (m, sn, si, se, w):
+            o.close()
+        return out
+    A = [run(s, 0.10) for s in range(N_SEEDS)]            # patched lists
+    B = [run(100 + s, 0.0) for s in range(N_SEEDS)]       # full re-sort, as the reference does every step
+    pg.set_mover_fraction(0.10)
+    assert np.mean([b["coll"] for b in B]) > 100
+    for key in ("coll", "ion", "ne", "nn", "ke"):
+        _agree([a[key] for a in A], [b[key] for b in B], key)
+
+
 def test_cross_sections_match_reference(picgpu, ref):
     x0, xm, rects = util.discharge_geometry(7, 7, 9)
     E, s = util.momentum_transfer_table()
