@@ -116,6 +116,7 @@ extern int g_device;          // -1 until picg_init succeeds
 extern int g_sm_count;
 extern uint64_t g_seed;
 extern int g_rank, g_world_size;
+extern uint64_t g_reallocs;     // device (re)allocations of particle stores / scratch since start (a timed region should see none)
 int  set_error(int code, const char* fmt, ...);
 int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 void count_launch(int kernel_id);

@@ -11,6 +11,7 @@ int g_device = -1;
 int g_sm_count = PICG_SM_COUNT_FALLBACK;
 uint64_t g_seed = 0x5EED0000ull;
 int g_rank = 0, g_world_size = 1;
+uint64_t g_reallocs = 0;
 static thread_local char g_err[1024] = "";
 static uint64_t g_launches = 0;
 static bool g_timers_on = false;
@@ -60,7 +61,7 @@ int ensure_scratch(picg_world_s* w, size_t bytes) {
     cudaError_t e = cudaMalloc(&w->scratch, want);
     if (e != cudaSuccess) { e = cudaMalloc(&w->scratch, bytes); want = bytes; }
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)", __FILE__, __LINE__);
-    w->scratch_bytes = want;
+    w->scratch_bytes = want; g_reallocs++;
     return PICG_OK;
 }
 }  // namespace picg
@@ -116,9 +117,17 @@ int picg_set_rank(int rank, int world_size) {
     REQUIRE_ARG(world_size >= 1 && rank >= 0 && rank < world_size, "picg_set_rank: need 0 <= rank < world_size");
     g_rank = rank; g_world_size = world_size; return PICG_OK;
 }
+uint64_t picg_realloc_count(void) { return g_reallocs; }
 uint64_t picg_launch_count(void) { return g_launches; }
 void picg_launch_count_reset(void) { g_launches = 0; }
-int picg_timers_enable(int on) { drain_timers(); g_timers_on = on != 0; return PICG_OK; }
+int picg_timers_enable(int on) {
+    drain_timers();
+    if (on && g_event_pool.size() < 8192) {            // create the events up front: cudaEventCreate inside a timed region would distort it
+        g_event_pool.reserve(8192);
+        while (g_event_pool.size() < 8192) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) break; g_event_pool.push_back(e); }
+    }
+    g_timers_on = on != 0; return PICG_OK;
+}
 int picg_timers_reset(void) { drain_timers(); memset(g_timer_ms, 0, sizeof(g_timer_ms)); memset(g_timer_n, 0, sizeof(g_timer_n)); return PICG_OK; }
 int picg_timer_read(int id, double* total_ms, uint64_t* launches) {
     if (id < 0 || id >= K_NUM_KERNELS) return set_error(PICG_ERR_ARG, "picg_timer_read: bad kernel id %d", id);

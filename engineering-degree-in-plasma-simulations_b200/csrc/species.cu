@@ -131,6 +131,7 @@ int species_ensure_capacity(picg_species_s* s, size_t cap) {
     cudaStreamSynchronize(g_stream);
     for (int c = 0; c < 7; c++) { cudaFree(s->a[c]); s->a[c] = na[c]; }
     cudaFree(s->spare); s->spare = na[7];
+    g_reallocs++;
     s->cap = newcap;
     return PICG_OK;
 }

@@ -35,6 +35,7 @@ def lib():
         l.picg_timer_name.restype = C.c_char_p
         l.picg_stream.restype = C.c_void_p
         l.picg_launch_count.restype = C.c_uint64
+        l.picg_realloc_count.restype = C.c_uint64
         l.picg_launch_count_reset.restype = None
         _lib = l
     return _lib
@@ -85,6 +86,10 @@ def stream_ptr():
 
 def launch_count():
     return int(lib().picg_launch_count())
+
+
+def realloc_count():
+    return int(lib().picg_realloc_count())
 
 
 def launch_count_reset():

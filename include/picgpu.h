@@ -64,6 +64,8 @@ PICG_API int         picg_set_rank(int rank, int world_size); /* multi-GPU: deco
 /* number of kernels this library launched since the last reset (bench.py's gpu_launches) */
 PICG_API uint64_t    picg_launch_count(void);
 PICG_API void        picg_launch_count_reset(void);
+/* number of device (re)allocations of particle stores / scratch so far: a timed region should not see it change */
+PICG_API uint64_t    picg_realloc_count(void);
 /* per-kernel CUDA-event timers: enable, then read accumulated ms and launch counts by kernel id */
 PICG_API int         picg_timers_enable(int on);
 PICG_API int         picg_timers_reset(void);
