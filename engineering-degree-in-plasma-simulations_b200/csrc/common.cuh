@@ -91,6 +91,7 @@ struct picg_solver_s {
     double phi0 = 0, n0 = 0, Te0 = 1;
     int bc_mode = 0;
     double* partial = nullptr;         // residual partial sums
+    unsigned char* cls = nullptr;      // node class per node (poisson.cu), rebuilt at the start of every solve
 };
 
 struct picg_mcc_s {
@@ -100,6 +101,7 @@ struct picg_mcc_s {
     double* wsv = nullptr;             // device: [0] current max, [1] step max
     u64* stats = nullptr;              // device: candidates, collisions, ionizations
     u64 step = 0;
+    size_t last_appends[3] = {0, 0, 0};   // neutrals, electrons, ions appended by the previous apply (capacity estimate)
 };
 
 struct picg_source_s {

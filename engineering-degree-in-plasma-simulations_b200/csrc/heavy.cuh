@@ -47,6 +47,28 @@ static __device__ __noinline__ bool surface_interaction(const Grid& g, const Hea
     return true;
 }
 
+
+// State of a heavy particle whose first sub-move ended inside an object; heavy_after_impact runs the rest of the
+// reference's bounce loop (Species.cpp:194-249: up to 20 sub-moves in total).  Returns true when the particle is removed.
+struct HeavyState { double ox, oy, oz, x, y, z, u, v, w; };
+static __device__ __noinline__ bool heavy_after_impact(const Grid& g, const HeavyArgs& h, const double* __restrict__ ef, double dt, unsigned long long p,
+                                                       int obj, double mpw, HeavyState& st) {
+    PhiloxStream rs; rs.init(h.seed, h.stream, p, h.call);
+    double t_rem = 1; int n_b = 1;
+    double old[3] = {st.ox, st.oy, st.oz}, x[3] = {st.x, st.y, st.z}, v[3] = {st.u, st.v, st.w};
+    bool gone = surface_interaction(g, h, ef, rs, obj, old, x, v, mpw, t_rem);
+    while (!gone && t_rem > 0) {
+        if (++n_b > 20) { gone = true; break; }                                   // :198-203
+        old[0] = x[0]; old[1] = x[1]; old[2] = x[2];
+        for (int a = 0; a < 3; a++) x[a] = __dadd_rn(x[a], __dmul_rn(__dmul_rn(v[a], t_rem), dt));      // pos += vel*t_rem*dt
+        int o2 = in_object(g, x[0], x[1], x[2]);
+        if (!in_bounds(g, x[0], x[1], x[2])) { gone = true; break; }
+        if (o2) { gone = surface_interaction(g, h, ef, rs, o2, old, x, v, mpw, t_rem); continue; }
+        t_rem = 0;
+    }
+    st.x = x[0]; st.y = x[1]; st.z = x[2]; st.u = v[0]; st.v = v[1]; st.w = v[2];
+    return gone;
+}
 #endif
 
 static inline Emit emit_of(picg_species_s* t) {

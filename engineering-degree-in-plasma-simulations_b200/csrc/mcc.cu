@@ -106,22 +106,28 @@ __device__ __forceinline__ bool collide(PhiloxStream& r, const MccParams& P, con
     return false;
 }
 
-__device__ __forceinline__ long long append(const Store& s, const double pos[3], const double v[3], double mpw) {
+// Slot reservation BEFORE any state is changed: a collision whose products do not fit is skipped as a whole (and
+// counted), so a full store can never leave half-applied collisions behind.
+__device__ __forceinline__ long long reserve_slot(const Store& s) {
     u64 dst = atomicAdd(&s.ctr->n, 1ull);
-    if (dst >= s.cap) { atomicAdd(&s.ctr->overflow, 1ull); return -1; }
-    s.a[0][dst] = pos[0]; s.a[1][dst] = pos[1]; s.a[2][dst] = pos[2]; s.a[3][dst] = v[0]; s.a[4][dst] = v[1]; s.a[5][dst] = v[2]; s.a[6][dst] = mpw;
+    if (dst >= s.cap) { atomicAdd(&s.ctr->n, ~0ull); return -1; }          // give the slot back
     return (long long)dst;
+}
+__device__ __forceinline__ void release_slot(const Store& s) { atomicAdd(&s.ctr->n, ~0ull); }
+__device__ __forceinline__ void write_slot(const Store& s, long long dst, const double pos[3], const double v[3], double mpw) {
+    s.a[0][dst] = pos[0]; s.a[1][dst] = pos[1]; s.a[2][dst] = pos[2]; s.a[3][dst] = v[0]; s.a[4][dst] = v[1]; s.a[5][dst] = v[2]; s.a[6][dst] = mpw;
 }
 __device__ __forceinline__ void atomic_max_pos_double(double* addr, double v) {     // valid for non-negative doubles
     atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
 }
 
 // stats: [0] candidates [1] collisions [2] ionisations [3] skipped (electron heavier than neutral)
+//        [5] dropped because a product store was full (collision skipped untouched)
 __global__ void __launch_bounds__(128) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, CellLists Ln,
                                              CellLists Le, double* __restrict__ wsv, u64* __restrict__ stats, double dt,
                                              uint64_t seed, uint32_t stream, uint32_t call) {
     const double W_max = wsv[0];
-    u64 n_cand = 0, n_coll = 0, n_ion = 0, n_skip = 0; double step_max = 0;
+    u64 n_cand = 0, n_coll = 0, n_ion = 0, n_skip = 0, n_drop = 0; double step_max = 0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.nc; c += gridDim.x * blockDim.x) {
         CellView ve = cell_view(Le, c); int np_e = ve.np;
         if (np_e <= 0) continue;
@@ -152,18 +158,22 @@ __global__ void __launch_bounds__(128) k_mcc(Grid g, MccParams P, Store neu, Sto
             if (r.next() < Wsv / W_max) {
                 n_coll++;
                 if (Wn > We) {                                                             // split the neutral (:684-703)
-                    neu.a[6][pn] = Wn - We;
                     double vnew[3] = {0, 0, 0};
-                    bool ionised = collide(r, P, vn_, ve_, vnew, s_coll);
+                    bool ionised = collide(r, P, vn_, ve_, vnew, s_coll);                  // pure: works on local copies
+                    long long s1 = -1, s2 = -1;
+                    if (ionised) { s1 = reserve_slot(ion); if (s1 >= 0) { s2 = reserve_slot(ele); if (s2 < 0) { release_slot(ion); s1 = -1; } } }
+                    else s1 = reserve_slot(neu);
+                    if (s1 < 0) { n_drop++; n_coll--; continue; }                          // no room for the products: skip the collision untouched
+                    neu.a[6][pn] = Wn - We;
                     ele.a[3][pe] = ve_[0]; ele.a[4][pe] = ve_[1]; ele.a[5][pe] = ve_[2];
                     double pos[3] = {neu.a[0][pn], neu.a[1][pn], neu.a[2][pn]};
                     if (ionised) {
                         n_ion++;
-                        append(ion, pos, vn_, Wl);                                         // no half-step rewind (:694-695)
-                        append(ele, pos, vnew, Wl);
+                        write_slot(ion, s1, pos, vn_, Wl);                                 // no half-step rewind (:694-695)
+                        write_slot(ele, s2, pos, vnew, Wl);
                     } else {
-                        long long idx = append(neu, pos, vn_, We);                         // split-off neutral of the electron's weight
-                        if (idx >= 0 && n_extra < MCC_EXTRA) { extra[n_extra++] = idx; np_n++; }
+                        write_slot(neu, s1, pos, vn_, We);                                 // split-off neutral of the electron's weight
+                        if (n_extra < MCC_EXTRA) { extra[n_extra++] = s1; np_n++; }
                     }
                 } else if (Wn < We) {
                     n_skip++;          // the reference's electron-heavier branch is defective; not reproduced, counted
@@ -172,32 +182,18 @@ __global__ void __launch_bounds__(128) k_mcc(Grid g, MccParams P, Store neu, Sto
         }
     }
     // block-level reduction of the statistics
-    __shared__ u64 sh[4]; __shared__ double sh_max;
-    if (threadIdx.x == 0) { sh[0] = sh[1] = sh[2] = sh[3] = 0; sh_max = 0; }
+    __shared__ u64 sh[5]; __shared__ double sh_max;
+    if (threadIdx.x == 0) { sh[0] = sh[1] = sh[2] = sh[3] = sh[4] = 0; sh_max = 0; }
     __syncthreads();
-    if (n_cand) { atomicAdd(&sh[0], n_cand); atomicAdd(&sh[1], n_coll); atomicAdd(&sh[2], n_ion); atomicAdd(&sh[3], n_skip); atomic_max_pos_double(&sh_max, step_max); }
+    if (n_cand) { atomicAdd(&sh[0], n_cand); atomicAdd(&sh[1], n_coll); atomicAdd(&sh[2], n_ion); atomicAdd(&sh[3], n_skip); atomicAdd(&sh[4], n_drop); atomic_max_pos_double(&sh_max, step_max); }
     __syncthreads();
     if (threadIdx.x == 0 && sh[0]) {
-        atomicAdd(&stats[0], sh[0]); atomicAdd(&stats[1], sh[1]); atomicAdd(&stats[2], sh[2]); atomicAdd(&stats[3], sh[3]);
+        atomicAdd(&stats[0], sh[0]); atomicAdd(&stats[1], sh[1]); atomicAdd(&stats[2], sh[2]); atomicAdd(&stats[3], sh[3]); atomicAdd(&stats[5], sh[4]);
         atomic_max_pos_double(&wsv[1], sh_max);
     }
 }
 // W_sigma_v_rel_max <- max sampled value of this step, only if a collision happened (:751-756)
 __global__ void k_mcc_finish(double* wsv, const u64* stats) { if (stats[1]) wsv[0] = wsv[1]; }
-// upper bound on appended particles: sum over cells of n_groups
-__global__ void __launch_bounds__(256) k_mcc_count(Grid g, CellLists Ln, CellLists Le, const double* __restrict__ wsv,
-                                                   double dt, double inv_dv, double rank_scale, u64* __restrict__ total) {
-    u64 acc = 0;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.nc; c += gridDim.x * blockDim.x) {
-        int np_e = cell_view(Le, c).np, np_n = cell_view(Ln, c).np;
-        if (np_e <= 0 || np_n <= 0) continue;
-        int n_groups = (int)(np_n * np_e * wsv[0] * dt * inv_dv * rank_scale + 0.5);
-        if (n_groups > np_n) n_groups = np_n - 1;
-        if (n_groups > 0) acc += n_groups;
-    }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
-}
 __global__ void k_sigma_eval(MccParams P, int n, const double* __restrict__ E, double* __restrict__ sc, double* __restrict__ si) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) { sc[t] = sigma_coll(P, E[t]); si[t] = sigma_ion(P, E[t]); }
 }
@@ -301,39 +297,39 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     rc = species_exact_lists(ele); if (rc) return rc;
     MccParams P = make_params(m);
     const Grid& g = m->w->g;
-    // capacity for the appends: one pass over the cells gives the total number of candidates
+    // room for the products: 2x what the last call appended, at least 1 % of the store.  A collision whose products do
+    // not fit is skipped untouched on the device and counted (stats.dropped); the store is then grown for the next call.
     CUDA_TRY(cudaMemsetAsync(m->stats, 0, 64, g_stream));
-    int cgrid = std::max(1, std::min(div_up(g.nc, 256), g_sm_count * 8));
-    LAUNCH(K_MCC, k_mcc_count, cgrid, 256, 0, g, lists_of(neu), lists_of(ele), m->wsv, dt, P.inv_dv, P.rank_scale, m->stats + 4); CHECK_LAUNCH();
-    u64 host_stats[8];
-    CUDA_TRY(cudaMemcpyAsync(host_stats, m->stats, 64, cudaMemcpyDeviceToHost, g_stream));
     rc = species_refresh_count(neu); if (rc) return rc;        // synchronises
     rc = species_refresh_count(ele); if (rc) return rc;
     rc = species_refresh_count(ion); if (rc) return rc;
-    size_t bound = (size_t)host_stats[4];
-    if (bound) {
-        rc = species_ensure_capacity(neu, neu->n_host + bound); if (rc) return rc;
-        rc = species_ensure_capacity(ele, ele->n_host + bound); if (rc) return rc;
-        rc = species_ensure_capacity(ion, ion->n_host + bound); if (rc) return rc;
-        double zero = 0; CUDA_TRY(cudaMemcpyAsync(m->wsv + 1, &zero, 8, cudaMemcpyHostToDevice, g_stream));
-        m->step++;
-        int grid = std::max(1, std::min(div_up(g.nc, 128), g_sm_count * 16));
-        LAUNCH(K_MCC, k_mcc, grid, 128, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), m->wsv, m->stats, dt,
-               g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
-        CHECK_LAUNCH();
-        LAUNCH(K_MCC, k_mcc_finish, 1, 1, 0, m->wsv, m->stats); CHECK_LAUNCH();
-        CUDA_TRY(cudaMemcpyAsync(host_stats, m->stats, 64, cudaMemcpyDeviceToHost, g_stream));
-        for (picg_species_s* s : {neu, ele, ion}) { s->n_host_valid = false; s->n_upper = s->cap; }
-        rc = species_refresh_count(neu); if (rc) return rc;
-        rc = species_refresh_count(ele); if (rc) return rc;
-        rc = species_refresh_count(ion); if (rc) return rc;
-        if (host_stats[1]) { neu->sorted_valid = false; neu->lists_valid = false; ele->sorted_valid = false; ele->lists_valid = false; ion->sorted_valid = false; ion->lists_valid = false; }   // :751-754
-    } else {
-        m->step++;
-        host_stats[0] = host_stats[1] = host_stats[2] = 0;
+    size_t n_before[3] = {neu->n_host, ele->n_host, ion->n_host};
+    picg_species_s* sp3[3] = {neu, ele, ion};
+    for (int k = 0; k < 3; k++) {
+        size_t want = sp3[k]->n_host + std::max<size_t>(std::max<size_t>(2 * m->last_appends[k], sp3[k]->n_host / 100), 65536);
+        if (sp3[k]->cap < want) { rc = species_ensure_capacity(sp3[k], want); if (rc) return rc; }
+    }
+    double zero = 0; CUDA_TRY(cudaMemcpyAsync(m->wsv + 1, &zero, 8, cudaMemcpyHostToDevice, g_stream));
+    m->step++;
+    int grid = std::max(1, std::min(div_up(g.nc, 128), g_sm_count * 16));
+    LAUNCH(K_MCC, k_mcc, grid, 128, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), m->wsv, m->stats, dt,
+           g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
+    CHECK_LAUNCH();
+    LAUNCH(K_MCC, k_mcc_finish, 1, 1, 0, m->wsv, m->stats); CHECK_LAUNCH();
+    u64 host_stats[8];
+    CUDA_TRY(cudaMemcpyAsync(host_stats, m->stats, 64, cudaMemcpyDeviceToHost, g_stream));
+    for (picg_species_s* s : {neu, ele, ion}) { s->n_host_valid = false; s->n_upper = s->cap; }
+    rc = species_refresh_count(neu); if (rc) return rc;
+    rc = species_refresh_count(ele); if (rc) return rc;
+    rc = species_refresh_count(ion); if (rc) return rc;
+    for (int k = 0; k < 3; k++) m->last_appends[k] = sp3[k]->n_host - n_before[k];
+    if (host_stats[1]) { neu->sorted_valid = false; neu->lists_valid = false; ele->sorted_valid = false; ele->lists_valid = false; ion->sorted_valid = false; ion->lists_valid = false; }   // :751-754
+    if (host_stats[5]) {                                        // grow so that the next call has room, and tell the caller
+        for (int k = 0; k < 3; k++) { rc = species_ensure_capacity(sp3[k], sp3[k]->n_host + std::max<size_t>(4 * (size_t)host_stats[5], sp3[k]->n_host / 10)); if (rc) return rc; }
+        set_error(PICG_OK, "picg_mcc_apply: %llu collisions were skipped because a particle store was full; stores were grown (reserve more up front)", (unsigned long long)host_stats[5]);
     }
     if (out) {
-        out->candidates = host_stats[0]; out->collisions = host_stats[1]; out->ionizations = host_stats[2];
+        out->candidates = host_stats[0]; out->collisions = host_stats[1]; out->ionizations = host_stats[2]; out->dropped = host_stats[5];
         double wmax; CUDA_TRY(cudaMemcpyAsync(&wmax, m->wsv, 8, cudaMemcpyDeviceToHost, g_stream)); CUDA_TRY(cudaStreamSynchronize(g_stream));
         out->w_sigma_v_max = wmax;
     }

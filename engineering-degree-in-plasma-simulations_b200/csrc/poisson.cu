@@ -36,6 +36,32 @@ __device__ __forceinline__ size_t face_neighbor(const Grid& g, int cls, size_t u
     switch (cls) { case 1: return u + si; case 2: return u - si; case 3: return u + sj; case 4: return u - sj; case 5: return u + 1; default: return u - 1; }
 }
 
+// node classes precomputed once per solve (1 byte per node) so that the sweeps do no index arithmetic or branching on geometry
+__global__ void __launch_bounds__(256) k_node_classes(Grid g, int bc_mode, const int* __restrict__ object_id, unsigned char* __restrict__ cls) {
+    for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < (size_t)g.nv; u += (size_t)gridDim.x * blockDim.x) {
+        int k = (int)(u % g.nk); size_t row = u / g.nk; int j = (int)(row % g.nj), i = (int)(row / g.nj);
+        cls[u] = (unsigned char)node_class(g, bc_mode, object_id[u], i, j, k);
+    }
+}
+// One colour half-sweep, one block per (i,j) row: no divisions, coalesced along k, class byte instead of geometry tests.
+__global__ void __launch_bounds__(128) k_sor_row(Grid g, SorParams sp, int color, double* __restrict__ phi, const double* __restrict__ rho,
+                                                 const unsigned char* __restrict__ cls) {
+    const int j = blockIdx.x, i = blockIdx.y;
+    const size_t si = (size_t)g.nj * g.nk, sj = g.nk;
+    const size_t row = ((size_t)i * g.nj + j) * g.nk;
+    for (int k = 2 * threadIdx.x + ((i + j + color) & 1); k < g.nk; k += 2 * blockDim.x) {
+        const size_t u = row + k;
+        const int c = cls[u];
+        if (c == 0) continue;
+        if (c < 7) { phi[u] = phi[face_neighbor(g, c, u)]; continue; }
+        const double p = phi[u];
+        const double ne = (sp.n0 != 0.0) ? sp.n0 * exp((p - sp.phi0) / sp.Te0) : 0.0;
+        const double nw = ((rho[u] - sp.qe * ne) * sp.inv_eps0 + (phi[u - si] + phi[u + si]) * sp.inv_d2x + (phi[u - sj] + phi[u + sj]) * sp.inv_d2y +
+                           (phi[u - 1] + phi[u + 1]) * sp.inv_d2z) * sp.inv_twos;
+        phi[u] = p + sp.w * (nw - p);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_sor_color(Grid g, SorParams sp, int color, double* __restrict__ phi, const double* __restrict__ rho,
                                                    const int* __restrict__ object_id) {
     const int hk = (g.nk + 1) >> 1;
@@ -113,12 +139,17 @@ static SorParams make_params(const picg_solver_s* s) {
 }
 static const int kResidualBlocks = 1024;
 
+static int prepare_classes(picg_solver_s* s) {
+    const Grid& g = s->w->g;
+    if (!s->cls) { cudaError_t e = cudaMalloc(&s->cls, (size_t)g.nv); if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(node classes)", __FILE__, __LINE__); }
+    LAUNCH(K_MISC, k_node_classes, std::min(div_up(g.nv, 256), g_sm_count * 8), 256, 0, g, s->bc_mode, s->w->object_id, s->cls); CHECK_LAUNCH();
+    return PICG_OK;
+}
 static int launch_iteration(picg_solver_s* s, const SorParams& p) {
     const Grid& g = s->w->g;
-    size_t half = (size_t)g.ni * g.nj * ((g.nk + 1) >> 1);
-    int grid = std::max(1, std::min(div_up(half, 256), g_sm_count * 8));
-    LAUNCH(K_SOR, k_sor_color, grid, 256, 0, g, p, 0, s->w->phi, s->w->rho, s->w->object_id); CHECK_LAUNCH();
-    LAUNCH(K_SOR, k_sor_color, grid, 256, 0, g, p, 1, s->w->phi, s->w->rho, s->w->object_id); CHECK_LAUNCH();
+    dim3 grid(g.nj, g.ni);
+    LAUNCH(K_SOR, k_sor_row, grid, 128, 0, g, p, 0, s->w->phi, s->w->rho, s->cls); CHECK_LAUNCH();
+    LAUNCH(K_SOR, k_sor_row, grid, 128, 0, g, p, 1, s->w->phi, s->w->rho, s->cls); CHECK_LAUNCH();
     return PICG_OK;
 }
 static int compute_residual(picg_solver_s* s, const SorParams& p, double* L2) {
@@ -142,7 +173,7 @@ int picg_solver_create(picg_world_t w, unsigned max_it, double tol, picg_solver_
     if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMalloc(solver)", __FILE__, __LINE__); }
     *out = s; return PICG_OK;
 }
-int picg_solver_destroy(picg_solver_t s) { if (!s) return PICG_OK; if (g_stream) cudaStreamSynchronize(g_stream); cudaFree(s->partial); delete s; return PICG_OK; }
+int picg_solver_destroy(picg_solver_t s) { if (!s) return PICG_OK; if (g_stream) cudaStreamSynchronize(g_stream); cudaFree(s->partial); cudaFree(s->cls); delete s; return PICG_OK; }
 int picg_solver_set_reference(picg_solver_t s, double phi0, double n0, double Te0) {
     REQUIRE_ARG(s, "picg_solver_set_reference: null solver"); s->phi0 = phi0; s->n0 = n0; s->Te0 = Te0; return PICG_OK;
 }
@@ -153,6 +184,7 @@ int picg_solver_set_boundary_mode(picg_solver_t s, int mode) {
 int picg_solver_solve_gs(picg_solver_t s, int* converged, unsigned* iterations, double* L2_out) {
     REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_solver_solve_gs: null solver");
     SorParams p = make_params(s);
+    { int rc0 = prepare_classes(s); if (rc0) return rc0; }
     double L2 = 0; bool conv = false; unsigned it;
     for (it = 0; it < s->max_it; it++) {
         int rc = launch_iteration(s, p); if (rc) return rc;
@@ -168,6 +200,7 @@ int picg_solver_solve_gs(picg_solver_t s, int* converged, unsigned* iterations, 
 int picg_solver_iterate(picg_solver_t s, unsigned n) {
     REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_solver_iterate: null solver");
     SorParams p = make_params(s);
+    { int rc0 = prepare_classes(s); if (rc0) return rc0; }
     for (unsigned it = 0; it < n; it++) { int rc = launch_iteration(s, p); if (rc) return rc; }
     return PICG_OK;
 }

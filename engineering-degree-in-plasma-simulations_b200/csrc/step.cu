@@ -107,24 +107,16 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
                     xn = __dadd_rn(xn, __dmul_rn(un, A.dt)); yn = __dadd_rn(yn, __dmul_rn(vn, A.dt)); zn = __dadd_rn(zn, __dmul_rn(wn, A.dt));
                     dead = !in_bounds(g, xn, yn, zn) || in_object(g, xn, yn, zn) != 0;        // Species.cpp:375-388
                 } else {
-                    double t_rem = 1; int n_b = 0; bool rng_ready = false; PhiloxStream rs;
-                    while (t_rem > 0) {
-                        if (++n_b > 20) { dead = true; break; }                                // :198-203
-                        const double ox = xn, oy = yn, oz = zn;
-                        xn = __dadd_rn(xn, __dmul_rn(__dmul_rn(un, t_rem), A.dt));            // pos += vel*t_rem*dt
-                        yn = __dadd_rn(yn, __dmul_rn(__dmul_rn(vn, t_rem), A.dt));
-                        zn = __dadd_rn(zn, __dmul_rn(__dmul_rn(wn, t_rem), A.dt));
-                        int obj = in_object(g, xn, yn, zn);
-                        if (!in_bounds(g, xn, yn, zn)) { dead = true; break; }
-                        if (obj) {
-                            if (!rng_ready) { rs.init(H.seed, H.stream, p, H.call); rng_ready = true; }
-                            double xx[3] = {xn, yn, zn}, vv[3] = {un, vn, wn}, oo[3] = {ox, oy, oz};
-                            bool absorbed = surface_interaction(g, H, A.ef, rs, obj, oo, xx, vv, m[r], t_rem);
-                            xn = xx[0]; yn = xx[1]; zn = xx[2]; un = vv[0]; vn = vv[1]; wn = vv[2];
-                            if (absorbed) { dead = true; break; }
-                            continue;
-                        }
-                        t_rem = 0;
+                    // first sub-move (t_rem = 1, vel*1 is exact): identical to the electron drift.  Only particles that end it
+                    // inside an object take the out-of-line path with the remaining sub-moves (Species.cpp:194-249).
+                    const double ox = xn, oy = yn, oz = zn;
+                    xn = __dadd_rn(xn, __dmul_rn(un, A.dt)); yn = __dadd_rn(yn, __dmul_rn(vn, A.dt)); zn = __dadd_rn(zn, __dmul_rn(wn, A.dt));
+                    int obj = in_object(g, xn, yn, zn);
+                    if (!in_bounds(g, xn, yn, zn)) dead = true;
+                    else if (obj) {
+                        HeavyState st = {ox, oy, oz, xn, yn, zn, un, vn, wn};
+                        dead = heavy_after_impact(g, H, A.ef, A.dt, p, obj, m[r], st);
+                        xn = st.x; yn = st.y; zn = st.z; un = st.u; vn = st.v; wn = st.w;
                     }
                 }
                 if (!dead) { x[r] = xn; y[r] = yn; z[r] = zn; u[r] = un; v[r] = vn; w[r] = wn; }

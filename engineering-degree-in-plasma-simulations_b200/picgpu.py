@@ -366,7 +366,7 @@ class PotentialSolver:
 
 
 class MccStats(C.Structure):
-    _fields_ = [("candidates", C.c_uint64), ("collisions", C.c_uint64), ("ionizations", C.c_uint64), ("w_sigma_v_max", C.c_double)]
+    _fields_ = [("candidates", C.c_uint64), ("collisions", C.c_uint64), ("ionizations", C.c_uint64), ("w_sigma_v_max", C.c_double), ("dropped", C.c_uint64)]
 
 
 class MC_MEX_Ionization:

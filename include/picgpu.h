@@ -188,7 +188,8 @@ PICG_API int picg_solver_compute_ef(picg_solver_t s);
 PICG_API int picg_mcc_create(picg_species_t neutrals, picg_species_t ions, picg_species_t electrons, picg_world_t w,
                              const double* table_E, const double* table_sigma, int n_table, double E_ion_J, picg_mcc_t* out);
 PICG_API int picg_mcc_destroy(picg_mcc_t m);
-typedef struct { uint64_t candidates, collisions, ionizations; double w_sigma_v_max; } picg_mcc_stats;
+typedef struct { uint64_t candidates, collisions, ionizations; double w_sigma_v_max;
+                 uint64_t dropped; /* collisions skipped (untouched) because a product store was full; 0 in a healthy run */ } picg_mcc_stats;
 /* Interaction::apply(dt) -> MC_MEX_Ionization::apply_vector_indexes  Interactions.cpp:567-762 */
 PICG_API int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* stats /*may be NULL*/);
 PICG_API int picg_mcc_set_wsv_max(picg_mcc_t m, double v);
