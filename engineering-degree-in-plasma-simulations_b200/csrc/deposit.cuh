@@ -46,10 +46,17 @@ __device__ __forceinline__ i64 butterfly8(const i64 r[8], int lane) {
     return t;
 }
 
+// The warp's private window is NODE-indexed: 4 node rows (i,j) (i,j+1) (i+1,j) (i+1,j+1) of one cell column, WK nodes
+// along k starting at k0.  In the k-fastest sorted order a warp chunk stays in one column, and consecutive cells share
+// four of their eight nodes, so the window merges them before anything reaches global memory.
+struct NodeWindow { int wi, wj, k0; };
+template <int WK>
+__device__ __forceinline__ bool window_has(const NodeWindow& W, int i, int j, int k) { return i == W.wi && j == W.wj && k >= W.k0 && k + 1 < W.k0 + WK; }
+
 // Adds the contributions of the `active` lanes (cell, q[8]) to the warp's window / the global grid.
-// Warp-collective: all 32 lanes must call.  win: this warp's private window [WINDOW*8], c0: its first cell.
-template <int WINDOW>
-__device__ __forceinline__ void warp_accumulate_w(const Grid& g, bool active, int cell, const i64 q[8], i64* win, int c0,
+// Warp-collective: all 32 lanes must call.  win: this warp's private window [4*WK].
+template <int WK>
+__device__ __forceinline__ void warp_accumulate_w(const Grid& g, bool active, int cell, const i64 q[8], i64* win, const NodeWindow& W,
                                                   u64* __restrict__ den_fixed, int lane) {
     unsigned todo = __ballot_sync(0xffffffffu, active);
     while (todo) {
@@ -61,13 +68,27 @@ __device__ __forceinline__ void warp_accumulate_w(const Grid& g, bool active, in
 #pragma unroll
         for (int c = 0; c < 8; c++) r[c] = mine ? q[c] : 0;
         i64 t = butterfly8(r, lane);
-        int rel = lcell - c0;
         if ((lane & 3) == 0 && t != 0) {
-            int corner = lane >> 2;
-            if (rel >= 0 && rel < WINDOW) win[rel * 8 + corner] += t;            // private window, distinct slots: no atomic needed
-            else { int i, j, k; cell_to_ijk(g, lcell, i, j, k); atomicAdd(&den_fixed[corner_node(g, i, j, k, corner)], (u64)t); }
+            int corner = lane >> 2, i, j, k; cell_to_ijk(g, lcell, i, j, k);
+            if (window_has<WK>(W, i, j, k)) win[(corner >> 1) * WK + (k - W.k0) + (corner & 1)] += t;     // private window, 8 distinct nodes: no atomic needed
+            else atomicAdd(&den_fixed[corner_node(g, i, j, k, corner)], (u64)t);
         }
         __syncwarp();
     }
+}
+// Hands the non-zero window nodes over to the global grid (one RED.64 each) and clears them.  Warp-collective.
+template <int WK>
+__device__ __forceinline__ void window_flush(const Grid& g, i64* win, const NodeWindow& W, u64* __restrict__ den_fixed, int lane) {
+    __syncwarp();
+    for (int slot = lane; slot < 4 * WK; slot += 32) {
+        i64 t = win[slot];
+        if (t != 0) {
+            int row = slot / WK, kk = slot - row * WK;
+            size_t node = ((size_t)((W.wi + (row >> 1)) * g.nj + (W.wj + (row & 1))) * g.nk) + (W.k0 + kk);
+            atomicAdd(&den_fixed[node], (u64)t);
+            win[slot] = 0;
+        }
+    }
+    __syncwarp();
 }
 #endif

@@ -203,6 +203,16 @@ __global__ void k_gather_u32(const u64* __restrict__ n_ptr, const unsigned* __re
 }
 __global__ void k_clamp_u64(u64* v, u64 cap) { if (*v > cap) *v = cap; }
 
+// the same table for a SPARSE sorted key list (movers): one binary search per cell instead of one loop over the gap per key
+__global__ void __launch_bounds__(256) k_cell_start_search(const u64* __restrict__ n_ptr, const unsigned* __restrict__ keys, int nc, unsigned* __restrict__ cell_start) {
+    const u64 n = *n_ptr;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= nc; c += gridDim.x * blockDim.x) {
+        u64 lo = 0, hi = n;                                   // first position whose key >= c
+        while (lo < hi) { u64 mid = (lo + hi) >> 1; if (keys[mid] < (unsigned)c) lo = mid + 1; else hi = mid; }
+        cell_start[c] = (unsigned)lo;
+    }
+}
+
 namespace picg {
 double g_mover_fraction = 0.10;     // above this fraction of movers the store is re-sorted instead of patched
 // Stable LSD radix sort of (keys, vals) pairs; n is read on the device.  Returns the buffers that hold the result.
@@ -226,7 +236,7 @@ static int ensure_u32(unsigned*& p, size_t& cap, size_t want) {
     if (p) { cudaStreamSynchronize(g_stream); cudaFree(p); p = nullptr; cap = 0; }
     cudaError_t e = cudaMalloc(&p, want * 4);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(u32)", __FILE__, __LINE__);
-    cap = want; return PICG_OK;
+    cap = want; g_reallocs++; return PICG_OK;
 }
 
 // Sorts species s by cell.  Scratch: keysA | keysB | idxA | idxB | counts.
@@ -271,8 +281,9 @@ int species_exact_lists(picg_species_s* s) {
     if (!s->part_valid || n < 4096 || max_frac <= 0) return sort_species(s);
     const Grid& g = s->w->g;
     size_t mcap = (size_t)(max_frac * (double)n) + 1024;
+    size_t mcap_alloc = (size_t)(max_frac * (double)s->cap) + 1024;      // sized by the store capacity: no regrowth while the population grows
     // mover arrays: slot/cell/home triples plus radix ping-pong buffers, all in the scratch arena
-    size_t mcapa = (mcap + 63) & ~(size_t)63;
+    size_t mcapa = (mcap_alloc + 63) & ~(size_t)63;
     int nblocks = std::max(1, std::min(div_up(mcap, SORT_TILE), g_sm_count * 4));
     size_t bytes = mcapa * 4 * 7 + (size_t)256 * nblocks * 4 + 256;
     rc = ensure_scratch(s->w, bytes); if (rc) return rc;
@@ -299,7 +310,7 @@ int species_exact_lists(picg_species_s* s) {
         LAUNCH(K_SORT_KEYS, k_copy_u32, mgrid, 256, 0, cnt, m_cell, tmp); CHECK_LAUNCH();          // keep m_cell intact? (not needed later) -> sort a copy
         ka = tmp;
         rc = radix_sort_pairs(cnt, mcap, bits, ka, va, kb, vb, counts, nblocks); if (rc) return rc;
-        LAUNCH(K_CELL_START, k_cell_start, mgrid, 256, 0, cnt, ka, g.nc, s->in_start); CHECK_LAUNCH();
+        LAUNCH(K_CELL_START, k_cell_start_search, std::min(div_up((size_t)g.nc + 1, 256), g_sm_count * 8), 256, 0, cnt, ka, g.nc, s->in_start); CHECK_LAUNCH();
         LAUNCH(K_SORT_PERMUTE, k_gather_u32, mgrid, 256, 0, cnt, va, m_slot, s->mv_in); CHECK_LAUNCH();
     }
     // (2) out-lists: every slot whose particle left its home cell (live movers with a home + slots vacated beyond n), ordered by home
@@ -313,7 +324,7 @@ int species_exact_lists(picg_species_s* s) {
         LAUNCH(K_SORT_KEYS, k_iota_u32, mgrid2, 256, 0, cnt, va); CHECK_LAUNCH();
         int hbits = 1; while ((1ull << hbits) < (u64)g.nc + 1) hbits++;
         rc = radix_sort_pairs(cnt, mcap, hbits, ka, va, kb, vb, counts, nblocks); if (rc) return rc;
-        LAUNCH(K_CELL_START, k_cell_start, mgrid2, 256, 0, cnt, ka, g.nc, s->out_start); CHECK_LAUNCH();
+        LAUNCH(K_CELL_START, k_cell_start_search, std::min(div_up((size_t)g.nc + 1, 256), g_sm_count * 8), 256, 0, cnt, ka, g.nc, s->out_start); CHECK_LAUNCH();
         LAUNCH(K_SORT_PERMUTE, k_gather_u32, mgrid2, 256, 0, cnt, va, m_slot, s->mv_in + mcapa); CHECK_LAUNCH();
     }
     s->lists_valid = true;

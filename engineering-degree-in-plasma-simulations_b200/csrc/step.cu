@@ -35,7 +35,7 @@ using namespace picg;
 #define RUN_WARPS (RUN_THREADS / 32)
 #define RUN_LEN 4
 #define RUN_WARP_CHUNK (32 * RUN_LEN)                        // 128 particles per warp iteration
-#define RUN_WINDOW 16                                        // cells in the per-warp window (x 8 corners x 8 B = 1 KB)
+#define RUN_WINDOW 64                                        // nodes along k in the per-warp window (4 rows x 64 x 8 B = 2 KB)
 
 struct StepArgs {
     double* a[7]; SpeciesCounters* ctr; u64 n_fixed; int use_fixed_n;      // heavy pushes walk a snapshot of the count (Species.cpp:176)
@@ -67,10 +67,10 @@ __device__ __forceinline__ void store_run(double* base, u64 p0, bool full, u64 l
 
 template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT>
 __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, HeavyArgs H) {
-    __shared__ i64 s_win[DEPOSIT ? RUN_WARPS : 1][RUN_WINDOW * 8];
+    __shared__ i64 s_win[DEPOSIT ? RUN_WARPS : 1][RUN_WINDOW * 4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     i64* win = s_win[DEPOSIT ? wib : 0];
-    if (DEPOSIT) { for (int t = lane; t < RUN_WINDOW * 8; t += 32) win[t] = 0; __syncwarp(); }
+    if (DEPOSIT) { for (int t = lane; t < RUN_WINDOW * 4; t += 32) win[t] = 0; __syncwarp(); }
     const u64 n = A.use_fixed_n ? A.n_fixed : A.ctr->n;
     const u64 lo = A.tail_from ? (u64)*A.tail_from : 0;
     const u64 warp = (u64)blockIdx.x * RUN_WARPS + wib, nwarps = (u64)gridDim.x * RUN_WARPS;
@@ -82,12 +82,13 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
         load_run(A.a[0], p0, full, lo, n, x); load_run(A.a[1], p0, full, lo, n, y); load_run(A.a[2], p0, full, lo, n, z);
         if (PUSH) { load_run(A.a[3], p0, full, lo, n, u); load_run(A.a[4], p0, full, lo, n, v); load_run(A.a[5], p0, full, lo, n, w); }
         if (DEPOSIT || HEAVY) load_run(A.a[6], p0, full, lo, n, m);
-        int c0 = 0;
-        if (DEPOSIT) {                  // window placed at the warp's first particle (2 cells of slack below)
+        NodeWindow W = {0, 0, 0};
+        if (DEPOSIT) {                  // window placed at the column of the warp's first particle (2 nodes of slack below)
             int i = min(max((int)x_to_l(x[0], g.x0[0], g.inv_dx[0]), 0), g.ci - 1);
             int j = min(max((int)x_to_l(y[0], g.x0[1], g.inv_dx[1]), 0), g.cj - 1);
             int k = min(max((int)x_to_l(z[0], g.x0[2], g.inv_dx[2]), 0), g.ck - 1);
-            c0 = __shfl_sync(0xffffffffu, cell_of(g, i, j, k), 0) - 2;
+            W.wi = __shfl_sync(0xffffffffu, i, 0); W.wj = __shfl_sync(0xffffffffu, j, 0);
+            W.k0 = min(max(__shfl_sync(0xffffffffu, k, 0) - 2, 0), max(g.nk - RUN_WINDOW, 0));
         }
         int cur = -1; i64 acc[8]; double cur_count = 0;
 #pragma unroll
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
             {
                 bool leave = have && cur >= 0 && newcell != cur;
                 if (__any_sync(0xffffffffu, leave)) {
-                    if (DEPOSIT) warp_accumulate_w<RUN_WINDOW>(g, leave, cur, acc, win, c0, A.den_fixed, lane);
+                    if (DEPOSIT) warp_accumulate_w<RUN_WINDOW>(g, leave, cur, acc, win, W, A.den_fixed, lane);
                     if (COUNT && leave) atomicAdd(&A.macro_count[cur], cur_count);
                 }
                 if (have) {
@@ -166,17 +167,8 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
         }
         // run totals: lanes ending in the same cell are combined before they touch shared / global memory
         if (DEPOSIT) {
-            warp_accumulate_w<RUN_WINDOW>(g, cur >= 0, cur, acc, win, c0, A.den_fixed, lane);
-            __syncwarp();
-            for (int slot = lane; slot < RUN_WINDOW * 8; slot += 32) {
-                i64 t = win[slot];
-                if (t != 0) {
-                    int i2, j2, k2; cell_to_ijk(g, c0 + (slot >> 3), i2, j2, k2);
-                    atomicAdd(&A.den_fixed[corner_node(g, i2, j2, k2, slot & 7)], (u64)t);
-                    win[slot] = 0;
-                }
-            }
-            __syncwarp();
+            warp_accumulate_w<RUN_WINDOW>(g, cur >= 0, cur, acc, win, W, A.den_fixed, lane);
+            window_flush<RUN_WINDOW>(g, win, W, A.den_fixed, lane);
         }
         if (COUNT) {
             unsigned peers = __match_any_sync(0xffffffffu, cur);
