@@ -5,13 +5,14 @@
 // associative, so ANY aggregation order (register runs, warp shuffles, shared-memory staging, global
 // atomics, NCCL all-reduce across GPUs) yields the same bits.
 //
-// Staging (step.cu): every warp owns a private shared-memory window of WINDOW consecutive cells x 8
-// corner accumulators.  Lanes whose run totals fall in the same cell are combined with a transposed
-// butterfly (9 64-bit shuffles for all eight corners instead of 40); afterwards eight lanes hold the eight
-// corner sums and add them to eight DISTINCT window slots.  The window is private to the warp and the
-// slots are distinct, so plain read-modify-write is enough - 64-bit shared-memory atomics would compile to
-// compare-and-swap spin loops (ATOMS.CAST.SPIN.64).  Cells outside the window (unsorted input, stragglers)
-// go straight to global memory with RED.64.
+// Staging (step.cu): every warp owns a private shared-memory window of NODES: the 4 node rows (i,j) (i,j+1) (i+1,j)
+// (i+1,j+1) of one cell column, WK nodes along k.  A thread accumulates its run of consecutive particles in registers
+// and adds the eight corner sums of the run to the window when the run ends or leaves its cell.  64-bit shared-memory
+// atomics do not exist in hardware (they compile to compare-and-swap spin loops, ATOMS.CAST.SPIN.64), so every window
+// node is a (lo, hi) pair of 32-bit words updated with two NATIVE 32-bit atomics and an explicit carry:
+//     old = atomicAdd(&lo, x_lo);  carry = (old + x_lo) wrapped;  atomicAdd(&hi, x_hi + carry)
+// which is exact for non-negative contributions in any interleaving.  The window is flushed with one RED.64 per
+// touched node; cells outside the window (unsorted input, stragglers) go straight to global memory.
 #pragma once
 #include "common.cuh"
 
@@ -53,40 +54,37 @@ struct NodeWindow { int wi, wj, k0; };
 template <int WK>
 __device__ __forceinline__ bool window_has(const NodeWindow& W, int i, int j, int k) { return i == W.wi && j == W.wj && k >= W.k0 && k + 1 < W.k0 + WK; }
 
-// Adds the contributions of the `active` lanes (cell, q[8]) to the warp's window / the global grid.
-// Warp-collective: all 32 lanes must call.  win: this warp's private window [4*WK].
+// v >= 0 is added to window node `slot` ((lo,hi) pair of native 32-bit shared atomics, exact 64-bit sum)
+__device__ __forceinline__ void window_add(unsigned* lo, unsigned* hi, int slot, i64 v) {
+    unsigned xl = (unsigned)(u64)v, xh = (unsigned)((u64)v >> 32);
+    unsigned old = atomicAdd(&lo[slot], xl);
+    unsigned carry = (unsigned)(old + xl < old);
+    if (xh | carry) atomicAdd(&hi[slot], xh + carry);
+}
+// Hands the eight corner sums of a finished run (cell (i,j,k)) to the window or, outside it, to the global grid.
 template <int WK>
-__device__ __forceinline__ void warp_accumulate_w(const Grid& g, bool active, int cell, const i64 q[8], i64* win, const NodeWindow& W,
-                                                  u64* __restrict__ den_fixed, int lane) {
-    unsigned todo = __ballot_sync(0xffffffffu, active);
-    while (todo) {
-        int leader = __ffs(todo) - 1;
-        int lcell = __shfl_sync(0xffffffffu, cell, leader);
-        bool mine = active && cell == lcell;
-        todo &= ~__ballot_sync(0xffffffffu, mine);
-        i64 r[8];
+__device__ __forceinline__ void run_flush(const Grid& g, const NodeWindow& W, unsigned* lo, unsigned* hi, int i, int j, int k, const i64 acc[8],
+                                          u64* __restrict__ den_fixed) {
+    if (window_has<WK>(W, i, j, k)) {
+        const int base = k - W.k0;
 #pragma unroll
-        for (int c = 0; c < 8; c++) r[c] = mine ? q[c] : 0;
-        i64 t = butterfly8(r, lane);
-        if ((lane & 3) == 0 && t != 0) {
-            int corner = lane >> 2, i, j, k; cell_to_ijk(g, lcell, i, j, k);
-            if (window_has<WK>(W, i, j, k)) win[(corner >> 1) * WK + (k - W.k0) + (corner & 1)] += t;     // private window, 8 distinct nodes: no atomic needed
-            else atomicAdd(&den_fixed[corner_node(g, i, j, k, corner)], (u64)t);
-        }
-        __syncwarp();
+        for (int c = 0; c < 8; c++) if (acc[c]) window_add(lo, hi, (c >> 1) * WK + base + (c & 1), acc[c]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; c++) if (acc[c]) atomicAdd(&den_fixed[corner_node(g, i, j, k, c)], (u64)acc[c]);
     }
 }
 // Hands the non-zero window nodes over to the global grid (one RED.64 each) and clears them.  Warp-collective.
 template <int WK>
-__device__ __forceinline__ void window_flush(const Grid& g, i64* win, const NodeWindow& W, u64* __restrict__ den_fixed, int lane) {
+__device__ __forceinline__ void window_flush(const Grid& g, unsigned* lo, unsigned* hi, const NodeWindow& W, u64* __restrict__ den_fixed, int lane) {
     __syncwarp();
     for (int slot = lane; slot < 4 * WK; slot += 32) {
-        i64 t = win[slot];
+        u64 t = ((u64)hi[slot] << 32) | lo[slot];
         if (t != 0) {
             int row = slot / WK, kk = slot - row * WK;
             size_t node = ((size_t)((W.wi + (row >> 1)) * g.nj + (W.wj + (row & 1))) * g.nk) + (W.k0 + kk);
-            atomicAdd(&den_fixed[node], (u64)t);
-            win[slot] = 0;
+            atomicAdd(&den_fixed[node], t);
+            lo[slot] = 0; hi[slot] = 0;
         }
     }
     __syncwarp();

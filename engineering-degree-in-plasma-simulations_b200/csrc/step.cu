@@ -67,10 +67,10 @@ __device__ __forceinline__ void store_run(double* base, u64 p0, bool full, u64 l
 
 template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT>
 __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, HeavyArgs H) {
-    __shared__ i64 s_win[DEPOSIT ? RUN_WARPS : 1][RUN_WINDOW * 4];
+    __shared__ unsigned s_lo[DEPOSIT ? RUN_WARPS : 1][RUN_WINDOW * 4], s_hi[DEPOSIT ? RUN_WARPS : 1][RUN_WINDOW * 4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    i64* win = s_win[DEPOSIT ? wib : 0];
-    if (DEPOSIT) { for (int t = lane; t < RUN_WINDOW * 4; t += 32) win[t] = 0; __syncwarp(); }
+    unsigned* wlo = s_lo[DEPOSIT ? wib : 0]; unsigned* whi = s_hi[DEPOSIT ? wib : 0];
+    if (DEPOSIT) { for (int t = lane; t < RUN_WINDOW * 4; t += 32) { wlo[t] = 0; whi[t] = 0; } __syncwarp(); }
     const u64 n = A.use_fixed_n ? A.n_fixed : A.ctr->n;
     const u64 lo = A.tail_from ? (u64)*A.tail_from : 0;
     const u64 warp = (u64)blockIdx.x * RUN_WARPS + wib, nwarps = (u64)gridDim.x * RUN_WARPS;
@@ -90,10 +90,10 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
             W.wi = __shfl_sync(0xffffffffu, i, 0); W.wj = __shfl_sync(0xffffffffu, j, 0);
             W.k0 = min(max(__shfl_sync(0xffffffffu, k, 0) - 2, 0), max(g.nk - RUN_WINDOW, 0));
         }
-        int cur = -1; i64 acc[8]; double cur_count = 0;
+        int cur = -1, cur_i = 0, cur_j = 0, cur_k = 0; i64 acc[8]; double cur_count = 0;
 #pragma unroll
         for (int c = 0; c < 8; c++) acc[c] = 0;
-        constexpr int kUnroll = DEPOSIT ? 1 : 4;
+        constexpr int kUnroll = (DEPOSIT && PUSH) ? 1 : 4;     // the fused body is too large for the instruction cache when unrolled
 #pragma unroll kUnroll
         for (int r = 0; r < RUN_LEN; r++) {
             const u64 p = p0 + r;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
                 if (!dead) { x[r] = xn; y[r] = yn; z[r] = zn; u[r] = un; v[r] = vn; w[r] = wn; }
             }
             if (PUSH) record_dead(dead, lane, p, A.ctr, A.dead_list);
-            int newcell = -1; bool have = false; i64 qq[8];
+            int newcell = -1, ni_ = 0, nj_ = 0, nk_ = 0; bool have = false; i64 qq[8];
             if ((DEPOSIT || COUNT) && ok && !dead) {
                 int ci, cj, ck; i64 q[8];
                 if (DEPOSIT) scatter_weights_fixed(g, x_to_l(x[r], g.x0[0], g.inv_dx[0]), x_to_l(y[r], g.x0[1], g.inv_dx[1]), x_to_l(z[r], g.x0[2], g.inv_dx[2]),
@@ -133,31 +133,27 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
                     ck = min((int)x_to_l(z[r], g.x0[2], g.inv_dx[2]), g.ck - 1);
                 }
                 int cell = cell_of(g, ci, cj, ck);
-                newcell = cell; have = true;
+                newcell = cell; ni_ = ci; nj_ = cj; nk_ = ck; have = true;
                 if (DEPOSIT) {
 #pragma unroll
                     for (int c = 0; c < 8; c++) qq[c] = q[c];
                 }
             }
-            // a run that leaves its cell hands its partial sums over (warp-collective, rare in a sorted store)
-            {
-                bool leave = have && cur >= 0 && newcell != cur;
-                if (__any_sync(0xffffffffu, leave)) {
-                    if (DEPOSIT) warp_accumulate_w<RUN_WINDOW>(g, leave, cur, acc, win, W, A.den_fixed, lane);
-                    if (COUNT && leave) atomicAdd(&A.macro_count[cur], cur_count);
-                }
-                if (have) {
-                    if (newcell != cur) {
-                        cur = newcell; cur_count = 0;
-#pragma unroll
-                        for (int c = 0; c < 8; c++) acc[c] = 0;
+            if (have) {
+                if (newcell != cur) {                                   // the run leaves its cell: hand the partial sums over
+                    if (cur >= 0) {
+                        if (DEPOSIT) run_flush<RUN_WINDOW>(g, W, wlo, whi, cur_i, cur_j, cur_k, acc, A.den_fixed);
+                        if (COUNT) atomicAdd(&A.macro_count[cur], cur_count);
                     }
-                    if (DEPOSIT) {
+                    cur = newcell; cur_i = ni_; cur_j = nj_; cur_k = nk_; cur_count = 0;
 #pragma unroll
-                        for (int c = 0; c < 8; c++) acc[c] += qq[c];
-                    }
-                    cur_count += 1.0;
+                    for (int c = 0; c < 8; c++) acc[c] = 0;
                 }
+                if (DEPOSIT) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) acc[c] += qq[c];
+                }
+                cur_count += 1.0;
             }
         }
         // results back to the store (dead slots keep their old contents; the compaction fills them)
@@ -165,10 +161,10 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
             store_run(A.a[0], p0, full, lo, n, x); store_run(A.a[1], p0, full, lo, n, y); store_run(A.a[2], p0, full, lo, n, z);
             store_run(A.a[3], p0, full, lo, n, u); store_run(A.a[4], p0, full, lo, n, v); store_run(A.a[5], p0, full, lo, n, w);
         }
-        // run totals: lanes ending in the same cell are combined before they touch shared / global memory
+        // end of the run: the register sums go to the warp's window, the window to the global grid
         if (DEPOSIT) {
-            warp_accumulate_w<RUN_WINDOW>(g, cur >= 0, cur, acc, win, W, A.den_fixed, lane);
-            window_flush<RUN_WINDOW>(g, win, W, A.den_fixed, lane);
+            if (cur >= 0) run_flush<RUN_WINDOW>(g, W, wlo, whi, cur_i, cur_j, cur_k, acc, A.den_fixed);
+            window_flush<RUN_WINDOW>(g, wlo, whi, W, A.den_fixed, lane);
         }
         if (COUNT) {
             unsigned peers = __match_any_sync(0xffffffffu, cur);
