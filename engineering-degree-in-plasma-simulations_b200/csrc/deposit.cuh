@@ -59,7 +59,7 @@ __device__ __forceinline__ void window_add(unsigned* lo, unsigned* hi, int slot,
     unsigned xl = (unsigned)(u64)v, xh = (unsigned)((u64)v >> 32);
     unsigned old = atomicAdd(&lo[slot], xl);
     unsigned carry = (unsigned)(old + xl < old);
-    if (xh | carry) atomicAdd(&hi[slot], xh + carry);
+    atomicAdd(&hi[slot], xh + carry);
 }
 // Hands the eight corner sums of a finished run (cell (i,j,k)) to the window or, outside it, to the global grid.
 template <int WK>
@@ -68,7 +68,7 @@ __device__ __forceinline__ void run_flush(const Grid& g, const NodeWindow& W, un
     if (window_has<WK>(W, i, j, k)) {
         const int base = k - W.k0;
 #pragma unroll
-        for (int c = 0; c < 8; c++) if (acc[c]) window_add(lo, hi, (c >> 1) * WK + base + (c & 1), acc[c]);
+        for (int c = 0; c < 8; c++) window_add(lo, hi, (c >> 1) * WK + base + (c & 1), acc[c]);
     } else {
 #pragma unroll
         for (int c = 0; c < 8; c++) if (acc[c]) atomicAdd(&den_fixed[corner_node(g, i, j, k, c)], (u64)acc[c]);

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
         double x[4], y[4], z[4], u[4], v[4], w[4], m[4];
         load_run(A.a[0], p0, full, lo, n, x); load_run(A.a[1], p0, full, lo, n, y); load_run(A.a[2], p0, full, lo, n, z);
         if (PUSH) { load_run(A.a[3], p0, full, lo, n, u); load_run(A.a[4], p0, full, lo, n, v); load_run(A.a[5], p0, full, lo, n, w); }
-        if (DEPOSIT || HEAVY) load_run(A.a[6], p0, full, lo, n, m);
+        if (DEPOSIT) load_run(A.a[6], p0, full, lo, n, m);       // a push alone needs the weight only at an ion impact (read there)
         NodeWindow W = {0, 0, 0};
         if (DEPOSIT) {                  // window placed at the column of the warp's first particle (2 nodes of slack below)
             int i = min(max((int)x_to_l(x[0], g.x0[0], g.inv_dx[0]), 0), g.ci - 1);
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
                     if (!in_bounds(g, xn, yn, zn)) dead = true;
                     else if (obj) {
                         HeavyState st = {ox, oy, oz, xn, yn, zn, un, vn, wn};
-                        dead = heavy_after_impact(g, H, A.ef, A.dt, p, obj, m[r], st);
+                        dead = heavy_after_impact(g, H, A.ef, A.dt, p, obj, DEPOSIT ? m[r] : A.a[6][p], st);
                         xn = st.x; yn = st.y; zn = st.z; un = st.u; vn = st.v; wn = st.w;
                     }
                 }
