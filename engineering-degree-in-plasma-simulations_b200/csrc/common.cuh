@@ -41,7 +41,9 @@ struct SpeciesCounters {    // lives in device memory, one per species
     u64 overflow;           // appends dropped because capacity was exhausted
     i64 den_max;            // max fixed-point node sum of the last finalize
     u64 den_neg;            // number of negative (overflowed) nodes seen by finalize
-    u64 pad;
+    u64 pad;                // device-side mover count (sort.cu)
+    u64 n_impact;           // heavy push: particles that ended their first sub-move inside an object (handled by k_heavy_impacts)
+    u64 pad2;
 };
 
 struct picg_world_s {
@@ -80,6 +82,7 @@ struct picg_species_s {
     // exact per-cell lists on top of a stale partition (sort.cu: movers)
     unsigned *home = nullptr, *in_start = nullptr, *out_start = nullptr, *mv_in = nullptr;
     size_t home_cap = 0, lists_cap = 0, mv_cap = 0, mv_stride = 0;
+    bool count_valid = false;          // macro_count holds the per-cell counts of the current particle positions (a deposit produces them for free)
     bool lists_valid = false;          // cell_start + in/out mover lists describe the current cell membership exactly
     bool part_valid = false;           // cell_start is a partition of [0, part_n) (possibly stale: particles may have drifted)
     size_t part_n = 0;                 // upper bound of the particle count at the last sort
@@ -133,7 +136,7 @@ enum KernelId {
     K_PUSH_ELECTRONS = 0, K_PUSH_DEPOSIT, K_PUSH_REFLECT, K_PUSH_HEAVY, K_COMPACT, K_DEPOSIT, K_FINALIZE_DEN,
     K_CHARGE_DENSITY, K_SOR, K_RESIDUAL, K_COMPUTE_EF, K_SORT_KEYS, K_SORT_HIST, K_SORT_SCAN, K_SORT_SCATTER,
     K_SORT_PERMUTE, K_CELL_START, K_MCC, K_SOURCE, K_ADD_PARTICLES, K_MOMENTS, K_COUNT_CELLS, K_TRANSPOSE,
-    K_DIAG, K_MISC, K_PUSH_HEAVY_DEPOSIT, K_NUM_KERNELS
+    K_DIAG, K_MISC, K_PUSH_HEAVY_DEPOSIT, K_HEAVY_IMPACTS, K_NUM_KERNELS
 };
 
 #define CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return picg::cuda_fail(_e, #expr, __FILE__, __LINE__); } while (0)

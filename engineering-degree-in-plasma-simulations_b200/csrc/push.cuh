@@ -38,4 +38,15 @@ __device__ __forceinline__ void record_dead(bool dead, int lane, u64 p, SpeciesC
         if (dead) dead_list[base + __popc(mask & ((1u << lane) - 1))] = (unsigned)p;
     }
 }
+// Same, for any index list with its own cursor (used for the heavy push's impact list).  All 32 lanes must call.
+__device__ __forceinline__ void record_index(bool flag, int lane, u64 p, u64* cursor, unsigned* __restrict__ list) {
+    unsigned mask = __ballot_sync(0xffffffffu, flag);
+    if (mask) {
+        int leader = __ffs(mask) - 1;
+        u64 base = 0;
+        if (lane == leader) base = atomicAdd(cursor, (u64)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (flag) list[base + __popc(mask & ((1u << lane) - 1))] = (unsigned)p;
+    }
+}
 #endif

@@ -41,7 +41,7 @@ struct StepArgs {
     double* a[7]; SpeciesCounters* ctr; u64 n_fixed; int use_fixed_n;      // heavy pushes walk a snapshot of the count (Species.cpp:176)
     const unsigned* tail_from;                                              // non-null: only particles [*tail_from, n) (the part beyond the cell partition)
     const double* ef; double qm_dt, dt;
-    unsigned* dead_list; u64* den_fixed; double scale; double* macro_count;
+    unsigned* dead_list; unsigned* impact_list; u64* den_fixed; double scale; double* macro_count;
 };
 
 __device__ __forceinline__ void ld4_stream(const double* p, double v[4]) {
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
         for (int r = 0; r < RUN_LEN; r++) {
             const u64 p = p0 + r;
             const bool ok = p >= lo && p < n;
-            bool dead = false;
+            bool dead = false, impact = false;
             if (PUSH && ok) {
                 double ex, ey, ez;
                 gather_ef(g, A.ef, x_to_l(x[r], g.x0[0], g.inv_dx[0]), x_to_l(y[r], g.x0[1], g.inv_dx[1]), x_to_l(z[r], g.x0[2], g.inv_dx[2]), ex, ey, ez);
@@ -114,17 +114,14 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
                     xn = __dadd_rn(xn, __dmul_rn(un, A.dt)); yn = __dadd_rn(yn, __dmul_rn(vn, A.dt)); zn = __dadd_rn(zn, __dmul_rn(wn, A.dt));
                     int obj = in_object(g, xn, yn, zn);
                     if (!in_bounds(g, xn, yn, zn)) dead = true;
-                    else if (obj) {
-                        HeavyState st = {ox, oy, oz, xn, yn, zn, un, vn, wn};
-                        dead = heavy_after_impact(g, H, A.ef, A.dt, p, obj, DEPOSIT ? m[r] : A.a[6][p], st);
-                        xn = st.x; yn = st.y; zn = st.z; un = st.u; vn = st.v; wn = st.w;
-                    }
+                    else if (obj) impact = true;          // rare: the whole particle is re-done by k_heavy_impacts from its untouched state
                 }
-                if (!dead) { x[r] = xn; y[r] = yn; z[r] = zn; u[r] = un; v[r] = vn; w[r] = wn; }
+                if (!dead && !impact) { x[r] = xn; y[r] = yn; z[r] = zn; u[r] = un; v[r] = vn; w[r] = wn; }
             }
             if (PUSH) record_dead(dead, lane, p, A.ctr, A.dead_list);
+            if (HEAVY) record_index(impact, lane, p, &A.ctr->n_impact, A.impact_list);
             int newcell = -1, ni_ = 0, nj_ = 0, nk_ = 0; bool have = false; i64 qq[8];
-            if ((DEPOSIT || COUNT) && ok && !dead) {
+            if ((DEPOSIT || COUNT) && ok && !dead && !impact) {
                 int ci, cj, ck; i64 q[8];
                 if (DEPOSIT) scatter_weights_fixed(g, x_to_l(x[r], g.x0[0], g.inv_dx[0]), x_to_l(y[r], g.x0[1], g.inv_dx[1]), x_to_l(z[r], g.x0[2], g.inv_dx[2]),
                                                    m[r], A.scale, ci, cj, ck, q);
@@ -175,6 +172,32 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
     }
 }
 
+// Second pass of the heavy push: the (few) particles whose first sub-move ended inside an object.  Each is re-done from
+// its untouched state: kick, first sub-move, then the reference's bounce loop (surface hit, diffuse re-emission of
+// neutrals, neutralisation of ions with injection of neutrals / sputtered material), Species.cpp:194-249.
+template <bool DEPOSIT, bool COUNT>
+__global__ void __launch_bounds__(128) k_heavy_impacts(Grid g, StepArgs A, HeavyArgs H) {
+    const u64 n_imp = A.ctr->n_impact;
+    for (u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x; t < n_imp; t += (u64)gridDim.x * blockDim.x) {
+        const u64 p = A.impact_list[t];
+        double x = A.a[0][p], y = A.a[1][p], z = A.a[2][p], u = A.a[3][p], v = A.a[4][p], w = A.a[5][p], m = A.a[6][p];
+        double ex, ey, ez;
+        gather_ef(g, A.ef, x_to_l(x, g.x0[0], g.inv_dx[0]), x_to_l(y, g.x0[1], g.inv_dx[1]), x_to_l(z, g.x0[2], g.inv_dx[2]), ex, ey, ez);
+        u = __dadd_rn(u, __dmul_rn(ex, A.qm_dt)); v = __dadd_rn(v, __dmul_rn(ey, A.qm_dt)); w = __dadd_rn(w, __dmul_rn(ez, A.qm_dt));
+        HeavyState st = {x, y, z, __dadd_rn(x, __dmul_rn(u, A.dt)), __dadd_rn(y, __dmul_rn(v, A.dt)), __dadd_rn(z, __dmul_rn(w, A.dt)), u, v, w};
+        int obj = in_object(g, st.x, st.y, st.z);
+        bool gone = heavy_after_impact(g, H, A.ef, A.dt, p, obj, m, st);
+        if (gone) { A.dead_list[atomicAdd(&A.ctr->n_dead, 1ull)] = (unsigned)p; continue; }
+        A.a[0][p] = st.x; A.a[1][p] = st.y; A.a[2][p] = st.z; A.a[3][p] = st.u; A.a[4][p] = st.v; A.a[5][p] = st.w;
+        if (DEPOSIT || COUNT) {
+            int ci, cj, ck; i64 q[8];
+            scatter_weights_fixed(g, x_to_l(st.x, g.x0[0], g.inv_dx[0]), x_to_l(st.y, g.x0[1], g.inv_dx[1]), x_to_l(st.z, g.x0[2], g.inv_dx[2]), m, A.scale, ci, cj, ck, q);
+            if (DEPOSIT) { for (int c = 0; c < 8; c++) if (q[c]) atomicAdd(&A.den_fixed[corner_node(g, ci, cj, ck, c)], (u64)q[c]); }
+            if (COUNT) atomicAdd(&A.macro_count[cell_of(g, ci, cj, ck)], 1.0);
+        }
+    }
+}
+
 namespace picg {
 int launch_finalize(picg_species_s* s);
 int calibrate_scale(picg_species_s* s, bool count_cells);
@@ -198,7 +221,8 @@ int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals
     for (int c = 0; c < 7; c++) A.a[c] = s->a[c];
     A.ctr = s->ctr; A.use_fixed_n = (mode & 2) ? 1 : 0; A.n_fixed = n_snapshot;
     A.ef = s->w->ef; A.qm_dt = dt * s->charge / s->mass; A.dt = dt;                 // Species.cpp:372 `dt*charge/mass`
-    A.dead_list = (unsigned*)s->w->scratch; A.den_fixed = (u64*)s->den_fixed; A.scale = std::ldexp(1.0, s->S); A.macro_count = s->macro_count;
+    A.dead_list = (unsigned*)s->w->scratch; A.impact_list = (unsigned*)((char*)s->w->scratch + compact_scratch_bytes(std::max<size_t>(n_snapshot, 1)));
+    A.den_fixed = (u64*)s->den_fixed; A.scale = std::ldexp(1.0, s->S); A.macro_count = s->macro_count;
     HeavyArgs H; memset(&H, 0, sizeof(H));
     if (mode & 2) {
         uint32_t call = ++s->n_heavy_calls;
@@ -216,18 +240,30 @@ int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals
         A.tail_from = s->cell_start + g.nc;               // the appended tail goes through the generic kernel
         nu = nu - s->part_n;
     }
+    if (mode & 2) CUDA_TRY(cudaMemsetAsync(&s->ctr->n_impact, 0, 8, g_stream));
+    int rc;
     switch (mode) {
-        case 1:  return launch_variant<true, false, false, false>(g, A, H, nu, K_PUSH_ELECTRONS);
-        case 3:  return launch_variant<true, true, false, false>(g, A, H, nu, K_PUSH_HEAVY);
-        case 4:  return launch_variant<false, false, true, false>(g, A, H, nu, K_DEPOSIT);
-        case 12: return launch_variant<false, false, true, true>(g, A, H, nu, K_DEPOSIT);
-        case 8:  return launch_variant<false, false, false, true>(g, A, H, nu, K_COUNT_CELLS);
-        case 5:  return launch_variant<true, false, true, false>(g, A, H, nu, K_PUSH_DEPOSIT);
-        case 13: return launch_variant<true, false, true, true>(g, A, H, nu, K_PUSH_DEPOSIT);
-        case 7:  return launch_variant<true, true, true, false>(g, A, H, nu, K_PUSH_HEAVY_DEPOSIT);
-        case 15: return launch_variant<true, true, true, true>(g, A, H, nu, K_PUSH_HEAVY_DEPOSIT);
+        case 1:  rc = launch_variant<true, false, false, false>(g, A, H, nu, K_PUSH_ELECTRONS); break;
+        case 3:  rc = launch_variant<true, true, false, false>(g, A, H, nu, K_PUSH_HEAVY); break;
+        case 4:  rc = launch_variant<false, false, true, false>(g, A, H, nu, K_DEPOSIT); break;
+        case 12: rc = launch_variant<false, false, true, true>(g, A, H, nu, K_DEPOSIT); break;
+        case 8:  rc = launch_variant<false, false, false, true>(g, A, H, nu, K_COUNT_CELLS); break;
+        case 5:  rc = launch_variant<true, false, true, false>(g, A, H, nu, K_PUSH_DEPOSIT); break;
+        case 13: rc = launch_variant<true, false, true, true>(g, A, H, nu, K_PUSH_DEPOSIT); break;
+        case 7:  rc = launch_variant<true, true, true, false>(g, A, H, nu, K_PUSH_HEAVY_DEPOSIT); break;
+        case 15: rc = launch_variant<true, true, true, true>(g, A, H, nu, K_PUSH_HEAVY_DEPOSIT); break;
         default: return set_error(PICG_ERR_ARG, "launch_step: unsupported mode %d", mode);
     }
+    if (rc) return rc;
+    if (mode & 2) {                                   // surface interactions of the particles that hit an object (usually a handful)
+        int grid = g_sm_count * 2;
+        if ((mode & 4) && (mode & 8)) LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<true, true>), grid, 128, 0, g, A, H);
+        else if (mode & 4) LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<true, false>), grid, 128, 0, g, A, H);
+        else if (mode & 8) LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<false, true>), grid, 128, 0, g, A, H);
+        else LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<false, false>), grid, 128, 0, g, A, H);
+        CHECK_LAUNCH();
+    }
+    return PICG_OK;
 }
 
 // common driver: optional push (electron or heavy), optional deposit (full or partial), optional count
@@ -248,14 +284,16 @@ int species_step(picg_species_s* s, bool push, bool heavy, bool deposit, bool fi
     }
     if (push) {
         if (cap >= 0xffffffffull) return set_error(PICG_ERR_ARG, "more than 2^32-1 particles per GPU are not supported");
-        rc = ensure_scratch(s->w, compact_scratch_bytes(cap)); if (rc) return rc;
+        rc = ensure_scratch(s->w, compact_scratch_bytes(cap) + (heavy ? cap * 4 + 64 : 0)); if (rc) return rc;     // + the heavy push's impact list
     }
+    if (deposit) count = true;                       // the per-cell count is a by-product of the deposit pass (computeMacroParticlesCount then costs nothing)
     int mode = (push ? 1 : 0) | (heavy ? 2 : 0) | (deposit ? 4 : 0) | (count ? 8 : 0);
     rc = launch_step(s, mode, dt, neutrals, spherium, sputtering, n_snapshot); if (rc) return rc;
     if (heavy && s->charge != 0) {
-        for (picg_species_s* t : {neutrals, spherium}) { t->n_host_valid = false; t->sorted_valid = false; t->lists_valid = false; t->n_upper = t->cap; }
+        for (picg_species_s* t : {neutrals, spherium}) { t->n_host_valid = false; t->sorted_valid = false; t->lists_valid = false; t->count_valid = false; t->n_upper = t->cap; }
     }
     if (push) { rc = compact_dead(s, cap); if (rc) return rc; }
+    if (count) s->count_valid = true;                // counted at the post-push positions; the compaction only permutes survivors
     if (deposit && finalize) {
         rc = launch_finalize(s); if (rc) return rc;
         if (!s->S_pinned) {
@@ -312,6 +350,7 @@ int picg_species_deposit_density_partial(picg_species_t s) {
 }
 int picg_species_count_per_cell(picg_species_t s) {
     REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_species_count_per_cell: null species");
+    if (s->count_valid) return PICG_OK;              // already produced by the last deposit pass over the same particle state
     return species_step(s, false, false, false, false, true, 0.0, nullptr, nullptr, 0);
 }
 
