@@ -33,8 +33,8 @@ using namespace picg;
 
 #define RUN_THREADS 256
 #define RUN_WARPS (RUN_THREADS / 32)
-#define RUN_LEN 4
-#define RUN_WARP_CHUNK (32 * RUN_LEN)                        // 128 particles per warp iteration
+#define RUN_LEN_PUSH 4                                       // particles per thread run when the kernel pushes (7 arrays live in registers)
+#define RUN_LEN_SCAN 8                                       // deposit / count only (4 arrays): longer runs, fewer flushes per particle
 #define RUN_WINDOW 64                                        // nodes along k in the per-warp window (4 rows x 64 x 8 B = 2 KB)
 
 struct StepArgs {
@@ -50,18 +50,24 @@ __device__ __forceinline__ void ld4_stream(const double* p, double v[4]) {
 __device__ __forceinline__ void st4_stream(double* p, const double v[4]) {
     asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
-__device__ __forceinline__ void load_run(const double* base, u64 p0, bool full, u64 lo, u64 n, double v[4]) {
-    if (full) ld4_stream(base + p0, v);
-    else {
+template <int RL>
+__device__ __forceinline__ void load_run(const double* base, u64 p0, bool full, u64 lo, u64 n, double* v) {
+    if (full) {
 #pragma unroll
-        for (int r = 0; r < RUN_LEN; r++) v[r] = (p0 + r >= lo && p0 + r < n) ? __ldcs(base + p0 + r) : 0.0;
+        for (int q = 0; q < RL / 4; q++) ld4_stream(base + p0 + 4 * q, v + 4 * q);
+    } else {
+#pragma unroll
+        for (int r = 0; r < RL; r++) v[r] = (p0 + r >= lo && p0 + r < n) ? __ldcs(base + p0 + r) : 0.0;
     }
 }
-__device__ __forceinline__ void store_run(double* base, u64 p0, bool full, u64 lo, u64 n, const double v[4]) {
-    if (full) st4_stream(base + p0, v);
-    else {
+template <int RL>
+__device__ __forceinline__ void store_run(double* base, u64 p0, bool full, u64 lo, u64 n, const double* v) {
+    if (full) {
 #pragma unroll
-        for (int r = 0; r < RUN_LEN; r++) if (p0 + r >= lo && p0 + r < n) __stcs(base + p0 + r, v[r]);
+        for (int q = 0; q < RL / 4; q++) st4_stream(base + p0 + 4 * q, v + 4 * q);
+    } else {
+#pragma unroll
+        for (int r = 0; r < RL; r++) if (p0 + r >= lo && p0 + r < n) __stcs(base + p0 + r, v[r]);
     }
 }
 
@@ -75,13 +81,15 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
     const u64 lo = A.tail_from ? (u64)*A.tail_from : 0;
     const u64 warp = (u64)blockIdx.x * RUN_WARPS + wib, nwarps = (u64)gridDim.x * RUN_WARPS;
 
-    for (u64 chunk = (lo & ~(u64)3) + warp * RUN_WARP_CHUNK; chunk < n; chunk += nwarps * RUN_WARP_CHUNK) {
-        const u64 p0 = chunk + (u64)lane * RUN_LEN;
-        const bool full = p0 >= lo && p0 + RUN_LEN <= n;
-        double x[4], y[4], z[4], u[4], v[4], w[4], m[4];
-        load_run(A.a[0], p0, full, lo, n, x); load_run(A.a[1], p0, full, lo, n, y); load_run(A.a[2], p0, full, lo, n, z);
-        if (PUSH) { load_run(A.a[3], p0, full, lo, n, u); load_run(A.a[4], p0, full, lo, n, v); load_run(A.a[5], p0, full, lo, n, w); }
-        if (DEPOSIT) load_run(A.a[6], p0, full, lo, n, m);       // a push alone needs the weight only at an ion impact (read there)
+    constexpr int RL = PUSH ? RUN_LEN_PUSH : RUN_LEN_SCAN;
+    constexpr int WARP_CHUNK = 32 * RL;
+    for (u64 chunk = (lo & ~(u64)3) + warp * WARP_CHUNK; chunk < n; chunk += nwarps * WARP_CHUNK) {
+        const u64 p0 = chunk + (u64)lane * RL;
+        const bool full = p0 >= lo && p0 + RL <= n;
+        double x[RL], y[RL], z[RL], u[PUSH ? RL : 1], v[PUSH ? RL : 1], w[PUSH ? RL : 1], m[RL];
+        load_run<RL>(A.a[0], p0, full, lo, n, x); load_run<RL>(A.a[1], p0, full, lo, n, y); load_run<RL>(A.a[2], p0, full, lo, n, z);
+        if (PUSH) { load_run<RL>(A.a[3], p0, full, lo, n, u); load_run<RL>(A.a[4], p0, full, lo, n, v); load_run<RL>(A.a[5], p0, full, lo, n, w); }
+        if (DEPOSIT) load_run<RL>(A.a[6], p0, full, lo, n, m);       // a push alone needs the weight only at an ion impact (read there)
         NodeWindow W = {0, 0, 0};
         if (DEPOSIT) {                  // window placed at the column of the warp's first particle (2 nodes of slack below)
             int i = min(max((int)x_to_l(x[0], g.x0[0], g.inv_dx[0]), 0), g.ci - 1);
@@ -93,9 +101,9 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
         int cur = -1, cur_i = 0, cur_j = 0, cur_k = 0; i64 acc[8]; double cur_count = 0;
 #pragma unroll
         for (int c = 0; c < 8; c++) acc[c] = 0;
-        constexpr int kUnroll = (DEPOSIT && PUSH) ? 1 : 4;     // the fused body is too large for the instruction cache when unrolled
+        constexpr int kUnroll = (DEPOSIT && PUSH) ? 1 : RL;     // the fused body is too large for the instruction cache when unrolled
 #pragma unroll kUnroll
-        for (int r = 0; r < RUN_LEN; r++) {
+        for (int r = 0; r < RL; r++) {
             const u64 p = p0 + r;
             const bool ok = p >= lo && p < n;
             bool dead = false, impact = false;
@@ -155,8 +163,8 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
         }
         // results back to the store (dead slots keep their old contents; the compaction fills them)
         if (PUSH) {
-            store_run(A.a[0], p0, full, lo, n, x); store_run(A.a[1], p0, full, lo, n, y); store_run(A.a[2], p0, full, lo, n, z);
-            store_run(A.a[3], p0, full, lo, n, u); store_run(A.a[4], p0, full, lo, n, v); store_run(A.a[5], p0, full, lo, n, w);
+            store_run<RL>(A.a[0], p0, full, lo, n, x); store_run<RL>(A.a[1], p0, full, lo, n, y); store_run<RL>(A.a[2], p0, full, lo, n, z);
+            store_run<RL>(A.a[3], p0, full, lo, n, u); store_run<RL>(A.a[4], p0, full, lo, n, v); store_run<RL>(A.a[5], p0, full, lo, n, w);
         }
         // end of the run: the register sums go to the warp's window, the window to the global grid
         if (DEPOSIT) {
@@ -205,7 +213,8 @@ int check_scale_after(picg_species_s* s);
 
 template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT>
 static int launch_variant(const Grid& g, const StepArgs& A, const HeavyArgs& H, size_t n_upper, int kid) {
-    int grid = std::max(1, std::min(div_up(std::max<size_t>(n_upper, 1), RUN_WARP_CHUNK * RUN_WARPS), g_sm_count * 2 * 4));
+    constexpr int chunk = 32 * (PUSH ? RUN_LEN_PUSH : RUN_LEN_SCAN) * RUN_WARPS;
+    int grid = std::max(1, std::min(div_up(std::max<size_t>(n_upper, 1), chunk), g_sm_count * 2 * 4));
     LAUNCH(kid, (k_run<PUSH, HEAVY, DEPOSIT, COUNT>), grid, RUN_THREADS, 0, g, A, H);
     CHECK_LAUNCH();
     return PICG_OK;
