@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--moments", action="store_true", help="also run Species::sampleMoments every step (SURVEY 8f row 1)")
     ap.add_argument("--cpu_sample_nodes", type=int, default=49, help="nodes per axis of the CPU-baseline sub-volume (same dx, same particles per cell)")
     ap.add_argument("--skip_cpu_baseline", action="store_true")
+    ap.add_argument("--init_max_it", type=int, default=20000, help="iteration cap of the initial vacuum solve (profiling runs use a small value)")
     ap.add_argument("--inject", type=int, default=1 << 20, help="e2e: electrons injected from pinned host memory per step")
     return ap.parse_args()
 
@@ -165,7 +166,7 @@ def run_ours(args):
     w.computeObjectID()
     sol = pg.PotentialSolver(w, args.s_max_it, args.s_tol)
     sol.setReferenceValues(0.0, 0.0, 1e20)                 # main.cpp:138
-    cold = pg.PotentialSolver(w, 20000, args.s_tol)          # initial vacuum solve (main.cpp:172-173)
+    cold = pg.PotentialSolver(w, args.init_max_it, args.s_tol)   # initial vacuum solve (main.cpp:172-173)
     cold.setReferenceValues(0.0, 0.0, 1e20)
     t0 = time.time()
     cold.solveGS(); cold.computeEF()
