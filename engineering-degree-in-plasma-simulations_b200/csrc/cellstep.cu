@@ -1,203 +1,281 @@
-// Cell-centric particle kernel: the fast path of push / deposit / count for a species whose store carries a cell
-// partition (cell_start[] from the last sort).  Same arithmetic per particle as k_step (step.cu) and the reference
-// (ch4/v3/src/Species.cpp:356-416, Field.h:157-232); only the work decomposition differs.
+// Cell-group deposit: the fast path of Species::computeNumberDensity (ch4/v3/src/Species.cpp:401-413, Field::scatter
+// Field.h:157-199) and Species::computeMacroParticlesCount (:813-819) for a species whose store carries a cell partition
+// (cell_start[] of the last sort, possibly stale).  Same arithmetic per particle as k_run (step.cu); only the work
+// decomposition and the data movement differ.
 //
-//   one WARP owns one CELL:  particles [cell_start[c], cell_start[c+1]) are contiguous, so
-//     * their loads and stores are coalesced streaming accesses (ld.global.cs / st.global.cs: they must not evict the
-//       field from L2);
-//     * the 8 corner nodes of E are the same for every particle that is still in cell c: the warp fetches the
-//       24 values ONCE per cell into shared memory and the trilinear gather becomes broadcast LDS + arithmetic -
-//       no dependent per-particle global gather is left on the critical path;
-//     * the 8 fixed-point corner sums of the deposit are accumulated in registers over the whole cell and leave the
-//       warp once per cell through a transposed butterfly and 8 global integer atomics (not 8 per particle).
-//   Particles that drifted out of the cell since the last sort ("stragglers"), and particles moved into holes by the
-//   compaction, are handled individually (global gather / global atomics): correctness never depends on how stale
-//   the partition is, only speed does.  Particles appended after the sort lie beyond the partition and are covered
-//   by a launch of the generic kernel on that tail.
-// Algorithmic bytes per particle: push 96 B, deposit 32 B, fused 104 B.
+//   * STREAMS THROUGH TMA.  A warp owns a PASS of P = 32/G consecutive cells = one contiguous particle range.  Lane 0
+//     issues one cp.async.bulk (global -> shared, mbarrier complete_tx, L2 evict-first) per particle array for the NEXT
+//     chunk of the range while the warp computes on the current one (two stages per warp): the loads never occupy
+//     registers and never stall the computing lanes.
+//   * G LANES PER CELL (G = 4, 8, 16 or 32, chosen per launch from the mean cell population so that a lane sees ~5 particles
+//     of its cell).  The particles of a cell are consecutive and all (but the stragglers) share the cell's eight nodes, so
+//     the eight fixed-point corner sums stay in registers for the whole cell: no cell-change test, no shared-memory
+//     atomics, no divergent flush.  "Still in its home cell" is 0 <= l - c < 1 on the already formed fractional
+//     coordinates (exact, see below), tested on the high words - no float->int conversions.
+//   * QUANTISATION ON THE FP64 PIPE.  q = llrint(w) is taken from the mantissa of w + 1.5*2^52 (round-to-nearest-even, the
+//     same integer for 0 <= w < 2^51; larger weights take the generic path), the biased words are summed as integers and
+//     the bias (trips x bits(1.5*2^52)) is removed once per cell.  No F2I on the slow conversion pipe.
+//   * ONE EXIT PER CELL.  A transposed butterfly inside the lane group (the payload halves every round) leaves each
+//     corner sum in one lane; the (.., k+1) sums are handed to the next group when its cell is the next cell of the same
+//     column (they share the nodes), and what is left goes out as RED.64: about 4.5 global reductions per cell.
+//   * Stragglers (particles that drifted out of the slot's home cell since the sort, or that the compaction moved into a
+//     hole) deposit on their own with global reductions: correctness never depends on how stale the partition is.
+//     Particles appended after the sort lie beyond the partition and go through k_run on that tail (step.cu).
+// Algorithmic bytes per particle: deposit 32 B (pos + mpw), count 24 B.
 #include "common.cuh"
-#include "push.cuh"
 #include "deposit.cuh"
-#include "samplers.cuh"
-#include "heavy.cuh"
 #include <algorithm>
 #include <cmath>
 
 using namespace picg;
 
-#define CS_THREADS 256
-#define CS_WARPS (CS_THREADS / 32)
+#define CG_THREADS 256
+#define CG_WARPS (CG_THREADS / 32)
+#define CG_CAP 192                                  // particles per stage and array (1.5 KB)
+#define CG_CHUNK (CG_CAP - 2)                       // the copied range is widened to even particle indices (16-byte alignment)
 
 struct CellArgs {
-    double* a[7]; SpeciesCounters* ctr; u64 n_limit;        // particles [0, n_limit) are covered by the partition
-    const unsigned* cell_start; const double* ef; double qm_dt, dt;
-    unsigned* dead_list; u64* den_fixed; double scale; double* macro_count;
+    const double* a[4];                             // x y z mpw
+    const SpeciesCounters* ctr; u64 n_limit;        // particles [0, n_limit) are covered by the partition (~0: the live count)
+    const unsigned* cell_start; u64* den_fixed; double scale; double* macro_count;
 };
 
-// Field<Vec3>::gather (Field.h:201-232) from four row pointers (rows (i,j) (i,j+1) (i+1,j) (i+1,j+1), each holding the
-// nodes k and k+1 as 6 consecutive doubles).  Identical association to gather_ef().
-__device__ __forceinline__ void gather_rows(const double* r00, const double* r01, const double* r10, const double* r11,
-                                            double di, double dj, double dk, double& ex, double& ey, double& ez) {
-    double odi = __dsub_rn(1.0, di), odj = __dsub_rn(1.0, dj), odk = __dsub_rn(1.0, dk);
-    double wa = __dmul_rn(odi, odj), wb = __dmul_rn(odi, dj), wc = __dmul_rn(di, odj), wd = __dmul_rn(di, dj);
-    double acc[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        double v;
-        v = __dmul_rn(__dmul_rn(r00[c], wa), odk);
-        v = __dadd_rn(v, __dmul_rn(__dmul_rn(r00[3 + c], wa), dk));
-        v = __dadd_rn(v, __dmul_rn(__dmul_rn(r01[c], wb), odk));
-        v = __dadd_rn(v, __dmul_rn(__dmul_rn(r01[3 + c], wb), dk));
-        v = __dadd_rn(v, __dmul_rn(__dmul_rn(r10[c], wc), odk));
-        v = __dadd_rn(v, __dmul_rn(__dmul_rn(r10[3 + c], wc), dk));
-        v = __dadd_rn(v, __dmul_rn(__dmul_rn(r11[c], wd), odk));
-        v = __dadd_rn(v, __dmul_rn(__dmul_rn(r11[3 + c], wd), dk));
-        acc[c] = v;
-    }
-    ex = acc[0]; ey = acc[1]; ez = acc[2];
+// ---------------------------------------------------------------- PTX: mbarrier + bulk async copy (TMA, 1-D)
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
+    asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n}"
+                 :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, u64* bar, u64 policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ u64 policy_evict_first() {
+    u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
 }
 
-template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT>
-__global__ void __launch_bounds__(CS_THREADS, 3) k_cell_step(Grid g, CellArgs A, HeavyArgs H) {
-    __shared__ double s_E[CS_WARPS][24];
+// ---------------------------------------------------------------- the kernel
+// Uniform per warp (every lane holds the same values) except cs: lane l <= P holds cell_start[c0 + l] of the pass.
+struct Cursor { int pass; unsigned cs, cs_next, pos, end; };
+struct Item { int pass; unsigned cs, lo, hi; bool last; };
+
+template <bool DEPOSIT, bool COUNT, int LG>
+__global__ void __launch_bounds__(CG_THREADS, 2) k_cell_deposit(Grid g, CellArgs A) {
+    constexpr int NA = DEPOSIT ? 4 : 3;
+    constexpr int G = 1 << LG, P = 32 >> LG;                    // lanes per cell, cells per pass
+    extern __shared__ __align__(128) unsigned char cg_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int warp = blockIdx.x * CS_WARPS + wib, nwarps = gridDim.x * CS_WARPS;
-    double* E = s_E[wib];
-    const u64 n_limit = (A.n_limit == ~0ull) ? A.ctr->n : A.n_limit;
-    const size_t row_j = (size_t)g.nk * 3, row_i = (size_t)g.nj * g.nk * 3;
+    double* wbuf = reinterpret_cast<double*>(cg_smem) + (size_t)wib * 2 * NA * CG_CAP;
+    u64* bars = reinterpret_cast<u64*>(reinterpret_cast<double*>(cg_smem) + (size_t)CG_WARPS * 2 * NA * CG_CAP) + wib * 2;
+    if (lane == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    const u64 policy = policy_evict_first();
+    // the partition covers [0, n_lim): live particles that were in the store at the last sort
+    const unsigned n_lim = (unsigned)min(min(A.n_limit == ~0ull ? A.ctr->n : A.n_limit, (u64)__ldg(A.cell_start + g.nc)), (u64)0xfffffff0u);
+    const int npass = (g.nc + P - 1) / P;
+    const int nw = gridDim.x * CG_WARPS;
+    const int grp = lane >> LG, sub = lane & (G - 1);
 
-    for (int cell = warp; cell < g.nc; cell += nwarps) {
-        const u64 s = A.cell_start[cell];
-        u64 e = A.cell_start[cell + 1];
-        if (e > n_limit) e = n_limit;
-        if (s >= e) continue;                                             // warp-uniform
-        int ci, cj, ck; cell_to_ijk(g, cell, ci, cj, ck);
-        if (PUSH) {                                                       // the cell's 8 E nodes: 4 rows x (k, k+1) x 3 components
-            __syncwarp();
-            if (lane < 24) {
-                int q = lane / 6, t = lane - q * 6;
-                size_t base = ((size_t)((ci + (q >> 1)) * g.nj + (cj + (q & 1))) * g.nk + ck) * 3;
-                E[lane] = __ldg(A.ef + base + t);
-            }
-            __syncwarp();
+    auto load_cs = [&](int pass) -> unsigned {
+        if (pass >= npass) return 0u;
+        return min(__ldg(A.cell_start + min(pass * P + min(lane, P), g.nc)), n_lim);
+    };
+    auto next_pass = [&](Cursor& F) {
+        F.pass += nw; F.cs = F.cs_next; F.cs_next = load_cs(F.pass + nw);
+        F.pos = __shfl_sync(0xffffffffu, F.cs, 0); F.end = __shfl_sync(0xffffffffu, F.cs, P);
+    };
+    auto skip_empty = [&](Cursor& F) { while (F.pass < npass && F.pos >= F.end) next_pass(F); };
+    auto take = [&](Cursor& F) -> Item {                       // the chunk at the cursor; moves the cursor past it
+        Item it; it.pass = F.pass; it.cs = F.cs; it.lo = F.pos; it.hi = min(F.pos + CG_CHUNK, F.end); it.last = it.hi == F.end;
+        F.pos = it.hi;
+        if (it.last) { next_pass(F); skip_empty(F); }
+        return it;
+    };
+    auto issue = [&](const Item& it, int stage) {              // lane 0: one bulk copy per array into the stage
+        if (lane == 0) {
+            const unsigned a0 = it.lo & ~1u, a1 = (it.hi + 1) & ~1u, bytes = (a1 - a0) * 8;
+            mbar_expect_tx(&bars[stage], NA * bytes);
+#pragma unroll
+            for (int c = 0; c < NA; c++) bulk_g2s(wbuf + (size_t)(stage * NA + c) * CG_CAP, A.a[c] + a0, bytes, &bars[stage], policy);
         }
-        i64 acc[8]; double cnt = 0;
-#pragma unroll
-        for (int c = 0; c < 8; c++) acc[c] = 0;
+    };
 
-        for (u64 base = s; base < e; base += 32) {
-            const u64 p = base + lane;
-            const bool ok = p < e;
-            bool dead = false;
-            double x = 0, y = 0, z = 0, u = 0, v = 0, w = 0, m = 0;
-            if (ok) {
-                x = __ldcs(A.a[0] + p); y = __ldcs(A.a[1] + p); z = __ldcs(A.a[2] + p);
-                if (PUSH) { u = __ldcs(A.a[3] + p); v = __ldcs(A.a[4] + p); w = __ldcs(A.a[5] + p); }
-                if (DEPOSIT || HEAVY) m = __ldcs(A.a[6] + p);
-            }
-            if (PUSH && ok) {
-                double lx = x_to_l(x, g.x0[0], g.inv_dx[0]), ly = x_to_l(y, g.x0[1], g.inv_dx[1]), lz = x_to_l(z, g.x0[2], g.inv_dx[2]);
-                int i = min((int)lx, g.ni - 2), j = min((int)ly, g.nj - 2), k = min((int)lz, g.nk - 2);
-                double di = __dsub_rn(lx, (double)i), dj = __dsub_rn(ly, (double)j), dk = __dsub_rn(lz, (double)k);
-                double ex, ey, ez;
-                if (i == ci && j == cj && k == ck) gather_rows(E, E + 6, E + 12, E + 18, di, dj, dk, ex, ey, ez);
-                else {                                                    // straggler: its own 8 nodes from global memory
-                    const double* r00 = A.ef + ((size_t)(i * g.nj + j) * g.nk + k) * 3;
-                    gather_rows(r00, r00 + row_j, r00 + row_i, r00 + row_i + row_j, di, dj, dk, ex, ey, ez);
-                }
-                u = __dadd_rn(u, __dmul_rn(ex, A.qm_dt)); v = __dadd_rn(v, __dmul_rn(ey, A.qm_dt)); w = __dadd_rn(w, __dmul_rn(ez, A.qm_dt));
-                if (!HEAVY) {
-                    x = __dadd_rn(x, __dmul_rn(u, A.dt)); y = __dadd_rn(y, __dmul_rn(v, A.dt)); z = __dadd_rn(z, __dmul_rn(w, A.dt));
-                    dead = !in_bounds(g, x, y, z) || in_object(g, x, y, z) != 0;             // Species.cpp:375-388
-                } else {
-                    double t_rem = 1; int n_b = 0; bool rng_ready = false; PhiloxStream rs;
-                    while (t_rem > 0) {
-                        if (++n_b > 20) { dead = true; break; }                                // :198-203
-                        const double ox = x, oy = y, oz = z;
-                        x = __dadd_rn(x, __dmul_rn(__dmul_rn(u, t_rem), A.dt));
-                        y = __dadd_rn(y, __dmul_rn(__dmul_rn(v, t_rem), A.dt));
-                        z = __dadd_rn(z, __dmul_rn(__dmul_rn(w, t_rem), A.dt));
-                        int obj = in_object(g, x, y, z);
-                        if (!in_bounds(g, x, y, z)) { dead = true; break; }
-                        if (obj) {
-                            if (!rng_ready) { rs.init(H.seed, H.stream, p, H.call); rng_ready = true; }
-                            double xx[3] = {x, y, z}, vv[3] = {u, v, w}, oo[3] = {ox, oy, oz};
-                            bool absorbed = surface_interaction(g, H, A.ef, rs, obj, oo, xx, vv, m, t_rem);
-                            x = xx[0]; y = xx[1]; z = xx[2]; u = vv[0]; v = vv[1]; w = vv[2];
-                            if (absorbed) { dead = true; break; }
-                            continue;
-                        }
-                        t_rem = 0;
-                    }
-                }
-                if (!dead) {
-                    __stcs(A.a[0] + p, x); __stcs(A.a[1] + p, y); __stcs(A.a[2] + p, z);
-                    __stcs(A.a[3] + p, u); __stcs(A.a[4] + p, v); __stcs(A.a[5] + p, w);
-                }
-            }
-            if (PUSH) record_dead(dead, lane, p, A.ctr, A.dead_list);
-            if ((DEPOSIT || COUNT) && ok && !dead) {
-                int i, j, k; i64 q[8];
-                if (DEPOSIT) scatter_weights_fixed(g, x_to_l(x, g.x0[0], g.inv_dx[0]), x_to_l(y, g.x0[1], g.inv_dx[1]), x_to_l(z, g.x0[2], g.inv_dx[2]), m, A.scale, i, j, k, q);
-                else {
-                    i = min((int)x_to_l(x, g.x0[0], g.inv_dx[0]), g.ci - 1); j = min((int)x_to_l(y, g.x0[1], g.inv_dx[1]), g.cj - 1);
-                    k = min((int)x_to_l(z, g.x0[2], g.inv_dx[2]), g.ck - 1);
-                }
-                if (i == ci && j == cj && k == ck) {
-                    if (DEPOSIT) {
+    Cursor F; F.pass = blockIdx.x * CG_WARPS + wib;
+    F.cs = load_cs(F.pass); F.cs_next = load_cs(F.pass + nw);
+    F.pos = __shfl_sync(0xffffffffu, F.cs, 0); F.end = __shfl_sync(0xffffffffu, F.cs, P);
+    skip_empty(F);
+    if (F.pass >= npass) return;                               // warp-uniform
+    Item cur = take(F);
+    issue(cur, 0);
+    unsigned phase0 = 0, phase1 = 0; int stage = 0;
+
+    constexpr double kMagic = 6755399441055744.0;              // 1.5 * 2^52: w + kMagic holds llrint(w) in its low mantissa bits for 0 <= w < 2^51
+    constexpr int kMagicHi = 0x43380000;                       // high word of kMagic (its low word is 0)
+    i64 acc[8]; int cnt = 0; int trips = 0;                    // acc carries trips * bits(kMagic) of bias until the flush
 #pragma unroll
-                        for (int c = 0; c < 8; c++) acc[c] += q[c];
-                    }
-                    cnt += 1.0;
-                } else {                                                  // left the cell: deposit on its own
+    for (int c = 0; c < 8; c++) acc[c] = 0;
+    const double x0 = g.x0[0], y0 = g.x0[1], z0 = g.x0[2], idx = g.inv_dx[0], idy = g.inv_dx[1], idz = g.inv_dx[2];
+    const int scale_hi = __double2hiint(A.scale);              // scale = 2^S: its low word is 0
+
+    while (true) {
+        const bool more = F.pass < npass;
+        Item nxt = cur;
+        if (more) { nxt = take(F); issue(nxt, stage ^ 1); }
+        // ---- this lane's share of the chunk: cell c0+grp, particles [my_lo, my_hi), every G-th from sub
+        const int cell = cur.pass * P + grp;
+        const unsigned s_g = __shfl_sync(0xffffffffu, cur.cs, grp), e_g = __shfl_sync(0xffffffffu, cur.cs, grp + 1);
+        const unsigned my_lo = max(s_g, cur.lo), my_hi = min(e_g, cur.hi);
+        const int len = my_hi > my_lo ? (int)(my_hi - my_lo) : 0;
+        const int ntrip = __reduce_max_sync(0xffffffffu, (len + G - 1) >> LG);
+        int ci = 0, cj = 0, ck = 0;
+        if (cell < g.nc) cell_to_ijk(g, cell, ci, cj, ck);
+        const double dci = (double)ci, dcj = (double)cj, dck = (double)ck;
+        const unsigned a0 = cur.lo & ~1u;
+        const double* sx = wbuf + (size_t)(stage * NA) * CG_CAP; const double* sy = sx + CG_CAP; const double* sz = sy + CG_CAP; const double* sm = sz + CG_CAP;
+        mbar_wait(&bars[stage], stage ? phase1 : phase0);
+        if (stage) phase1 ^= 1; else phase0 ^= 1;
+        trips += ntrip;
+#pragma unroll 2
+        for (int t = 0; t < ntrip; t++) {
+            const unsigned p = my_lo + (t << LG) + sub;
+            const bool ok = p < my_hi;
+            const unsigned off = ok ? p - a0 : 0u;
+            const double lx = x_to_l(sx[off], x0, idx), ly = x_to_l(sy[off], y0, idy), lz = x_to_l(sz[off], z0, idz);
+            // (int)l == c  <=>  0 <= l - c < 1 (the subtraction is exact for l in [c, c+1)), and then l - c is the reference's
+            // fractional weight l - (double)(int)l bit for bit (Field.h:161-169).  The reference's index clamp never acts here.
+            // 0 <= d < 1  <=>  high word of d, as unsigned, below that of 1.0 (negative values and NaN have larger high words).
+            const double di = __dsub_rn(lx, dci), dj = __dsub_rn(ly, dcj), dk = __dsub_rn(lz, dck);
+            bool home = ok && (unsigned)__double2hiint(di) < 0x3ff00000u && (unsigned)__double2hiint(dj) < 0x3ff00000u && (unsigned)__double2hiint(dk) < 0x3ff00000u;
+            if (DEPOSIT) {
+                const double m = sm[off];
+                home = home && (unsigned)__double2hiint(m) < (unsigned)(0x43200000 - (scale_hi - 0x3ff00000));   // 0 <= m * 2^S < 2^51
+                const double odi = __dsub_rn(1.0, di), odj = __dsub_rn(1.0, dj), odk = __dsub_rn(1.0, dk);
+                const double vs = __dmul_rn(m, __hiloint2double(home ? scale_hi : 0, 0));   // zero weight: every product below is +-0
+                const double a_ = __dmul_rn(vs, odi), b_ = __dmul_rn(vs, di);
+                const double w00 = __dmul_rn(a_, odj), w01 = __dmul_rn(a_, dj), w10 = __dmul_rn(b_, odj), w11 = __dmul_rn(b_, dj);
+                acc[0] += __double_as_longlong(__dadd_rn(__dmul_rn(w00, odk), kMagic)); acc[1] += __double_as_longlong(__dadd_rn(__dmul_rn(w00, dk), kMagic));
+                acc[2] += __double_as_longlong(__dadd_rn(__dmul_rn(w01, odk), kMagic)); acc[3] += __double_as_longlong(__dadd_rn(__dmul_rn(w01, dk), kMagic));
+                acc[4] += __double_as_longlong(__dadd_rn(__dmul_rn(w10, odk), kMagic)); acc[5] += __double_as_longlong(__dadd_rn(__dmul_rn(w10, dk), kMagic));
+                acc[6] += __double_as_longlong(__dadd_rn(__dmul_rn(w11, odk), kMagic)); acc[7] += __double_as_longlong(__dadd_rn(__dmul_rn(w11, dk), kMagic));
+            }
+            cnt += home ? 1 : 0;
+            const bool stray = ok && !home;
+            if (__any_sync(0xffffffffu, stray)) {
+                if (stray) {                                                              // generic path, reference index rules
+                    int i, j, k; i64 q[8];
                     if (DEPOSIT) {
+                        scatter_weights_fixed(g, lx, ly, lz, sm[off], A.scale, i, j, k, q);
 #pragma unroll
                         for (int c = 0; c < 8; c++) if (q[c]) atomicAdd(&A.den_fixed[corner_node(g, i, j, k, c)], (u64)q[c]);
-                    }
+                    } else { i = min((int)lx, g.ci - 1); j = min((int)ly, g.cj - 1); k = min((int)lz, g.ck - 1); }
                     if (COUNT) atomicAdd(&A.macro_count[cell_of(g, i, j, k)], 1.0);
                 }
             }
         }
-        // once per cell: combine the 32 lanes (transposed butterfly, deposit.cuh) and hand the 8 corner sums over
-        if (DEPOSIT) {
-            i64 t = butterfly8(acc, lane);
-            if ((lane & 3) == 0 && t != 0) atomicAdd(&A.den_fixed[corner_node(g, ci, cj, ck, lane >> 2)], (u64)t);
+        // ---- end of a pass: the lane groups' sums leave the registers.  Corner c = 4a + 2b + d (a, b, d = the i, j, k offsets);
+        // the butterfly splits on a (lane bit G/2), then b (G/4), then d (G/8): the payload halves every round; the
+        // remaining rounds (G > 8) are plain sums.
+        if (cur.last) {
+            const bool cell_ok = cell < g.nc;
+            if (DEPOSIT) {
+                const unsigned bias = (unsigned)trips * (unsigned)kMagicHi;              // the low word of bits(kMagic) is 0
+#pragma unroll
+                for (int c = 0; c < 8; c++) acc[c] -= (i64)((u64)bias << 32);
+                const bool ba = sub & (G >> 1), bb = sub & (G >> 2);
+                i64 v0 = (ba ? acc[4] : acc[0]) + __shfl_xor_sync(0xffffffffu, ba ? acc[0] : acc[4], G >> 1);
+                i64 v1 = (ba ? acc[5] : acc[1]) + __shfl_xor_sync(0xffffffffu, ba ? acc[1] : acc[5], G >> 1);
+                i64 v2 = (ba ? acc[6] : acc[2]) + __shfl_xor_sync(0xffffffffu, ba ? acc[2] : acc[6], G >> 1);
+                i64 v3 = (ba ? acc[7] : acc[3]) + __shfl_xor_sync(0xffffffffu, ba ? acc[3] : acc[7], G >> 1);
+                i64 t0 = (bb ? v2 : v0) + __shfl_xor_sync(0xffffffffu, bb ? v0 : v2, G >> 2);          // node (ci+a, cj+b, ck)
+                i64 t1 = (bb ? v3 : v1) + __shfl_xor_sync(0xffffffffu, bb ? v1 : v3, G >> 2);          // node (ci+a, cj+b, ck+1)
+                // the next group's cell is the next cell of the same column: its (.., ck') nodes are this group's (.., ck+1) nodes
+                const bool chain = grp + 1 < P && cell + 1 < g.nc && ck + 1 < g.ck;
+                const bool prev_chains = __shfl_up_sync(0xffffffffu, (int)chain, G) != 0 && grp > 0;
+                u64* node = A.den_fixed + ((size_t)((ci + (ba ? 1 : 0)) * g.nj + (cj + (bb ? 1 : 0))) * g.nk + ck);
+                if (LG == 2) {                                                            // lane holds (a, b; d): two nodes along k
+                    const i64 from_prev = __shfl_up_sync(0xffffffffu, t1, G);
+                    if (prev_chains) t0 += from_prev;
+                    if (cell_ok) {
+                        if (t0 != 0) atomicAdd(node, (u64)t0);
+                        if (!chain && t1 != 0) atomicAdd(node + 1, (u64)t1);
+                    }
+                } else {                                                                  // one more split on d, then plain sums: one node per lane
+                    const bool bd = sub & (G >> 3);
+                    i64 u0 = (bd ? t1 : t0) + __shfl_xor_sync(0xffffffffu, bd ? t0 : t1, G >> 3);
+#pragma unroll
+                    for (int dist = G >> 4; dist >= 1; dist >>= 1) u0 += __shfl_xor_sync(0xffffffffu, u0, dist);
+                    const i64 from_prev = __shfl_sync(0xffffffffu, u0, max(lane - G + (G >> 3), 0));   // same (a, b), d = 1, previous group
+                    if (prev_chains && !bd) u0 += from_prev;
+                    const bool writer = (sub & ((G >> 3) - 1)) == 0;
+                    if (cell_ok && writer && u0 != 0 && !(bd && chain)) atomicAdd(node + (bd ? 1 : 0), (u64)u0);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) acc[c] = 0;
+            }
+            if (COUNT) {
+                int tot = cnt;
+#pragma unroll
+                for (int dist = G >> 1; dist >= 1; dist >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, dist);
+                if (sub == 0 && cell_ok && tot != 0) atomicAdd(&A.macro_count[cell], (double)tot);         // integer-valued: exact in any order
+            }
+            cnt = 0; trips = 0;
         }
-        if (COUNT) {
-            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);      // integer-valued: exact
-            if (lane == 0 && cnt != 0) atomicAdd(&A.macro_count[cell], cnt);
-        }
+        if (!more) break;
+        __syncwarp();                                          // every lane is done with this stage before it is refilled
+        cur = nxt; stage ^= 1;
     }
 }
 
 namespace picg {
-template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT>
-static int launch_cell_variant(const Grid& g, const CellArgs& A, const HeavyArgs& H, int kid) {
-    int grid = std::max(1, std::min(div_up((size_t)g.nc, CS_WARPS), g_sm_count * 3 * 4));
-    LAUNCH(kid, (k_cell_step<PUSH, HEAVY, DEPOSIT, COUNT>), grid, CS_THREADS, 0, g, A, H);
+static size_t cell_smem_bytes(int na) { return (size_t)CG_WARPS * 2 * na * CG_CAP * 8 + CG_WARPS * 2 * 8; }
+
+template <bool DEPOSIT, bool COUNT, int LG>
+static int launch_cell_variant(const Grid& g, const CellArgs& A, int kid) {
+    static bool attr_set = false;
+    const size_t smem = cell_smem_bytes(DEPOSIT ? 4 : 3);
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_cell_deposit<DEPOSIT, COUNT, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    const int npass = div_up((size_t)g.nc, 32 >> LG);
+    int grid = std::max(1, std::min(div_up((size_t)npass, CG_WARPS), g_sm_count * 2));
+    LAUNCH(kid, (k_cell_deposit<DEPOSIT, COUNT, LG>), grid, CG_THREADS, smem, g, A);
     CHECK_LAUNCH();
     return PICG_OK;
 }
+template <int LG>
+static int launch_cell_mode(const Grid& g, const CellArgs& A, int mode) {
+    switch (mode) {
+        case 4:  return launch_cell_variant<true, false, LG>(g, A, K_DEPOSIT);
+        case 12: return launch_cell_variant<true, true, LG>(g, A, K_DEPOSIT);
+        case 8:  return launch_cell_variant<false, true, LG>(g, A, K_COUNT_CELLS);
+        default: return set_error(PICG_ERR_ARG, "launch_cell_step: unsupported mode %d", mode);
+    }
+}
 
-// mode bits as in launch_step: 1 push, 2 heavy, 4 deposit, 8 count.  Covers particles [0, n_limit).
-int launch_cell_step(picg_species_s* s, int mode, double dt, const HeavyArgs& H, size_t n_limit) {
+// mode bits as in launch_step (step.cu): 4 deposit, 8 count (no push variants).  Covers particles [0, min(n_limit, partition)).
+// n_est: an estimate of the particle count (sizes the lane groups: about 5 particles of a cell per lane).
+int launch_cell_step(picg_species_s* s, int mode, size_t n_limit, size_t n_est) {
     const Grid& g = s->w->g;
     CellArgs A;
-    for (int c = 0; c < 7; c++) A.a[c] = s->a[c];
-    A.ctr = s->ctr; A.n_limit = n_limit; A.cell_start = s->cell_start; A.ef = s->w->ef;
-    A.qm_dt = dt * s->charge / s->mass; A.dt = dt;
-    A.dead_list = (unsigned*)s->w->scratch; A.den_fixed = (u64*)s->den_fixed; A.scale = std::ldexp(1.0, s->S); A.macro_count = s->macro_count;
-    switch (mode) {
-        case 1:  return launch_cell_variant<true, false, false, false>(g, A, H, K_PUSH_ELECTRONS);
-        case 3:  return launch_cell_variant<true, true, false, false>(g, A, H, K_PUSH_HEAVY);
-        case 4:  return launch_cell_variant<false, false, true, false>(g, A, H, K_DEPOSIT);
-        case 12: return launch_cell_variant<false, false, true, true>(g, A, H, K_DEPOSIT);
-        case 8:  return launch_cell_variant<false, false, false, true>(g, A, H, K_COUNT_CELLS);
-        case 5:  return launch_cell_variant<true, false, true, false>(g, A, H, K_PUSH_DEPOSIT);
-        case 13: return launch_cell_variant<true, false, true, true>(g, A, H, K_PUSH_DEPOSIT);
-        case 7:  return launch_cell_variant<true, true, true, false>(g, A, H, K_PUSH_HEAVY_DEPOSIT);
-        case 15: return launch_cell_variant<true, true, true, true>(g, A, H, K_PUSH_HEAVY_DEPOSIT);
-        default: return set_error(PICG_ERR_ARG, "launch_cell_step: unsupported mode %d", mode);
+    A.a[0] = s->a[0]; A.a[1] = s->a[1]; A.a[2] = s->a[2]; A.a[3] = s->a[6];
+    A.ctr = s->ctr; A.n_limit = n_limit; A.cell_start = s->cell_start;
+    A.den_fixed = (u64*)s->den_fixed; A.scale = std::ldexp(1.0, s->S); A.macro_count = s->macro_count;
+    static const int force_lg = getenv("PICG_CELL_LG") ? atoi(getenv("PICG_CELL_LG")) : 0;             // tuning switch
+    const double ppc = (double)n_est / std::max(1, g.nc);
+    int lg = force_lg ? force_lg : (ppc <= 26 ? 2 : ppc <= 52 ? 3 : ppc <= 104 ? 4 : 5);
+    switch (lg) {
+        case 2:  return launch_cell_mode<2>(g, A, mode);
+        case 3:  return launch_cell_mode<3>(g, A, mode);
+        case 4:  return launch_cell_mode<4>(g, A, mode);
+        default: return launch_cell_mode<5>(g, A, mode);
     }
 }
 }  // namespace picg

@@ -221,7 +221,7 @@ static int launch_variant(const Grid& g, const StepArgs& A, const HeavyArgs& H, 
 }
 
 // mode bits: 1 push, 2 heavy, 4 deposit, 8 count
-int launch_cell_step(picg_species_s* s, int mode, double dt, const HeavyArgs& H, size_t n_limit);     // cellstep.cu
+int launch_cell_step(picg_species_s* s, int mode, size_t n_limit, size_t n_est);     // cellstep.cu: deposit / count over the cell partition
 
 int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals, picg_species_s* spherium, int sputtering, size_t n_snapshot) {
     const Grid& g = s->w->g;
@@ -241,10 +241,11 @@ int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals
     if (mode & 4) cudaMemsetAsync(s->den_fixed, 0, (size_t)g.nv * 8, g_stream);
     if (mode & 8) cudaMemsetAsync(s->macro_count, 0, (size_t)g.nc * 8, g_stream);
     size_t nu = (mode & 2) ? n_snapshot : s->n_upper;
-    // fast path: the store carries a cell partition (cell_start[] of the last sort) and is dense enough for a warp per cell
-    static const bool cell_path = getenv("PICG_CELL_PATH") && atoi(getenv("PICG_CELL_PATH")) != 0;      // A/B switch, see DESIGN.md
-    if (cell_path && s->part_valid && nu >= (size_t)4 * g.nc) {
-        int rc = launch_cell_step(s, mode, dt, H, (mode & 2) ? n_snapshot : (size_t)-1); if (rc) return rc;
+    // fast path of the deposit passes: the store carries a cell partition (cell_start[] of the last sort, possibly stale) and
+    // is dense enough for a lane group per cell.  (A count alone is a pure stream: the thread-run kernel is at 85 % of HBM.)
+    static const bool no_cell_path = getenv("PICG_NO_CELL_PATH") && atoi(getenv("PICG_NO_CELL_PATH")) != 0;      // A/B switch, see DESIGN.md
+    if (!no_cell_path && (mode == 4 || mode == 12) && s->part_valid && nu >= (size_t)12 * g.nc) {
+        int rc = launch_cell_step(s, mode, (size_t)-1, nu); if (rc) return rc;
         if (nu <= s->part_n) return PICG_OK;              // nothing was appended since the sort
         A.tail_from = s->cell_start + g.nc;               // the appended tail goes through the generic kernel
         nu = nu - s->part_n;

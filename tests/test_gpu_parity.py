@@ -138,6 +138,28 @@ def test_deposit_bit_exact(picgpu, orc, n, sort):
     sp.close(); w.close()
 
 
+@pytest.mark.parametrize("n,lo,hi", [(50000, (0.3, 0.0, 0.45), (0.6, 1.0, 0.55)), (300000, (0.0, 0.5, 0.12), (1.0, 0.62, 0.88)), (40000, (0.0, 0.0, 0.12), (1.0, 1.0, 0.88)), (20000, (0.0, 0.0, 0.12), (1.0, 1.0, 0.88))])
+def test_deposit_cell_partition_ragged(picgpu, orc, n, lo, hi):
+    """Cell-partition deposit on ragged cell populations: empty passes, cells holding many chunks, count-only pass, and the
+    same bits as the thread-run kernel (unsorted store) and the oracle."""
+    w, g, x0, xm = _setup(picgpu, orc)
+    parts = util.random_particles(n, x0, xm, seed=91 + n, mpw=(1.0, 1e6), lo_frac=lo, hi_frac=hi)
+    a = picgpu.Species("O", 16 * util.AMU, 0.0, w, 1.0)
+    b = picgpu.Species("O", 16 * util.AMU, 0.0, w, 1.0)
+    a.setParticles(parts); a.sort(); a.setDensityScale(24)
+    b.setParticles(parts); b.setDensityScale(24)            # unsorted: generic kernel
+    a.computeNumberDensity(); b.computeNumberDensity()
+    fixed = g.deposit_fixed(parts, 24)
+    assert np.array_equal(a.den_fixed, fixed) and np.array_equal(b.den_fixed, fixed)
+    cnt = g.count_per_cell(parts)
+    a.computeMacroParticlesCount()                           # by-product of the deposit pass
+    assert np.array_equal(a.macro_part_count, cnt)
+    a.advanceNonElectron(a, a, 0.0)                          # a (null) push invalidates the cached count: count-only pass (all particles lie in the gap)
+    a.computeMacroParticlesCount()
+    assert np.array_equal(a.macro_part_count, cnt)
+    a.close(); b.close(); w.close()
+
+
 def test_deposit_pinned_scale_and_empty(picgpu, orc):
     w, g, x0, xm = _setup(picgpu, orc)
     sp = picgpu.Species("e-", util.ME, -util.QE, w, 100.0)
@@ -213,7 +235,10 @@ def test_cell_partition_path_with_stragglers_holes_and_appended_tail(picgpu, orc
     sp.setParticles(parts); sp.sort(); sp.setDensityScale(28)
     cur = sp.getParticles()
     for it in range(4):                                   # several pushes on one (increasingly stale) partition
-        sp.advanceElectronsDeposit(6e-11, count_cells=True)
+        if it % 2 == 0:                                   # push, then deposit + count over the cell partition (lane group per cell)
+            sp.advanceElectrons(6e-11); sp.computeNumberDensity(); sp.computeMacroParticlesCount()
+        else:                                             # fused push + deposit (thread runs)
+            sp.advanceElectronsDeposit(6e-11, count_cells=True)
         want, alive = g.push_electrons(ef, -util.QE, util.ME, 6e-11, cur)
         cur = want[alive]
         assert sp.getNumParticles() == len(cur)
