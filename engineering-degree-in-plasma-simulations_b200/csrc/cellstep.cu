@@ -33,11 +33,14 @@ using namespace picg;
 #define CG_WARPS (CG_THREADS / 32)
 #define CG_CAP 192                                  // particles per stage and array (1.5 KB)
 #define CG_CHUNK (CG_CAP - 2)                       // the copied range is widened to even particle indices (16-byte alignment)
+#define CG_MVB 64                                   // movers staged per warp before they go to the global list (one atomic per batch)
 
 struct CellArgs {
     const double* a[4];                             // x y z mpw
     const SpeciesCounters* ctr; u64 n_limit;        // particles [0, n_limit) are covered by the partition (~0: the live count)
     const unsigned* cell_start; u64* den_fixed; double scale; double* macro_count;
+    // optional by-product: (slot, current cell, home cell) of every particle found outside its slot's home cell (sort.cu: movers)
+    unsigned *mv_slot, *mv_cell, *mv_home; u64* mv_count; u64 mv_cap;
 };
 
 // ---------------------------------------------------------------- PTX: mbarrier + bulk async copy (TMA, 1-D)
@@ -73,6 +76,18 @@ __global__ void __launch_bounds__(CG_THREADS, 2) k_cell_deposit(Grid g, CellArgs
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double* wbuf = reinterpret_cast<double*>(cg_smem) + (size_t)wib * 2 * NA * CG_CAP;
     u64* bars = reinterpret_cast<u64*>(reinterpret_cast<double*>(cg_smem) + (size_t)CG_WARPS * 2 * NA * CG_CAP) + wib * 2;
+    unsigned* mvbuf = reinterpret_cast<unsigned*>(reinterpret_cast<u64*>(reinterpret_cast<double*>(cg_smem) + (size_t)CG_WARPS * 2 * NA * CG_CAP) + CG_WARPS * 2) + wib * 3 * CG_MVB;
+    int mv_fill = 0;                                           // warp-uniform
+    auto mv_flush = [&]() {                                    // staged (slot, cell, home) triples -> global list, one atomic per batch
+        __syncwarp();
+        u64 base = 0;
+        if (lane == 0) base = atomicAdd(A.mv_count, (u64)mv_fill);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int e = lane; e < mv_fill; e += 32)
+            if (base + e < A.mv_cap) { A.mv_slot[base + e] = mvbuf[e]; A.mv_cell[base + e] = mvbuf[CG_MVB + e]; A.mv_home[base + e] = mvbuf[2 * CG_MVB + e]; }
+        __syncwarp();
+        mv_fill = 0;
+    };
     if (lane == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -156,6 +171,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) k_cell_deposit(Grid g, CellArgs
             // 0 <= d < 1  <=>  high word of d, as unsigned, below that of 1.0 (negative values and NaN have larger high words).
             const double di = __dsub_rn(lx, dci), dj = __dsub_rn(ly, dcj), dk = __dsub_rn(lz, dck);
             bool home = ok && (unsigned)__double2hiint(di) < 0x3ff00000u && (unsigned)__double2hiint(dj) < 0x3ff00000u && (unsigned)__double2hiint(dk) < 0x3ff00000u;
+            const bool moved = ok && !home;
             if (DEPOSIT) {
                 const double m = sm[off];
                 home = home && (unsigned)__double2hiint(m) < (unsigned)(0x43200000 - (scale_hi - 0x3ff00000));   // 0 <= m * 2^S < 2^51
@@ -171,14 +187,24 @@ __global__ void __launch_bounds__(CG_THREADS, 2) k_cell_deposit(Grid g, CellArgs
             cnt += home ? 1 : 0;
             const bool stray = ok && !home;
             if (__any_sync(0xffffffffu, stray)) {
+                int i = 0, j = 0, k = 0;
                 if (stray) {                                                              // generic path, reference index rules
-                    int i, j, k; i64 q[8];
+                    i64 q[8];
                     if (DEPOSIT) {
                         scatter_weights_fixed(g, lx, ly, lz, sm[off], A.scale, i, j, k, q);
 #pragma unroll
                         for (int c = 0; c < 8; c++) if (q[c]) atomicAdd(&A.den_fixed[corner_node(g, i, j, k, c)], (u64)q[c]);
                     } else { i = min((int)lx, g.ci - 1); j = min((int)ly, g.cj - 1); k = min((int)lz, g.ck - 1); }
                     if (COUNT) atomicAdd(&A.macro_count[cell_of(g, i, j, k)], 1.0);
+                }
+                if (A.mv_count) {                                                         // warp-aggregated append to the staged mover list
+                    const unsigned mask = __ballot_sync(0xffffffffu, moved);
+                    if (mask) {
+                        if (mv_fill + __popc(mask) > CG_MVB) mv_flush();
+                        const int e = mv_fill + __popc(mask & ((1u << lane) - 1));
+                        if (moved) { mvbuf[e] = p; mvbuf[CG_MVB + e] = (unsigned)cell_of(g, max(i, 0), max(j, 0), max(k, 0)); mvbuf[2 * CG_MVB + e] = (unsigned)cell; }
+                        mv_fill += __popc(mask);
+                    }
                 }
             }
         }
@@ -234,10 +260,12 @@ __global__ void __launch_bounds__(CG_THREADS, 2) k_cell_deposit(Grid g, CellArgs
         __syncwarp();                                          // every lane is done with this stage before it is refilled
         cur = nxt; stage ^= 1;
     }
+    if (A.mv_count && mv_fill) mv_flush();
 }
 
 namespace picg {
-static size_t cell_smem_bytes(int na) { return (size_t)CG_WARPS * 2 * na * CG_CAP * 8 + CG_WARPS * 2 * 8; }
+int ensure_mover_triples(picg_species_s* s);                  // sort.cu
+static size_t cell_smem_bytes(int na) { return (size_t)CG_WARPS * 2 * na * CG_CAP * 8 + CG_WARPS * 2 * 8 + (size_t)CG_WARPS * 3 * CG_MVB * 4; }
 
 template <bool DEPOSIT, bool COUNT, int LG>
 static int launch_cell_variant(const Grid& g, const CellArgs& A, int kid) {
@@ -268,14 +296,26 @@ int launch_cell_step(picg_species_s* s, int mode, size_t n_limit, size_t n_est) 
     A.a[0] = s->a[0]; A.a[1] = s->a[1]; A.a[2] = s->a[2]; A.a[3] = s->a[6];
     A.ctr = s->ctr; A.n_limit = n_limit; A.cell_start = s->cell_start;
     A.den_fixed = (u64*)s->den_fixed; A.scale = std::ldexp(1.0, s->S); A.macro_count = s->macro_count;
+    A.mv_slot = A.mv_cell = A.mv_home = nullptr; A.mv_count = nullptr; A.mv_cap = 0;
+    const bool emit = s->wants_lists && n_limit == (size_t)-1;                    // per-cell lists are in use: list the movers on the fly
+    if (emit) {
+        int rc = ensure_mover_triples(s); if (rc) return rc;
+        A.mv_slot = s->mv_trip; A.mv_cell = s->mv_trip + s->mv_trip_cap; A.mv_home = s->mv_trip + 2 * s->mv_trip_cap;
+        A.mv_count = &s->ctr->n_movers; A.mv_cap = s->mv_trip_cap;
+        CUDA_TRY(cudaMemsetAsync(&s->ctr->n_movers, 0, 8, g_stream));
+    }
+    s->movers_fresh = false;
     static const int force_lg = getenv("PICG_CELL_LG") ? atoi(getenv("PICG_CELL_LG")) : 0;             // tuning switch
     const double ppc = (double)n_est / std::max(1, g.nc);
     int lg = force_lg ? force_lg : (ppc <= 26 ? 2 : ppc <= 52 ? 3 : ppc <= 104 ? 4 : 5);
+    int rc;
     switch (lg) {
-        case 2:  return launch_cell_mode<2>(g, A, mode);
-        case 3:  return launch_cell_mode<3>(g, A, mode);
-        case 4:  return launch_cell_mode<4>(g, A, mode);
-        default: return launch_cell_mode<5>(g, A, mode);
+        case 2:  rc = launch_cell_mode<2>(g, A, mode); break;
+        case 3:  rc = launch_cell_mode<3>(g, A, mode); break;
+        case 4:  rc = launch_cell_mode<4>(g, A, mode); break;
+        default: rc = launch_cell_mode<5>(g, A, mode); break;
     }
+    if (rc == PICG_OK && emit) s->movers_fresh = true;       // stays true until the particles move, die or are appended to
+    return rc;
 }
 }  // namespace picg

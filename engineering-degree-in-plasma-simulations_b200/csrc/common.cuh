@@ -41,7 +41,7 @@ struct SpeciesCounters {    // lives in device memory, one per species
     u64 overflow;           // appends dropped because capacity was exhausted
     i64 den_max;            // max fixed-point node sum of the last finalize
     u64 den_neg;            // number of negative (overflowed) nodes seen by finalize
-    u64 pad;                // device-side mover count (sort.cu)
+    u64 n_movers;           // device-side mover count (sort.cu, cellstep.cu)
     u64 n_impact;           // heavy push: particles that ended their first sub-move inside an object (handled by k_heavy_impacts)
     u64 pad2;
 };
@@ -84,6 +84,10 @@ struct picg_species_s {
     size_t home_cap = 0, lists_cap = 0, mv_cap = 0, mv_stride = 0;
     bool count_valid = false;          // macro_count holds the per-cell counts of the current particle positions (a deposit produces them for free)
     bool lists_valid = false;          // cell_start + in/out mover lists describe the current cell membership exactly
+    // (slot, current cell, home cell) of the particles that left their slot's home cell: three arrays of mv_trip_cap entries
+    unsigned* mv_trip = nullptr; size_t mv_trip_cap = 0;
+    bool wants_lists = false;          // per-cell lists have been asked for (MC collisions): deposit passes emit the movers on the fly
+    bool movers_fresh = false;         // mv_trip[0, ctr->n_movers) lists the movers of the partition for the current particle positions
     bool part_valid = false;           // cell_start is a partition of [0, part_n) (possibly stale: particles may have drifted)
     size_t part_n = 0;                 // upper bound of the particle count at the last sort
 };

@@ -76,7 +76,7 @@ int compact_dead(picg_species_s* s, size_t cap) {
     LAUNCH(K_COMPACT, k_compact_move, grid, 256, 0, s->ctr, a, s->a[6], hole, surv); CHECK_LAUNCH();
     LAUNCH(K_COMPACT, k_compact_finish, 1, 1, 0, s->ctr); CHECK_LAUNCH();
     s->n_host_valid = false;       // count changed on the device; n_upper stays an upper bound
-    s->sorted_valid = false; s->lists_valid = false; s->count_valid = false;
+    s->sorted_valid = false; s->lists_valid = false; s->movers_fresh = false; s->count_valid = false;
     return PICG_OK;
 }
 size_t compact_scratch_bytes(size_t cap) { return ((cap * 13 + 64) + 255) & ~(size_t)255; }    // 256-byte multiple: what follows stays aligned
@@ -91,7 +91,7 @@ int picg_species_push_reflect(picg_species_t s, double dt) {
     PushArrays a = {s->a[0], s->a[1], s->a[2], s->a[3], s->a[4], s->a[5]};
     LAUNCH(K_PUSH_REFLECT, k_push_reflect, push_grid(s->n_upper), 256, 0, s->w->g, a, s->ctr, s->w->ef, qm_dt, dt);
     CHECK_LAUNCH();
-    s->sorted_valid = false; s->lists_valid = false; s->count_valid = false;
+    s->sorted_valid = false; s->lists_valid = false; s->movers_fresh = false; s->count_valid = false;
     return PICG_OK;
 }
 

@@ -156,14 +156,15 @@ __global__ void __launch_bounds__(256) k_cell_start(const u64* __restrict__ n_pt
 //   list(c) = home range of c  minus  movers whose home is c  plus  movers whose current cell is c.
 __global__ void __launch_bounds__(256) k_find_movers(Grid g, const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pz,
                                                      const unsigned* __restrict__ home, const u64* __restrict__ n_ptr, const unsigned* __restrict__ part_n_ptr,
-                                                     u64* __restrict__ count, u64 cap, unsigned* __restrict__ m_slot, unsigned* __restrict__ m_cell,
-                                                     unsigned* __restrict__ m_home) {
+                                                     int tail_only, u64* __restrict__ count, u64 cap, unsigned* __restrict__ m_slot,
+                                                     unsigned* __restrict__ m_cell, unsigned* __restrict__ m_home) {
     const u64 n = *n_ptr, part_n = *part_n_ptr;
+    const u64 first = tail_only ? min(part_n, n) : 0;                        // tail_only: the partition's movers are already listed (deposit pass)
     const int lane = threadIdx.x & 31;
-    for (u64 p0 = (blockIdx.x * (u64)blockDim.x + threadIdx.x) - lane; p0 < n; p0 += (u64)gridDim.x * blockDim.x) {
+    for (u64 p0 = (first & ~(u64)31) + (blockIdx.x * (u64)blockDim.x + threadIdx.x) - lane; p0 < n; p0 += (u64)gridDim.x * blockDim.x) {
         u64 p = p0 + lane;
         bool mover = false; unsigned cell = 0, hm = (unsigned)g.nc;          // home == nc: no home (appended after the sort)
-        if (p < n) {
+        if (p >= first && p < n) {
             int i = min(max((int)x_to_l(px[p], g.x0[0], g.inv_dx[0]), 0), g.ci - 1);
             int j = min(max((int)x_to_l(py[p], g.x0[1], g.inv_dx[1]), 0), g.cj - 1);
             int k = min(max((int)x_to_l(pz[p], g.x0[2], g.inv_dx[2]), 0), g.ck - 1);
@@ -215,6 +216,7 @@ __global__ void __launch_bounds__(256) k_cell_start_search(const u64* __restrict
 
 namespace picg {
 double g_mover_fraction = 0.10;     // above this fraction of movers the store is re-sorted instead of patched
+static uint64_t g_movers_from_deposit = 0, g_mover_scans = 0, g_mover_resorts = 0;
 // Stable LSD radix sort of (keys, vals) pairs; n is read on the device.  Returns the buffers that hold the result.
 static int radix_sort_pairs(const u64* n_ptr, size_t n_upper, int key_bits, unsigned*& keysA, unsigned*& valsA, unsigned*& keysB, unsigned*& valsB,
                             unsigned* counts, int nblocks) {
@@ -242,6 +244,8 @@ static int ensure_u32(unsigned*& p, size_t& cap, size_t want) {
 // Sorts species s by cell.  Scratch: keysA | keysB | idxA | idxB | counts.
 int sort_species(picg_species_s* s) {
     const Grid& g = s->w->g;
+    int rc0 = species_refresh_count(s); if (rc0) return rc0;               // a sort is rare: the exact count makes part_n exact
+    s->n_upper = s->n_host;
     size_t cap = std::max<size_t>(s->n_upper, 1);
     if (cap >= 0xffffffffull) return set_error(PICG_ERR_ARG, "picg_species_sort: more than 2^32-1 particles per GPU are not supported");
     int nblocks = std::max(1, std::min(div_up(cap, SORT_TILE), g_sm_count * 4));
@@ -267,13 +271,24 @@ int sort_species(picg_species_s* s) {
     LAUNCH(K_CELL_START, k_copy_u32, pgrid, 256, 0, n_ptr, keysA, s->home); CHECK_LAUNCH();                 // home cell of every slot
     CUDA_TRY(cudaMemsetAsync(s->in_start, 0, ((size_t)g.nc + 1) * 4, g_stream));                           // no movers right after a sort
     CUDA_TRY(cudaMemsetAsync(s->out_start, 0, ((size_t)g.nc + 1) * 4, g_stream));
-    s->sorted_valid = true; s->part_valid = true; s->part_n = cap; s->lists_valid = true;
+    s->sorted_valid = true; s->part_valid = true; s->part_n = cap; s->lists_valid = true; s->movers_fresh = false;
     return PICG_OK;
 }
 
 // Makes the per-cell lists of s exact for its current particle positions: nothing to do if the store is exactly sorted,
 // a mover pass over a stale partition when few particles changed cell, a full sort otherwise.
+// The species-owned (slot, cell, home) arrays sized by the store capacity (no regrowth while the population grows).
+int ensure_mover_triples(picg_species_s* s) {
+    size_t mcapa = ((size_t)(g_mover_fraction * (double)s->cap) + 1024 + 63) & ~(size_t)63;
+    if (s->mv_trip_cap >= mcapa) return PICG_OK;
+    size_t c3 = s->mv_trip_cap * 3;
+    int rc = ensure_u32(s->mv_trip, c3, mcapa * 3); if (rc) return rc;
+    s->mv_trip_cap = mcapa; s->movers_fresh = false;
+    return PICG_OK;
+}
+
 int species_exact_lists(picg_species_s* s) {
+    s->wants_lists = true;                                   // from now on deposit passes over the partition list the movers on the fly
     if (s->sorted_valid || s->lists_valid) return PICG_OK;
     int rc = species_refresh_count(s); if (rc) return rc;
     size_t n = s->n_host;
@@ -282,25 +297,30 @@ int species_exact_lists(picg_species_s* s) {
     const Grid& g = s->w->g;
     size_t mcap = (size_t)(max_frac * (double)n) + 1024;
     size_t mcap_alloc = (size_t)(max_frac * (double)s->cap) + 1024;      // sized by the store capacity: no regrowth while the population grows
-    // mover arrays: slot/cell/home triples plus radix ping-pong buffers, all in the scratch arena
+    // mover triples (slot / current cell / home cell) live in the species (a deposit pass may have listed them already);
+    // radix ping-pong buffers in the scratch arena
     size_t mcapa = (mcap_alloc + 63) & ~(size_t)63;
     int nblocks = std::max(1, std::min(div_up(mcap, SORT_TILE), g_sm_count * 4));
-    size_t bytes = mcapa * 4 * 7 + (size_t)256 * nblocks * 4 + 256;
+    size_t bytes = mcapa * 4 * 4 + (size_t)256 * nblocks * 4 + 256;
     rc = ensure_scratch(s->w, bytes); if (rc) return rc;
     rc = ensure_u32(s->mv_in, s->mv_cap, mcapa * 2); if (rc) return rc;     // [0,mcapa): slots ordered by current cell, [mcapa, 2 mcapa): slots ordered by home cell
     s->mv_stride = mcapa;
-    unsigned* m_slot = (unsigned*)s->w->scratch; unsigned* m_cell = m_slot + mcapa; unsigned* m_home = m_cell + mcapa;
-    unsigned* kB = m_home + mcapa; unsigned* vA = kB + mcapa; unsigned* vB = vA + mcapa; unsigned* tmp = vB + mcapa;
+    rc = ensure_mover_triples(s); if (rc) return rc;
+    unsigned* m_slot = s->mv_trip; unsigned* m_cell = m_slot + s->mv_trip_cap; unsigned* m_home = m_cell + s->mv_trip_cap;
+    unsigned* kB = (unsigned*)s->w->scratch; unsigned* vA = kB + mcapa; unsigned* vB = vA + mcapa; unsigned* tmp = vB + mcapa;
     unsigned* counts = tmp + mcapa;
-    u64* cnt = (u64*)&s->ctr->pad;                                           // device-side mover count
-    CUDA_TRY(cudaMemsetAsync(cnt, 0, 8, g_stream));
-    int pgrid = std::max(1, std::min(div_up(std::max<size_t>(n, 1), 256), g_sm_count * 8));
-    LAUNCH(K_SORT_KEYS, k_find_movers, pgrid, 256, 0, g, s->a[0], s->a[1], s->a[2], s->home, &s->ctr->n, s->cell_start + g.nc, cnt, (u64)mcap, m_slot, m_cell, m_home);
+    u64* cnt = &s->ctr->n_movers;                                            // device-side mover count
+    const int tail_only = s->movers_fresh ? 1 : 0;                           // the last deposit pass listed the partition's movers: only the appended tail is left
+    if (!tail_only) CUDA_TRY(cudaMemsetAsync(cnt, 0, 8, g_stream));
+    if (tail_only) g_movers_from_deposit++; else g_mover_scans++;
+    size_t n_scan = tail_only ? (n > s->part_n ? n - s->part_n : 0) + 32 : n;
+    int pgrid = std::max(1, std::min(div_up(std::max<size_t>(n_scan, 1), 256), g_sm_count * 8));
+    LAUNCH(K_SORT_KEYS, k_find_movers, pgrid, 256, 0, g, s->a[0], s->a[1], s->a[2], s->home, &s->ctr->n, s->cell_start + g.nc, tail_only, cnt, (u64)mcap, m_slot, m_cell, m_home);
     CHECK_LAUNCH();
     u64 n_live_movers = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_live_movers, cnt, 8, cudaMemcpyDeviceToHost, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));
-    if (n_live_movers > mcap) return sort_species(s);                        // too stale: periodic full radix sort
+    if (n_live_movers > mcap) { g_mover_resorts++; return sort_species(s); }  // too stale: periodic full radix sort
     int mgrid = std::max(1, std::min(div_up(std::max<size_t>((size_t)n_live_movers, 1), 256), g_sm_count * 4));
     int bits = key_bits_of(g);
     // (1) in-lists: live movers ordered by their current cell
@@ -317,7 +337,7 @@ int species_exact_lists(picg_species_s* s) {
     {
         // movers without a home (appended) carry home = nc; they sort to the end and fall outside every cell's range
         size_t vac_upper = s->part_n > n ? s->part_n - n : 0;
-        if (n_live_movers + vac_upper > mcap) return sort_species(s);
+        if (n_live_movers + vac_upper > mcap) { g_mover_resorts++; return sort_species(s); }
         if (vac_upper) { LAUNCH(K_SORT_KEYS, k_find_vacated, std::max(1, std::min(div_up(vac_upper, 256), g_sm_count * 4)), 256, 0, s->home, &s->ctr->n, s->cell_start + g.nc, cnt, (u64)mcap, m_slot, m_home); CHECK_LAUNCH(); }
         unsigned *ka = m_home, *kb = kB, *va = vA, *vb = vB;
         int mgrid2 = std::max(1, std::min(div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), 256), g_sm_count * 4));
@@ -334,6 +354,12 @@ int species_exact_lists(picg_species_s* s) {
 
 extern "C" {
 int picg_set_mover_fraction(double f) { REQUIRE_ARG(f >= 0 && f <= 0.5, "picg_set_mover_fraction: 0 <= f <= 0.5"); g_mover_fraction = f; return PICG_OK; }
+int picg_mover_stats(uint64_t* from_deposit, uint64_t* full_scans, uint64_t* resorts) {
+    if (from_deposit) *from_deposit = g_movers_from_deposit;
+    if (full_scans) *full_scans = g_mover_scans;
+    if (resorts) *resorts = g_mover_resorts;
+    return PICG_OK;
+}
 int picg_species_sort(picg_species_t s) {
     REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_species_sort: null species");
     return sort_species(s);

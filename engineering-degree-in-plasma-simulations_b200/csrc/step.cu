@@ -300,7 +300,7 @@ int species_step(picg_species_s* s, bool push, bool heavy, bool deposit, bool fi
     int mode = (push ? 1 : 0) | (heavy ? 2 : 0) | (deposit ? 4 : 0) | (count ? 8 : 0);
     rc = launch_step(s, mode, dt, neutrals, spherium, sputtering, n_snapshot); if (rc) return rc;
     if (heavy && s->charge != 0) {
-        for (picg_species_s* t : {neutrals, spherium}) { t->n_host_valid = false; t->sorted_valid = false; t->lists_valid = false; t->count_valid = false; t->n_upper = t->cap; }
+        for (picg_species_s* t : {neutrals, spherium}) { t->n_host_valid = false; t->sorted_valid = false; t->lists_valid = false; t->movers_fresh = false; t->count_valid = false; t->n_upper = t->cap; }
     }
     if (push) { rc = compact_dead(s, cap); if (rc) return rc; }
     if (count) s->count_valid = true;                // counted at the post-push positions; the compaction only permutes survivors

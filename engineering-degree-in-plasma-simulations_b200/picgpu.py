@@ -76,6 +76,13 @@ def set_mover_fraction(f):
     _chk(lib().picg_set_mover_fraction(C.c_double(f)))
 
 
+def mover_stats():
+    """(lists re-used from a deposit pass, full mover scans, fall-backs to a full sort) since start."""
+    a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    _chk(lib().picg_mover_stats(C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
 def synchronize():
     _chk(lib().picg_synchronize())
 

@@ -148,6 +148,9 @@ PICG_API int picg_species_count_per_cell(picg_species_t s);
  * changed cell ("movers"); when more than `f` of a species moved, it is re-sorted (periodic radix sort).  f = 0 forces a
  * full sort whenever the order is stale (the reference re-sorts every step). */
 PICG_API int picg_set_mover_fraction(double f);
+/* How the mover lists were obtained since start: passes that re-used the list a deposit pass produced on the fly (only the
+ * appended tail is scanned), full scans of the store, and fall-backs to a full radix sort. */
+PICG_API int picg_mover_stats(uint64_t* from_deposit, uint64_t* full_scans, uint64_t* resorts);
 PICG_API int picg_species_sort(picg_species_t s);
 /* diagnostics: getMicroCount, getMomentum, getKE  Species.cpp:726-755 */
 PICG_API int picg_species_diagnostics(picg_species_t s, double* micro_count, double momentum[3], double* ke);

@@ -127,6 +127,44 @@ def test_mover_lists_are_exact_and_equivalent_to_resorting(picgpu, orc=None):
         _agree([a[key] for a in A], [b[key] for b in B], key)
 
 
+def test_mover_lists_from_the_deposit_pass(picgpu):
+    """Once per-cell lists are in use, the cell-partition deposit lists the movers as a by-product and the next list build
+    only scans the appended tail.  The lists must stay exact through pushes, deaths, appends and MC products."""
+    pg = picgpu
+    ni, nj, nk = 9, 9, 13
+    x0, xm, rects = util.discharge_geometry(ni, nj, nk)
+    E, sg = util.momentum_transfer_table()
+    E_ion = 1313.9 * 1000 / util.NA
+    neu0 = util.random_particles(40000, x0, xm, seed=81, vth=600.0, mpw=(5e11, 5e11), lo_frac=(0, 0, 0.15), hi_frac=(1, 1, 0.85))
+    ele0 = util.random_particles(20000, x0, xm, seed=82, vth=2.5e6, mpw=(100.0, 100.0), lo_frac=(0, 0, 0.15), hi_frac=(1, 1, 0.85))
+    pg.set_mover_fraction(0.4); pg.seed(5)
+    w = util.build_world(pg.World, ni, nj, nk, x0, xm, rects, dt=1e-10)
+    w.upload(pg.F_EF, util.smooth_ef((ni, nj, nk), x0, xm, seed=3, amp=2e6))
+    sn = pg.Species("O", 16 * util.AMU, 0.0, w, 5e11, E_ion); si = pg.Species("O+", 16 * util.AMU, util.QE, w, 100.0); se = pg.Species("e-", util.ME, -util.QE, w, 100.0)
+    sn.setParticles(neu0); se.setParticles(ele0)
+    sn.sort(); se.sort()
+    m = pg.MC_MEX_Ionization(sn, si, se, w, E, sg)
+    m.setWsvMax(5e11 * 8e-20 * 8e6)
+    m.apply(1e-10)                                        # first use of the lists: from now on the deposit lists the movers
+    f0, s0, r0 = pg.mover_stats()
+    for it in range(4):
+        se.advanceElectrons(2e-12); se.computeNumberDensity()
+        sn.advanceNonElectron(sn, sn, 6e-9); sn.computeNumberDensity()
+        if it == 2:
+            se.addParticles(util.random_particles(700, x0, xm, seed=90 + it, vth=2.5e6, mpw=(100.0, 100.0), lo_frac=(0, 0, 0.2), hi_frac=(1, 1, 0.8)))   # invalidates the by-product
+        se.computeMacroParticlesCount(); sn.computeMacroParticlesCount()
+        assert np.array_equal(m.listCounts(1, w), se.macro_part_count)
+        assert np.array_equal(m.listCounts(0, w), sn.macro_part_count)
+        st = m.apply(1e-10)                               # appends ions / electrons (and split neutrals) beyond the partitions
+        assert st.collisions > 0
+    f1, s1, r1 = pg.mover_stats()
+    # the deposit's list was re-used (MC products pile up beyond the partition, so a periodic full sort may also occur: r1 >= r0)
+    assert f1 - f0 >= 3 and r1 >= r0
+    pg.set_mover_fraction(0.10)
+    for o in (m, sn, si, se, w):
+        o.close()
+
+
 def test_cross_sections_match_reference(picgpu, ref):
     x0, xm, rects = util.discharge_geometry(7, 7, 9)
     E, s = util.momentum_transfer_table()
