@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--moments", action="store_true", help="also run Species::sampleMoments every step (SURVEY 8f row 1)")
     ap.add_argument("--cpu_sample_nodes", type=int, default=49, help="nodes per axis of the CPU-baseline sub-volume (same dx, same particles per cell)")
     ap.add_argument("--skip_cpu_baseline", action="store_true")
+    ap.add_argument("--poisson", choices=["auto", "replicated", "slab"], default="auto",
+                    help="multi-GPU solve: every rank solves the whole grid, or planes split over the ranks with peer-memory halos (auto: slab when N > 1)")
     ap.add_argument("--init_max_it", type=int, default=20000, help="iteration cap of the initial vacuum solve (profiling runs use a small value)")
     ap.add_argument("--inject", type=int, default=1 << 20, help="e2e: electrons injected from pinned host memory per step")
     return ap.parse_args()
@@ -168,6 +170,21 @@ def run_ours(args):
     sol.setReferenceValues(0.0, 0.0, 1e20)                 # main.cpp:138
     cold = pg.PotentialSolver(w, args.init_max_it, args.s_tol)   # initial vacuum solve (main.cpp:172-173)
     cold.setReferenceValues(0.0, 0.0, 1e20)
+    poisson_mode = "replicated"
+    if world > 1 and args.poisson in ("auto", "slab"):
+        def all_gather_bytes(b):
+            t = torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+            out = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(out, t)
+            return [o.cpu().numpy().tobytes() for o in out]
+        try:
+            cold.enableSlabs(rank, world, all_gather_bytes)
+            sol.enableSlabs(rank, world, all_gather_bytes)
+            poisson_mode = "slab (planes of i split over %d ranks; halos, residual sum and all-gather through NVLink peer memory)" % world
+        except pg.PicgError as e:                              # no peer access on this node: every rank solves the whole grid
+            if args.poisson == "slab":
+                raise
+            poisson_mode = "replicated (slab mode unavailable: %s)" % e
     t0 = time.time()
     cold.solveGS(); cold.computeEF()
     init_iters = cold.iterations
@@ -371,9 +388,9 @@ def run_ours(args):
                "config": {"workload": "synthetic %d^3 mesh, %.3g macro-particles (O/O+/e- = 2:1:1), full PIC-DSMC step, Poisson live" % (m, args.particles),
                           "mesh": [m, m, m], "particles_global": int(n_avg), "species": {k: int(v) for k, v in per_rank_counts.items()},
                           "steps_per_sort": 1 if mcc else args.sort_every, "mcc": mcc is not None, "moments": bool(args.moments),
-                          "poisson": {"max_it": args.s_max_it, "tol": args.s_tol, "mode": "replicated", "iterations_per_step": its / args.steps,
+                          "poisson": {"max_it": args.s_max_it, "tol": args.s_tol, "mode": poisson_mode, "iterations_per_step": its / args.steps,
                                       "initial_solve_iterations": init_iters},
-                          "parallelism": "particles split by index over %d GPU(s); int64 density all-reduce; replicated Poisson" % world,
+                          "parallelism": "particles split by index over %d GPU(s); int64 density all-reduce; Poisson %s" % (world, poisson_mode.split(" ")[0]),
                           "l2_policy": "inputs larger than L2 (%.1f GB of particle arrays per GPU vs 126 MB L2)" % (sum(per_rank_counts.values()) * 56 / 1e9)},
                "poisson_ms_per_step": poisson_ms, "gpu_launches": int(launches), "device_reallocs_in_timed_region": int(reallocs_timed), "clocks": clk, "roofline": roofline, "kernels": kernels, "e2e": e2e,
                "setup_s": round(setup_s, 1)}

@@ -40,7 +40,7 @@ struct CellArgs {
     const SpeciesCounters* ctr; u64 n_limit;        // particles [0, n_limit) are covered by the partition (~0: the live count)
     const unsigned* cell_start; u64* den_fixed; double scale; double* macro_count;
     // optional by-product: (slot, current cell, home cell) of every particle found outside its slot's home cell (sort.cu: movers)
-    unsigned *mv_slot, *mv_cell, *mv_home; u64* mv_count; u64 mv_cap;
+    unsigned *mv_slot, *mv_cell, *mv_home; u64* mv_count; u64* mv_listed; u64 mv_cap;
 };
 
 // ---------------------------------------------------------------- PTX: mbarrier + bulk async copy (TMA, 1-D)
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) k_cell_deposit(Grid g, CellArgs
     const u64 policy = policy_evict_first();
     // the partition covers [0, n_lim): live particles that were in the store at the last sort
     const unsigned n_lim = (unsigned)min(min(A.n_limit == ~0ull ? A.ctr->n : A.n_limit, (u64)__ldg(A.cell_start + g.nc)), (u64)0xfffffff0u);
+    if (A.mv_count && blockIdx.x == 0 && threadIdx.x == 0) *A.mv_listed = n_lim;     // slots beyond are left to the tail scan (sort.cu)
     const int npass = (g.nc + P - 1) / P;
     const int nw = gridDim.x * CG_WARPS;
     const int grp = lane >> LG, sub = lane & (G - 1);
@@ -296,12 +297,12 @@ int launch_cell_step(picg_species_s* s, int mode, size_t n_limit, size_t n_est) 
     A.a[0] = s->a[0]; A.a[1] = s->a[1]; A.a[2] = s->a[2]; A.a[3] = s->a[6];
     A.ctr = s->ctr; A.n_limit = n_limit; A.cell_start = s->cell_start;
     A.den_fixed = (u64*)s->den_fixed; A.scale = std::ldexp(1.0, s->S); A.macro_count = s->macro_count;
-    A.mv_slot = A.mv_cell = A.mv_home = nullptr; A.mv_count = nullptr; A.mv_cap = 0;
+    A.mv_slot = A.mv_cell = A.mv_home = nullptr; A.mv_count = nullptr; A.mv_listed = nullptr; A.mv_cap = 0;
     const bool emit = s->wants_lists && n_limit == (size_t)-1;                    // per-cell lists are in use: list the movers on the fly
     if (emit) {
         int rc = ensure_mover_triples(s); if (rc) return rc;
         A.mv_slot = s->mv_trip; A.mv_cell = s->mv_trip + s->mv_trip_cap; A.mv_home = s->mv_trip + 2 * s->mv_trip_cap;
-        A.mv_count = &s->ctr->n_movers; A.mv_cap = s->mv_trip_cap;
+        A.mv_count = &s->ctr->n_movers; A.mv_listed = &s->ctr->n_listed; A.mv_cap = s->mv_trip_cap;
         CUDA_TRY(cudaMemsetAsync(&s->ctr->n_movers, 0, 8, g_stream));
     }
     s->movers_fresh = false;

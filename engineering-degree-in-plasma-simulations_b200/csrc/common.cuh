@@ -43,7 +43,7 @@ struct SpeciesCounters {    // lives in device memory, one per species
     u64 den_neg;            // number of negative (overflowed) nodes seen by finalize
     u64 n_movers;           // device-side mover count (sort.cu, cellstep.cu)
     u64 n_impact;           // heavy push: particles that ended their first sub-move inside an object (handled by k_heavy_impacts)
-    u64 pad2;
+    u64 n_listed;           // movers of slots [0, n_listed) are listed in mv_trip (written by the deposit pass that listed them)
 };
 
 struct picg_world_s {
@@ -99,6 +99,17 @@ struct picg_solver_s {
     int bc_mode = 0;
     double* partial = nullptr;         // residual partial sums
     unsigned char* cls = nullptr;      // node class per node (poisson.cu), rebuilt at the start of every solve
+    // multi-GPU slab decomposition (poisson.cu): planes [i0, i1) of the slowest index belong to this rank; halo planes,
+    // residual sums and the final all-gather go through peer memory (CUDA IPC), signalled by flags in the mailboxes
+    int slab_rank = 0, slab_world = 1, slab_i0 = 0, slab_i1 = 0;
+    u64* mbox = nullptr;               // this rank's mailbox (device memory, exported to the peers)
+    std::vector<double*> peer_phi;     // peer_phi[r]: rank r's phi (own pointer at r == rank)
+    std::vector<u64*> peer_mbox;
+    double** peer_phi_dev = nullptr; u64** peer_mbox_dev = nullptr;   // the same tables in device memory
+    u64 residual_seq = 0, gather_seq = 0;                             // monotone sequence numbers, identical on every rank (the half-sweep counter lives in the mailbox)
+    // CUDA graphs of n back-to-back iterations (2n half-sweep kernels), keyed by n and the parameter block they were captured with
+    struct SorGraph { unsigned n; unsigned char params[160]; void* exec; };
+    std::vector<SorGraph> graphs;
 };
 
 struct picg_mcc_s {
@@ -125,6 +136,7 @@ extern int g_device;          // -1 until picg_init succeeds
 extern int g_sm_count;
 extern uint64_t g_seed;
 extern int g_rank, g_world_size;
+extern bool g_capturing;       // a stream capture is in progress: no event records, launches are counted by the replay
 extern uint64_t g_reallocs;     // device (re)allocations of particle stores / scratch since start (a timed region should see none)
 int  set_error(int code, const char* fmt, ...);
 int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);

@@ -323,7 +323,7 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     rc = species_refresh_count(ele); if (rc) return rc;
     rc = species_refresh_count(ion); if (rc) return rc;
     for (int k = 0; k < 3; k++) m->last_appends[k] = sp3[k]->n_host - n_before[k];
-    if (host_stats[1]) { neu->sorted_valid = false; neu->lists_valid = false; neu->movers_fresh = false; neu->count_valid = false; ele->sorted_valid = false; ele->lists_valid = false; ele->movers_fresh = false; ele->count_valid = false; ion->sorted_valid = false; ion->lists_valid = false; ion->movers_fresh = false; ion->count_valid = false; }   // :751-754
+    if (host_stats[1]) { neu->sorted_valid = false; neu->lists_valid = false; neu->count_valid = false; ele->sorted_valid = false; ele->lists_valid = false; ele->count_valid = false; ion->sorted_valid = false; ion->lists_valid = false; ion->count_valid = false; }   // :751-754
     if (host_stats[5]) {                                        // grow so that the next call has room, and tell the caller
         for (int k = 0; k < 3; k++) { rc = species_ensure_capacity(sp3[k], sp3[k]->n_host + std::max<size_t>(4 * (size_t)host_stats[5], sp3[k]->n_host / 10)); if (rc) return rc; }
         set_error(PICG_OK, "picg_mcc_apply: %llu collisions were skipped because a particle store was full; stores were grown (reserve more up front)", (unsigned long long)host_stats[5]);

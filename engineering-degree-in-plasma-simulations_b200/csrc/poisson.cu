@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 using namespace picg;
 
@@ -62,6 +63,124 @@ __global__ void __launch_bounds__(128) k_sor_row(Grid g, SorParams sp, int color
     }
 }
 
+// ---------------------------------------------------------------- multi-GPU: slab decomposition with peer-memory halos
+// Mailbox layout (u64 words).  Written by the peers with system-scope stores, read with volatile loads.
+#define MB_FLAG_LEFT 0          // last half-sweep whose boundary plane the LEFT neighbour has delivered into this rank's phi
+#define MB_FLAG_RIGHT 1
+#define MB_RES_VAL 8            // + r: residual partial sum of rank r (bits of a double)
+#define MB_RES_TAG 72           // + r: sequence number of that sum
+#define MB_GATHER 136           // + r: sequence number of the last all-gather rank r has delivered
+#define MB_COUNT_LEFT 200       // local: boundary rows of the current half-sweep already delivered to the left / right neighbour
+#define MB_COUNT_RIGHT 201
+#define MB_SEQ 202              // local: number of half-sweeps completed before the current batch (advanced on the device: graph replays need no new arguments)
+#define MB_WORDS 256
+#define SLAB_MAX_RANKS 64
+
+struct SlabArgs { int i0, i1; double* left_phi; double* right_phi; u64* mbox; u64* left_mbox; u64* right_mbox; unsigned seq_off; };
+
+__device__ __forceinline__ void spin_until(const u64* flag, u64 want) {
+    while (*(volatile const u64*)flag < want) __nanosleep(64);
+    __threadfence_system();
+}
+
+// One colour half-sweep over the planes [i0, i1) of this rank.  Same update as k_sor_row.  The two boundary planes are
+// scheduled first; their rows wait for the neighbour's previous half-sweep (flag in the mailbox, long set), then write every
+// new value to the neighbour's copy of the plane as well (its halo) - the exchange is part of the sweep, tile by tile -
+// and the last row to finish raises the neighbour's flag.
+__global__ void __launch_bounds__(128) k_sor_slab(Grid g, SorParams sp, int color, double* __restrict__ phi, const double* __restrict__ rho,
+                                                  const unsigned char* __restrict__ cls, SlabArgs S) {
+    const int j = blockIdx.x, np = S.i1 - S.i0, y = blockIdx.y;
+    const u64 seq = S.mbox[MB_SEQ] + S.seq_off;                                  // number of this half-sweep (the same on every rank)
+    int i; bool to_left = false, to_right = false;
+    if (y == 0) { i = S.i0; to_left = S.left_phi != nullptr; }                   // boundary planes first: their delivery (peer stores +
+    else if (y == 1) { i = S.i1 - 1; to_right = S.right_phi != nullptr; }         // system fence) overlaps the interior planes
+    else i = S.i0 + y - 1;
+    if (to_left || to_right) {
+        if (threadIdx.x == 0) spin_until(S.mbox + (to_left ? MB_FLAG_LEFT : MB_FLAG_RIGHT), seq - 1);
+        __syncthreads();
+    }
+    double* peer = to_left ? S.left_phi : S.right_phi;
+    const size_t si = (size_t)g.nj * g.nk, sj = g.nk;
+    const size_t row = ((size_t)i * g.nj + j) * g.nk;
+    for (int k = 2 * threadIdx.x + ((i + j + color) & 1); k < g.nk; k += 2 * blockDim.x) {
+        const size_t u = row + k;
+        const int c = cls[u];
+        if (c == 0) continue;
+        double nv_;
+        if (c < 7) nv_ = phi[face_neighbor(g, c, u)];
+        else {
+            const double p = phi[u];
+            const double ne = (sp.n0 != 0.0) ? sp.n0 * exp((p - sp.phi0) / sp.Te0) : 0.0;
+            // the halo plane is written by the neighbour GPU: read it from L2 (ld.cg), never from a possibly stale L1 line
+            const double lo_i = to_left ? __ldcg(phi + u - si) : phi[u - si], hi_i = to_right ? __ldcg(phi + u + si) : phi[u + si];
+            const double nw = ((rho[u] - sp.qe * ne) * sp.inv_eps0 + (lo_i + hi_i) * sp.inv_d2x + (phi[u - sj] + phi[u + sj]) * sp.inv_d2y +
+                               (phi[u - 1] + phi[u + 1]) * sp.inv_d2z) * sp.inv_twos;
+            nv_ = p + sp.w * (nw - p);
+        }
+        phi[u] = nv_;
+        if (to_left || to_right) peer[u] = nv_;
+    }
+    if (to_left || to_right) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u64* counter = S.mbox + (to_left ? MB_COUNT_LEFT : MB_COUNT_RIGHT);
+            if (atomicAdd(counter, 1ull) == (u64)g.nj - 1) {                    // every row of the plane is delivered
+                *counter = 0;
+                __threadfence_system();
+                *(volatile u64*)((to_left ? S.left_mbox : S.right_mbox) + (to_left ? MB_FLAG_RIGHT : MB_FLAG_LEFT)) = seq;
+            }
+        }
+    }
+}
+// the halos of both colours are in place once both neighbours have delivered the last half-sweep
+__global__ void k_slab_wait_halos(SlabArgs S) {
+    const u64 seq = S.mbox[MB_SEQ];
+    if (S.left_phi) spin_until(S.mbox + MB_FLAG_LEFT, seq);
+    if (S.right_phi) spin_until(S.mbox + MB_FLAG_RIGHT, seq);
+}
+__global__ void k_slab_advance(u64* mbox, unsigned n) { mbox[MB_SEQ] += n; }
+// sum of this rank's residual partials -> every rank's mailbox; then the sum over ranks, in rank order (the same bits everywhere)
+__global__ void __launch_bounds__(256) k_slab_post_residual(const double* __restrict__ partial, int n, int rank, int world, u64* const* __restrict__ peer_mbox, u64 tag) {
+    __shared__ double sm[256];
+    double a = 0; for (int t = threadIdx.x; t < n; t += 256) a += partial[t];
+    sm[threadIdx.x] = a; __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s]; __syncthreads(); }
+    if (threadIdx.x < world) {
+        u64* mb = peer_mbox[threadIdx.x];
+        *(volatile u64*)(mb + MB_RES_VAL + rank) = (u64)__double_as_longlong(sm[0]);
+        __threadfence_system();
+        *(volatile u64*)(mb + MB_RES_TAG + rank) = tag;
+    }
+}
+__global__ void k_slab_collect_residual(const u64* __restrict__ mbox, int world, u64 tag, double* __restrict__ out) {
+    double s = 0;
+    for (int r = 0; r < world; r++) { spin_until(mbox + MB_RES_TAG + r, tag); s += __longlong_as_double((long long)*(volatile const u64*)(mbox + MB_RES_VAL + r)); }
+    out[0] = s;
+}
+// all-gather of phi: this rank's planes go to every peer, then the peers are told
+__global__ void __launch_bounds__(256) k_slab_push(const double* __restrict__ phi, size_t begin, size_t end, int rank, int world, double* const* __restrict__ peer_phi) {
+    const size_t n2 = (end - begin) / 2;                                        // plane sizes are even or handled by the tail below
+    for (int r = 0; r < world; r++) {
+        if (r == rank) continue;
+        double* dst = peer_phi[r];
+        if (((begin & 1) == 0)) {
+            const double2* s2 = reinterpret_cast<const double2*>(phi + begin); double2* d2 = reinterpret_cast<double2*>(dst + begin);
+            for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n2; t += (size_t)gridDim.x * blockDim.x) d2[t] = s2[t];
+            if (((end - begin) & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[end - 1] = phi[end - 1];
+        } else {
+            for (size_t t = begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < end; t += (size_t)gridDim.x * blockDim.x) dst[t] = phi[t];
+        }
+    }
+    __threadfence_system();
+}
+__global__ void k_slab_gather_signal(int rank, int world, u64* const* __restrict__ peer_mbox, u64 tag) {
+    if (threadIdx.x < world && threadIdx.x != rank) { __threadfence_system(); *(volatile u64*)(peer_mbox[threadIdx.x] + MB_GATHER + rank) = tag; }
+}
+__global__ void k_slab_gather_wait(const u64* __restrict__ mbox, int rank, int world, u64 tag) {
+    for (int r = 0; r < world; r++) if (r != rank) spin_until(mbox + MB_GATHER + r, tag);
+}
+
 __global__ void __launch_bounds__(256) k_sor_color(Grid g, SorParams sp, int color, double* __restrict__ phi, const double* __restrict__ rho,
                                                    const int* __restrict__ object_id) {
     const int hk = (g.nk + 1) >> 1;
@@ -85,11 +204,11 @@ __global__ void __launch_bounds__(256) k_sor_color(Grid g, SorParams sp, int col
 }
 
 __global__ void __launch_bounds__(256) k_residual(Grid g, SorParams sp, const double* __restrict__ phi, const double* __restrict__ rho,
-                                                  const int* __restrict__ object_id, double* __restrict__ partial) {
+                                                  const int* __restrict__ object_id, double* __restrict__ partial, size_t u_begin, size_t u_end) {
     __shared__ double sm[256];
     const size_t si = (size_t)g.nj * g.nk, sj = g.nk;
     double acc = 0.0;
-    for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < (size_t)g.nv; u += (size_t)gridDim.x * blockDim.x) {
+    for (size_t u = u_begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < u_end; u += (size_t)gridDim.x * blockDim.x) {
         int k = (int)(u % g.nk); size_t row = u / g.nk; int j = (int)(row % g.nj), i = (int)(row / g.nj);
         int cls = node_class(g, sp.bc_mode, object_id[u], i, j, k);
         if (cls == 0) continue;
@@ -145,21 +264,101 @@ static int prepare_classes(picg_solver_s* s) {
     LAUNCH(K_MISC, k_node_classes, std::min(div_up(g.nv, 256), g_sm_count * 8), 256, 0, g, s->bc_mode, s->w->object_id, s->cls); CHECK_LAUNCH();
     return PICG_OK;
 }
-static int launch_iteration(picg_solver_s* s, const SorParams& p) {
+static SlabArgs slab_args(picg_solver_s* s, unsigned seq_off) {
+    SlabArgs S; S.i0 = s->slab_i0; S.i1 = s->slab_i1; S.mbox = s->mbox; S.seq_off = seq_off;
+    const int r = s->slab_rank, G = s->slab_world;
+    S.left_phi = r > 0 ? s->peer_phi[r - 1] : nullptr; S.left_mbox = r > 0 ? s->peer_mbox[r - 1] : nullptr;
+    S.right_phi = r + 1 < G ? s->peer_phi[r + 1] : nullptr; S.right_mbox = r + 1 < G ? s->peer_mbox[r + 1] : nullptr;
+    return S;
+}
+// n iterations = 2n colour half-sweeps enqueued back to back (plain launches; `timed` adds the per-kernel bookkeeping)
+static int enqueue_iterations(picg_solver_s* s, const SorParams& p, unsigned n, bool timed) {
     const Grid& g = s->w->g;
-    dim3 grid(g.nj, g.ni);
-    LAUNCH(K_SOR, k_sor_row, grid, 128, 0, g, p, 0, s->w->phi, s->w->rho, s->cls); CHECK_LAUNCH();
-    LAUNCH(K_SOR, k_sor_row, grid, 128, 0, g, p, 1, s->w->phi, s->w->rho, s->cls); CHECK_LAUNCH();
+    const bool slab = s->slab_world > 1;
+    dim3 grid(g.nj, slab ? s->slab_i1 - s->slab_i0 : g.ni);
+    for (unsigned h = 0; h < 2 * n; h++) {
+        const int color = h & 1;
+        if (timed) {
+            if (slab) LAUNCH(K_SOR, k_sor_slab, grid, 128, 0, g, p, color, s->w->phi, s->w->rho, s->cls, slab_args(s, h + 1));
+            else LAUNCH(K_SOR, k_sor_row, grid, 128, 0, g, p, color, s->w->phi, s->w->rho, s->cls);
+        } else {
+            if (slab) k_sor_slab<<<grid, 128, 0, g_stream>>>(g, p, color, s->w->phi, s->w->rho, s->cls, slab_args(s, h + 1));
+            else k_sor_row<<<grid, 128, 0, g_stream>>>(g, p, color, s->w->phi, s->w->rho, s->cls);
+        }
+        CHECK_LAUNCH();
+    }
+    if (slab) { k_slab_advance<<<1, 1, 0, g_stream>>>(s->mbox, 2 * n); CHECK_LAUNCH(); }
     return PICG_OK;
+}
+// Runs n iterations.  Batches of 4 or more replay a CUDA graph captured once per (n, parameters): a half-sweep on a slab or on a
+// small mesh takes a few microseconds, less than a host-side launch.
+static int run_iterations(picg_solver_s* s, const SorParams& p, unsigned n) {
+    static const bool no_graph = getenv("PICG_NO_GRAPH") && atoi(getenv("PICG_NO_GRAPH")) != 0;
+    if (n == 0) return PICG_OK;
+    if (n < 4 || no_graph) return enqueue_iterations(s, p, n, true);
+    static_assert(sizeof(SorParams) <= sizeof(picg_solver_s::SorGraph::params), "SorGraph::params too small");
+    cudaGraphExec_t exec = nullptr;
+    for (auto& e : s->graphs) if (e.n == n && memcmp(e.params, &p, sizeof(SorParams)) == 0) exec = (cudaGraphExec_t)e.exec;
+    if (!exec) {
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+        g_capturing = true;
+        int rc = enqueue_iterations(s, p, n, false);
+        g_capturing = false;
+        cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+        picg_solver_s::SorGraph entry; entry.n = n; memset(entry.params, 0, sizeof(entry.params)); memcpy(entry.params, &p, sizeof(SorParams)); entry.exec = exec;
+        s->graphs.push_back(entry);
+    }
+    {
+        TimerScope t(K_SOR);                                      // the whole batch is one timed interval; every half-sweep counts as a launch
+        for (unsigned h = 0; h < 2 * n; h++) count_launch(K_SOR);
+        CUDA_TRY(cudaGraphLaunch(exec, g_stream));
+    }
+    return PICG_OK;
+}
+static void drop_graphs(picg_solver_s* s) {
+    for (auto& e : s->graphs) cudaGraphExecDestroy((cudaGraphExec_t)e.exec);
+    s->graphs.clear();
 }
 static int compute_residual(picg_solver_s* s, const SorParams& p, double* L2) {
     const Grid& g = s->w->g;
+    const size_t plane = (size_t)g.nj * g.nk;
+    if (s->slab_world > 1) {                                      // own planes only; the sum over ranks goes through the mailboxes
+        const size_t ub = s->slab_i0 * plane, ue = s->slab_i1 * plane;
+        int grid = std::min(div_up(ue - ub, 256), kResidualBlocks);
+        LAUNCH(K_RESIDUAL, k_slab_wait_halos, 1, 1, 0, slab_args(s, 0)); CHECK_LAUNCH();
+        LAUNCH(K_RESIDUAL, k_residual, grid, 256, 0, g, p, s->w->phi, s->w->rho, s->w->object_id, s->partial, ub, ue); CHECK_LAUNCH();
+        s->residual_seq++;
+        LAUNCH(K_RESIDUAL, k_slab_post_residual, 1, 256, 0, s->partial, grid, s->slab_rank, s->slab_world, s->peer_mbox_dev, s->residual_seq); CHECK_LAUNCH();
+        LAUNCH(K_RESIDUAL, k_slab_collect_residual, 1, 1, 0, s->mbox, s->slab_world, s->residual_seq, s->partial); CHECK_LAUNCH();
+        CUDA_TRY(cudaMemcpyAsync(s->w->reduce_host, s->partial, 8, cudaMemcpyDeviceToHost, g_stream));
+        CUDA_TRY(cudaStreamSynchronize(g_stream));
+        *L2 = std::sqrt(s->w->reduce_host[0] / g.nv);
+        return PICG_OK;
+    }
     int grid = std::min(div_up(g.nv, 256), kResidualBlocks);
-    LAUNCH(K_RESIDUAL, k_residual, grid, 256, 0, g, p, s->w->phi, s->w->rho, s->w->object_id, s->partial); CHECK_LAUNCH();
+    LAUNCH(K_RESIDUAL, k_residual, grid, 256, 0, g, p, s->w->phi, s->w->rho, s->w->object_id, s->partial, (size_t)0, (size_t)g.nv); CHECK_LAUNCH();
     CUDA_TRY(cudaMemcpyAsync(s->w->reduce_host, s->partial, grid * 8, cudaMemcpyDeviceToHost, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));
     double sum = 0; for (int b = 0; b < grid; b++) sum += s->w->reduce_host[b];
     *L2 = std::sqrt(sum / g.nv);                                  // normalised by all nv nodes (:154)
+    return PICG_OK;
+}
+// slab mode: every rank ends a solve with the full, identical phi (its own planes pushed to all peers)
+static int slab_allgather(picg_solver_s* s) {
+    if (s->slab_world <= 1) return PICG_OK;
+    const Grid& g = s->w->g;
+    const size_t plane = (size_t)g.nj * g.nk;
+    s->gather_seq++;
+    LAUNCH(K_MISC, k_slab_wait_halos, 1, 1, 0, slab_args(s, 0)); CHECK_LAUNCH();       // both neighbours have delivered their last half-sweep
+    LAUNCH(K_MISC, k_slab_push, g_sm_count * 2, 256, 0, s->w->phi, s->slab_i0 * plane, s->slab_i1 * plane, s->slab_rank, s->slab_world, s->peer_phi_dev); CHECK_LAUNCH();
+    LAUNCH(K_MISC, k_slab_gather_signal, 1, SLAB_MAX_RANKS, 0, s->slab_rank, s->slab_world, s->peer_mbox_dev, s->gather_seq); CHECK_LAUNCH();
+    LAUNCH(K_MISC, k_slab_gather_wait, 1, 1, 0, s->mbox, s->slab_rank, s->slab_world, s->gather_seq); CHECK_LAUNCH();
     return PICG_OK;
 }
 
@@ -173,7 +372,48 @@ int picg_solver_create(picg_world_t w, unsigned max_it, double tol, picg_solver_
     if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMalloc(solver)", __FILE__, __LINE__); }
     *out = s; return PICG_OK;
 }
-int picg_solver_destroy(picg_solver_t s) { if (!s) return PICG_OK; if (g_stream) cudaStreamSynchronize(g_stream); cudaFree(s->partial); cudaFree(s->cls); delete s; return PICG_OK; }
+int picg_solver_destroy(picg_solver_t s) {
+    if (!s) return PICG_OK;
+    if (g_stream) cudaStreamSynchronize(g_stream);
+    drop_graphs(s);
+    for (int r = 0; r < (int)s->peer_phi.size(); r++) if (r != s->slab_rank) { cudaIpcCloseMemHandle(s->peer_phi[r]); cudaIpcCloseMemHandle(s->peer_mbox[r]); }
+    cudaFree(s->peer_phi_dev); cudaFree(s->peer_mbox_dev); cudaFree(s->mbox);
+    cudaFree(s->partial); cudaFree(s->cls); delete s; return PICG_OK;
+}
+
+// Slab decomposition over `world` ranks on one node.  (1) every rank exports 128 bytes (the CUDA IPC handles of its phi and of
+// its mailbox); (2) the caller all-gathers them (torch.distributed, MPI ...) and hands the table of world x 128 bytes back.
+int picg_solver_slab_export(picg_solver_t s, void* handle128) {
+    REQUIRE_DEVICE(); REQUIRE_ARG(s && handle128, "picg_solver_slab_export: null argument");
+    if (!s->mbox) { CUDA_TRY(cudaMalloc(&s->mbox, MB_WORDS * 8)); CUDA_TRY(cudaMemset(s->mbox, 0, MB_WORDS * 8)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, s->w->phi)); memcpy(handle128, &h, 64);
+    CUDA_TRY(cudaIpcGetMemHandle(&h, s->mbox)); memcpy((char*)handle128 + 64, &h, 64);
+    return PICG_OK;
+}
+int picg_solver_slab_enable(picg_solver_t s, int rank, int world, const void* handles) {
+    REQUIRE_DEVICE(); REQUIRE_ARG(s && handles && world >= 1 && world <= SLAB_MAX_RANKS && rank >= 0 && rank < world, "picg_solver_slab_enable: bad argument");
+    REQUIRE_ARG(s->mbox, "picg_solver_slab_enable: call picg_solver_slab_export first");
+    const Grid& g = s->w->g;
+    REQUIRE_ARG(g.ni / world >= 2, "picg_solver_slab_enable: fewer than two planes per rank");
+    s->peer_phi.assign(world, nullptr); s->peer_mbox.assign(world, nullptr);
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { s->peer_phi[r] = s->w->phi; s->peer_mbox[r] = s->mbox; continue; }
+        cudaIpcMemHandle_t h; void* p = nullptr;
+        memcpy(&h, (const char*)handles + (size_t)r * 128, 64);
+        CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess)); s->peer_phi[r] = (double*)p;
+        memcpy(&h, (const char*)handles + (size_t)r * 128 + 64, 64);
+        CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess)); s->peer_mbox[r] = (u64*)p;
+    }
+    CUDA_TRY(cudaMalloc(&s->peer_phi_dev, world * sizeof(double*))); CUDA_TRY(cudaMalloc(&s->peer_mbox_dev, world * sizeof(u64*)));
+    CUDA_TRY(cudaMemcpy(s->peer_phi_dev, s->peer_phi.data(), world * sizeof(double*), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(s->peer_mbox_dev, s->peer_mbox.data(), world * sizeof(u64*), cudaMemcpyHostToDevice));
+    drop_graphs(s);
+    s->slab_rank = rank; s->slab_world = world;
+    s->slab_i0 = (int)(((long long)g.ni * rank) / world); s->slab_i1 = (int)(((long long)g.ni * (rank + 1)) / world);
+    return PICG_OK;
+}
 int picg_solver_set_reference(picg_solver_t s, double phi0, double n0, double Te0) {
     REQUIRE_ARG(s, "picg_solver_set_reference: null solver"); s->phi0 = phi0; s->n0 = n0; s->Te0 = Te0; return PICG_OK;
 }
@@ -185,14 +425,18 @@ int picg_solver_solve_gs(picg_solver_t s, int* converged, unsigned* iterations, 
     REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_solver_solve_gs: null solver");
     SorParams p = make_params(s);
     { int rc0 = prepare_classes(s); if (rc0) return rc0; }
-    double L2 = 0; bool conv = false; unsigned it;
-    for (it = 0; it < s->max_it; it++) {
-        int rc = launch_iteration(s, p); if (rc) return rc;
-        if (it % 25 == 0) {                                        // :124
+    double L2 = 0; bool conv = false; unsigned it = 0;               // it: iterations completed
+    while (it < s->max_it) {
+        // the reference checks the residual right after iteration index chk, chk % 25 == 0 (:124): run up to it in one batch
+        const unsigned chk = ((it + 24) / 25) * 25, last = std::min(chk, s->max_it - 1);
+        int rc = run_iterations(s, p, last - it + 1); if (rc) return rc;
+        it = last + 1;
+        if (last == chk) {
             rc = compute_residual(s, p, &L2); if (rc) return rc;
-            if (L2 < s->tol) { conv = true; it++; break; }
+            if (L2 < s->tol) { conv = true; break; }
         }
     }
+    { int rc = slab_allgather(s); if (rc) return rc; }
     if (converged) *converged = conv; if (iterations) *iterations = it; if (L2_out) *L2_out = L2;
     return PICG_OK;
 }
@@ -201,8 +445,8 @@ int picg_solver_iterate(picg_solver_t s, unsigned n) {
     REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_solver_iterate: null solver");
     SorParams p = make_params(s);
     { int rc0 = prepare_classes(s); if (rc0) return rc0; }
-    for (unsigned it = 0; it < n; it++) { int rc = launch_iteration(s, p); if (rc) return rc; }
-    return PICG_OK;
+    { int rc = run_iterations(s, p, n); if (rc) return rc; }
+    return slab_allgather(s);
 }
 
 int picg_solver_residual(picg_solver_t s, double* L2) {

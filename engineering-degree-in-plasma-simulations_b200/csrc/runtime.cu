@@ -12,6 +12,7 @@ int g_sm_count = PICG_SM_COUNT_FALLBACK;
 uint64_t g_seed = 0x5EED0000ull;
 int g_rank = 0, g_world_size = 1;
 uint64_t g_reallocs = 0;
+bool g_capturing = false;
 static thread_local char g_err[1024] = "";
 static uint64_t g_launches = 0;
 static bool g_timers_on = false;
@@ -31,13 +32,13 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     cudaGetLastError();   // clear the sticky-less error state
     return code;
 }
-void count_launch(int id) { g_launches++; if (id >= 0 && id < K_NUM_KERNELS) g_timer_n[id]++; }
+void count_launch(int id) { if (g_capturing) return; g_launches++; if (id >= 0 && id < K_NUM_KERNELS) g_timer_n[id]++; }
 
 static cudaEvent_t get_event() {
     if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
-TimerScope::TimerScope(int id_) : id(id_), on(g_timers_on) {
+TimerScope::TimerScope(int id_) : id(id_), on(g_timers_on && !g_capturing) {
     if (on) { a = get_event(); b = get_event(); cudaEventRecord(a, g_stream); }
 }
 TimerScope::~TimerScope() {

@@ -156,10 +156,10 @@ __global__ void __launch_bounds__(256) k_cell_start(const u64* __restrict__ n_pt
 //   list(c) = home range of c  minus  movers whose home is c  plus  movers whose current cell is c.
 __global__ void __launch_bounds__(256) k_find_movers(Grid g, const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pz,
                                                      const unsigned* __restrict__ home, const u64* __restrict__ n_ptr, const unsigned* __restrict__ part_n_ptr,
-                                                     int tail_only, u64* __restrict__ count, u64 cap, unsigned* __restrict__ m_slot,
+                                                     const u64* __restrict__ listed_ptr, u64* __restrict__ count, u64 cap, unsigned* __restrict__ m_slot,
                                                      unsigned* __restrict__ m_cell, unsigned* __restrict__ m_home) {
     const u64 n = *n_ptr, part_n = *part_n_ptr;
-    const u64 first = tail_only ? min(part_n, n) : 0;                        // tail_only: the partition's movers are already listed (deposit pass)
+    const u64 first = listed_ptr ? min(*listed_ptr, n) : 0;                  // slots below are already listed (by the last deposit pass)
     const int lane = threadIdx.x & 31;
     for (u64 p0 = (first & ~(u64)31) + (blockIdx.x * (u64)blockDim.x + threadIdx.x) - lane; p0 < n; p0 += (u64)gridDim.x * blockDim.x) {
         u64 p = p0 + lane;
@@ -313,9 +313,9 @@ int species_exact_lists(picg_species_s* s) {
     const int tail_only = s->movers_fresh ? 1 : 0;                           // the last deposit pass listed the partition's movers: only the appended tail is left
     if (!tail_only) CUDA_TRY(cudaMemsetAsync(cnt, 0, 8, g_stream));
     if (tail_only) g_movers_from_deposit++; else g_mover_scans++;
-    size_t n_scan = tail_only ? (n > s->part_n ? n - s->part_n : 0) + 32 : n;
+    size_t n_scan = tail_only ? std::max<size_t>(n > s->part_n ? n - s->part_n : 0, (size_t)1 << 18) : n;   // grid size only (grid-stride loop)
     int pgrid = std::max(1, std::min(div_up(std::max<size_t>(n_scan, 1), 256), g_sm_count * 8));
-    LAUNCH(K_SORT_KEYS, k_find_movers, pgrid, 256, 0, g, s->a[0], s->a[1], s->a[2], s->home, &s->ctr->n, s->cell_start + g.nc, tail_only, cnt, (u64)mcap, m_slot, m_cell, m_home);
+    LAUNCH(K_SORT_KEYS, k_find_movers, pgrid, 256, 0, g, s->a[0], s->a[1], s->a[2], s->home, &s->ctr->n, s->cell_start + g.nc, tail_only ? &s->ctr->n_listed : nullptr, cnt, (u64)mcap, m_slot, m_cell, m_home);
     CHECK_LAUNCH();
     u64 n_live_movers = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_live_movers, cnt, 8, cudaMemcpyDeviceToHost, g_stream));

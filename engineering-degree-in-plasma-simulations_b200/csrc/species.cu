@@ -146,7 +146,7 @@ int species_add_staged(picg_species_s* s, size_t n, const double* d_aos) {
     LAUNCH(K_ADD_PARTICLES, k_add_particles, std::max(1, std::min(div_up(n, 256), g_sm_count * 8)), 256, 0, s->w->g, n, d_aos,
            soa_of(s), s->cap, s->ctr, s->w->ef, q_over_m, half_dt);
     CHECK_LAUNCH();
-    s->n_host_valid = false; s->n_upper = std::min(s->cap, s->n_upper + n); s->sorted_valid = false; s->lists_valid = false; s->movers_fresh = false; s->count_valid = false;
+    s->n_host_valid = false; s->n_upper = std::min(s->cap, s->n_upper + n); s->sorted_valid = false; s->lists_valid = false; s->count_valid = false;
     return PICG_OK;
 }
 }
@@ -257,7 +257,7 @@ int picg_species_add_particles(picg_species_t s, size_t n, const double* aos7, s
         CHECK_LAUNCH();
         CUDA_TRY(cudaStreamSynchronize(g_stream));
     }
-    s->n_host_valid = false; s->n_upper = before + n; s->sorted_valid = false; s->lists_valid = false; s->movers_fresh = false; s->count_valid = false;
+    s->n_host_valid = false; s->n_upper = before + n; s->sorted_valid = false; s->lists_valid = false; s->count_valid = false;
     rc = species_refresh_count(s);
     if (accepted) *accepted = s->n_host - before;
     return rc;

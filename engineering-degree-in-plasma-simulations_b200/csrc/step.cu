@@ -244,7 +244,7 @@ int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals
     // fast path of the deposit passes: the store carries a cell partition (cell_start[] of the last sort, possibly stale) and
     // is dense enough for a lane group per cell.  (A count alone is a pure stream: the thread-run kernel is at 85 % of HBM.)
     static const bool no_cell_path = getenv("PICG_NO_CELL_PATH") && atoi(getenv("PICG_NO_CELL_PATH")) != 0;      // A/B switch, see DESIGN.md
-    if (!no_cell_path && (mode == 4 || mode == 12) && s->part_valid && nu >= (size_t)12 * g.nc) {
+    if (!no_cell_path && (mode == 4 || mode == 12) && s->part_valid && nu >= (size_t)6 * g.nc) {
         int rc = launch_cell_step(s, mode, (size_t)-1, nu); if (rc) return rc;
         if (nu <= s->part_n) return PICG_OK;              // nothing was appended since the sort
         A.tail_from = s->cell_start + g.nc;               // the appended tail goes through the generic kernel
@@ -300,7 +300,7 @@ int species_step(picg_species_s* s, bool push, bool heavy, bool deposit, bool fi
     int mode = (push ? 1 : 0) | (heavy ? 2 : 0) | (deposit ? 4 : 0) | (count ? 8 : 0);
     rc = launch_step(s, mode, dt, neutrals, spherium, sputtering, n_snapshot); if (rc) return rc;
     if (heavy && s->charge != 0) {
-        for (picg_species_s* t : {neutrals, spherium}) { t->n_host_valid = false; t->sorted_valid = false; t->lists_valid = false; t->movers_fresh = false; t->count_valid = false; t->n_upper = t->cap; }
+        for (picg_species_s* t : {neutrals, spherium}) { t->n_host_valid = false; t->sorted_valid = false; t->lists_valid = false; t->count_valid = false; t->n_upper = t->cap; }
     }
     if (push) { rc = compact_dead(s, cap); if (rc) return rc; }
     if (count) s->count_valid = true;                // counted at the post-push positions; the compaction only permutes survivors

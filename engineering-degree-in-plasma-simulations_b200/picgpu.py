@@ -371,6 +371,14 @@ class PotentialSolver:
     def computeEF(self):
         _chk(lib().picg_solver_compute_ef(self.h))
 
+    def enableSlabs(self, rank, world, all_gather_bytes):
+        """Multi-GPU slab decomposition of the solve.  all_gather_bytes(b: bytes) -> list of `world` bytes objects (rank order)."""
+        mine = C.create_string_buffer(128)
+        _chk(lib().picg_solver_slab_export(self.h, mine))
+        table = b"".join(all_gather_bytes(bytes(mine.raw)))
+        assert len(table) == 128 * world
+        _chk(lib().picg_solver_slab_enable(self.h, int(rank), int(world), table))
+
 
 class MccStats(C.Structure):
     _fields_ = [("candidates", C.c_uint64), ("collisions", C.c_uint64), ("ionizations", C.c_uint64), ("w_sigma_v_max", C.c_double), ("dropped", C.c_uint64)]

@@ -184,6 +184,12 @@ PICG_API int picg_solver_iterate(picg_solver_t s, unsigned n);
 PICG_API int picg_solver_residual(picg_solver_t s, double* L2);
 /* computeEF  PotentialSolver.cpp:354-408 */
 PICG_API int picg_solver_compute_ef(picg_solver_t s);
+/* multi-GPU (one process per GPU, one node): split the planes of the slowest index over `world` ranks.  Halo planes, the
+ * residual sum and the final all-gather of phi go through peer memory (CUDA IPC over NVLink), inside the sweep kernels.
+ * export: 128 bytes per rank (IPC handles of phi and of the mailbox); the caller all-gathers them and passes the table of
+ * world x 128 bytes to enable (a collective: every rank must call both).  Every rank must then make the same solver calls. */
+PICG_API int picg_solver_slab_export(picg_solver_t s, void* handle128);
+PICG_API int picg_solver_slab_enable(picg_solver_t s, int rank, int world, const void* handles);
 
 /* -------------------------------------------------------- MC_MEX_Ionization */
 /* MC_MEX_Ionization(neutrals, ions, electrons, world, table)  Interactions.cpp:476-539; the cross-section table
