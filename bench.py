@@ -221,12 +221,22 @@ def run_ours(args):
 
     counts = {}
 
+    prof = {} if os.environ.get("PICG_E2E_PROFILE") else None   # host wall time per phase (debugging aid; synchronises)
+
+    def stamp(name, t0):
+        if prof is not None:
+            pg.synchronize(); prof[name] = prof.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
+
     def step(ts, inject=None):
         """One pass of the v3 main-loop body (main.cpp:197-261) through the C ABI."""
+        t0 = time.perf_counter()
         if inject is not None:                              # Source::sample on the host side: H2D of this step's new particles
             ele.addParticles(inject)
+            t0 = stamp("inject", t0)
         if mcc is not None:
             mcc.apply(wl["dt"])
+            t0 = stamp("mcc", t0)
         for sp in order:
             if world == 1:
                 if sp is ele:
@@ -249,12 +259,14 @@ def run_ours(args):
                 sp.sampleMoments()
             if mcc is None and args.sort_every and ts % args.sort_every == 0:
                 sp.sort()
+            t0 = stamp("species " + sp.name, t0)
         if ts > 5:
             for sp in order:
                 sp.updateAverages()
         w.computeChargeDensity(order)
         sol.solveGS()
         sol.computeEF()
+        stamp("fields", t0)
         return sol.iterations
 
     def barrier():
@@ -276,9 +288,12 @@ def run_ours(args):
             it = step(ts0 + k, inject_bufs[k % len(inject_bufs)] if e2e else None)
             its += it
             if e2e:                                           # what the reference loop reads every step: counts + diagnostics + rho
+                t0 = time.perf_counter()
                 for sp in order:
                     sp.diagnostics()
+                t0 = stamp("diagnostics", t0)
                 pg._chk(pg.lib().picg_world_download(w.h, pg.F_RHO, rho_host.ctypes.data_as(pg.C.POINTER(pg.C.c_double))))
+                stamp("rho download", t0)
                 psteps += n_now
         ev1.record(stream)
         barrier()
@@ -352,8 +367,20 @@ def run_ours(args):
             entry["frac_of_peak"] = round(entry["GBps"] / peak, 4)
         kernels[name] = entry
     dom = max((k for k in kernels if "GBps" in kernels[k]), key=lambda k: kernels[k]["ms_total"])
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this workload (profiles/capture.sh ->
+    # profiles/ncu_traffic.py); only quoted when the run IS that workload (same mesh, particle count, one GPU)
+    traffic, traffic_src = None, None
+    ncu_names = {"push_heavy": "k_run<1, 1, 0, 0>", "push_electrons": "k_run<1, 0, 0, 0>", "sor_redblack": "k_sor_row"}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+        if world == 1 and m == 256 and abs(args.particles - 1e9) < 1 and dom in ncu_names:
+            ent = tj["kernels"][ncu_names[dom]]
+            traffic = float(np.mean([e["dram_bytes"] for e in ent]))
+            traffic_src = "profiles/ncu_traffic_r1.json (%s, mean of %d captured launches)" % (ncu_names[dom], len(ent))
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac_of_peak"],
-                "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": kernels[dom]["alg_GB_per_launch"] * 1e9}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "alg_bytes_per_launch": kernels[dom]["alg_GB_per_launch"] * 1e9}
     poisson_ms = sum(kernels[k]["ms_total"] for k in ("sor_redblack", "sor_tiled", "residual_l2", "compute_ef") if k in kernels) / args.steps
 
     # ---- end to end through the C ABI with host buffers (pinned): inject + diagnostics + rho download every step
@@ -371,7 +398,11 @@ def run_ours(args):
     e2e_steps = max(2, min(args.steps, 5))
     reallocs1 = pg.realloc_count()
     pg.timers_reset(); pg.timers_enable(True)
+    if prof is not None:
+        prof.clear()
     ms_e2e, ps_local, _ = timed(e2e_steps, ts, e2e=True, inject_bufs=inj, rho_host=rho_host)
+    if prof is not None and rank == 0:
+        print("e2e host profile (ms/step): " + json.dumps({k: round(v / e2e_steps, 2) for k, v in prof.items()}), file=sys.stderr)
     pg.timers_enable(False)
     kt_e2e = {k: round(v[0] / e2e_steps, 3) for k, v in pg.timers_read().items()}
     if world > 1:

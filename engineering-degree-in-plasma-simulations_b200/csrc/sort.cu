@@ -204,13 +204,26 @@ __global__ void k_gather_u32(const u64* __restrict__ n_ptr, const unsigned* __re
 }
 __global__ void k_clamp_u64(u64* v, u64 cap) { if (*v > cap) *v = cap; }
 
-// the same table for a SPARSE sorted key list (movers): one binary search per cell instead of one loop over the gap per key
-__global__ void __launch_bounds__(256) k_cell_start_search(const u64* __restrict__ n_ptr, const unsigned* __restrict__ keys, int nc, unsigned* __restrict__ cell_start) {
+// The same table for a SPARSE sorted key list (movers).  A key at position p owns the cells (previous key, its key]: short gaps are
+// filled by the key's thread, long ones (a few: at most nc/32) are queued and filled by a warp each.  nc + 1 writes in total.
+__global__ void __launch_bounds__(256) k_cell_start_sparse(const u64* __restrict__ n_ptr, const unsigned* __restrict__ keys, int nc, unsigned* __restrict__ cell_start,
+                                                           unsigned* __restrict__ queue /* [0]: count, then (lo, hi, p) triples */) {
     const u64 n = *n_ptr;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= nc; c += gridDim.x * blockDim.x) {
-        u64 lo = 0, hi = n;                                   // first position whose key >= c
-        while (lo < hi) { u64 mid = (lo + hi) >> 1; if (keys[mid] < (unsigned)c) lo = mid + 1; else hi = mid; }
-        cell_start[c] = (unsigned)lo;
+    for (u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x; p <= n; p += (u64)gridDim.x * blockDim.x) {
+        const unsigned prev = (p == 0) ? 0u : keys[p - 1];
+        if (p > 0 && prev >= (unsigned)nc) continue;                                      // everything up to nc is owned by an earlier position
+        const int lo = (p == 0) ? 0 : (int)prev + 1;
+        const int hi = (p == n) ? nc : (int)min(keys[p], (unsigned)nc);                   // keys >= nc (movers without a home) sort last
+        if (hi - lo < 32) { for (int c = lo; c <= hi; c++) cell_start[c] = (unsigned)p; }
+        else { unsigned q = atomicAdd(queue, 1u); queue[1 + 3 * q] = (unsigned)lo; queue[2 + 3 * q] = (unsigned)hi; queue[3 + 3 * q] = (unsigned)p; }
+    }
+}
+__global__ void __launch_bounds__(256) k_cell_start_long(const unsigned* __restrict__ queue, unsigned* __restrict__ cell_start) {
+    const unsigned nq = queue[0];
+    const int lane = threadIdx.x & 31;
+    for (unsigned q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += (gridDim.x * blockDim.x) >> 5) {
+        const unsigned lo = queue[1 + 3 * q], hi = queue[2 + 3 * q], p = queue[3 + 3 * q];
+        for (unsigned c = lo + lane; c <= hi; c += 32) cell_start[c] = p;
     }
 }
 
@@ -301,7 +314,8 @@ int species_exact_lists(picg_species_s* s) {
     // radix ping-pong buffers in the scratch arena
     size_t mcapa = (mcap_alloc + 63) & ~(size_t)63;
     int nblocks = std::max(1, std::min(div_up(mcap, SORT_TILE), g_sm_count * 4));
-    size_t bytes = mcapa * 4 * 4 + (size_t)256 * nblocks * 4 + 256;
+    const size_t queue_words = 4 + 3 * ((size_t)g.nc / 32 + 64);                 // long-gap queue of k_cell_start_sparse
+    size_t bytes = mcapa * 4 * 4 + (size_t)256 * nblocks * 4 + 256 + queue_words * 4;
     rc = ensure_scratch(s->w, bytes); if (rc) return rc;
     rc = ensure_u32(s->mv_in, s->mv_cap, mcapa * 2); if (rc) return rc;     // [0,mcapa): slots ordered by current cell, [mcapa, 2 mcapa): slots ordered by home cell
     s->mv_stride = mcapa;
@@ -309,6 +323,7 @@ int species_exact_lists(picg_species_s* s) {
     unsigned* m_slot = s->mv_trip; unsigned* m_cell = m_slot + s->mv_trip_cap; unsigned* m_home = m_cell + s->mv_trip_cap;
     unsigned* kB = (unsigned*)s->w->scratch; unsigned* vA = kB + mcapa; unsigned* vB = vA + mcapa; unsigned* tmp = vB + mcapa;
     unsigned* counts = tmp + mcapa;
+    unsigned* queue = counts + (size_t)256 * nblocks + 64;
     u64* cnt = &s->ctr->n_movers;                                            // device-side mover count
     const int tail_only = s->movers_fresh ? 1 : 0;                           // the last deposit pass listed the partition's movers: only the appended tail is left
     if (!tail_only) CUDA_TRY(cudaMemsetAsync(cnt, 0, 8, g_stream));
@@ -329,8 +344,10 @@ int species_exact_lists(picg_species_s* s) {
         LAUNCH(K_SORT_KEYS, k_iota_u32, mgrid, 256, 0, cnt, va); CHECK_LAUNCH();
         LAUNCH(K_SORT_KEYS, k_copy_u32, mgrid, 256, 0, cnt, m_cell, tmp); CHECK_LAUNCH();          // keep m_cell intact? (not needed later) -> sort a copy
         ka = tmp;
-        rc = radix_sort_pairs(cnt, mcap, bits, ka, va, kb, vb, counts, nblocks); if (rc) return rc;
-        LAUNCH(K_CELL_START, k_cell_start_search, std::min(div_up((size_t)g.nc + 1, 256), g_sm_count * 8), 256, 0, cnt, ka, g.nc, s->in_start); CHECK_LAUNCH();
+        rc = radix_sort_pairs(cnt, mcap, bits, ka, va, kb, vb, counts, std::min(nblocks, div_up(std::max<size_t>((size_t)n_live_movers, 1), SORT_TILE))); if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(queue, 0, 4, g_stream));
+        LAUNCH(K_CELL_START, k_cell_start_sparse, mgrid, 256, 0, cnt, ka, g.nc, s->in_start, queue); CHECK_LAUNCH();
+        LAUNCH(K_CELL_START, k_cell_start_long, g_sm_count * 2, 256, 0, queue, s->in_start); CHECK_LAUNCH();
         LAUNCH(K_SORT_PERMUTE, k_gather_u32, mgrid, 256, 0, cnt, va, m_slot, s->mv_in); CHECK_LAUNCH();
     }
     // (2) out-lists: every slot whose particle left its home cell (live movers with a home + slots vacated beyond n), ordered by home
@@ -343,8 +360,10 @@ int species_exact_lists(picg_species_s* s) {
         int mgrid2 = std::max(1, std::min(div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), 256), g_sm_count * 4));
         LAUNCH(K_SORT_KEYS, k_iota_u32, mgrid2, 256, 0, cnt, va); CHECK_LAUNCH();
         int hbits = 1; while ((1ull << hbits) < (u64)g.nc + 1) hbits++;
-        rc = radix_sort_pairs(cnt, mcap, hbits, ka, va, kb, vb, counts, nblocks); if (rc) return rc;
-        LAUNCH(K_CELL_START, k_cell_start_search, std::min(div_up((size_t)g.nc + 1, 256), g_sm_count * 8), 256, 0, cnt, ka, g.nc, s->out_start); CHECK_LAUNCH();
+        rc = radix_sort_pairs(cnt, mcap, hbits, ka, va, kb, vb, counts, std::min(nblocks, div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), SORT_TILE))); if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(queue, 0, 4, g_stream));
+        LAUNCH(K_CELL_START, k_cell_start_sparse, mgrid2, 256, 0, cnt, ka, g.nc, s->out_start, queue); CHECK_LAUNCH();
+        LAUNCH(K_CELL_START, k_cell_start_long, g_sm_count * 2, 256, 0, queue, s->out_start); CHECK_LAUNCH();
         LAUNCH(K_SORT_PERMUTE, k_gather_u32, mgrid2, 256, 0, cnt, va, m_slot, s->mv_in + mcapa); CHECK_LAUNCH();
     }
     s->lists_valid = true;
