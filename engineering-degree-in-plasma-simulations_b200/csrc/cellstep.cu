@@ -24,6 +24,7 @@
 // Algorithmic bytes per particle: deposit 32 B (pos + mpw), count 24 B.
 #include "common.cuh"
 #include "deposit.cuh"
+#include "tma.cuh"
 #include <algorithm>
 #include <cmath>
 
@@ -42,26 +43,6 @@ struct CellArgs {
     // optional by-product: (slot, current cell, home cell) of every particle found outside its slot's home cell (sort.cu: movers)
     unsigned *mv_slot, *mv_cell, *mv_home; u64* mv_count; u64* mv_listed; u64 mv_cap;
 };
-
-// ---------------------------------------------------------------- PTX: mbarrier + bulk async copy (TMA, 1-D)
-__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
-    asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n}"
-                 :: "r"(smem_addr(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, u64* bar, u64 policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
-}
-__device__ __forceinline__ u64 policy_evict_first() {
-    u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
-}
 
 // ---------------------------------------------------------------- the kernel
 // Uniform per warp (every lane holds the same values) except cs: lane l <= P holds cell_start[c0 + l] of the pass.

@@ -251,7 +251,7 @@ int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals
         nu = nu - s->part_n;
     }
     if (mode & 2) CUDA_TRY(cudaMemsetAsync(&s->ctr->n_impact, 0, 8, g_stream));
-    int rc;
+    int rc = PICG_OK;
     switch (mode) {
         case 1:  rc = launch_variant<true, false, false, false>(g, A, H, nu, K_PUSH_ELECTRONS); break;
         case 3:  rc = launch_variant<true, true, false, false>(g, A, H, nu, K_PUSH_HEAVY); break;

@@ -66,6 +66,28 @@ def test_push_electrons_matches_oracle(picgpu, orc, n):
     sp.close(); w.close()
 
 
+@pytest.mark.parametrize("n,steps", [(8000, 1), (24000, 3), (50000, 2), (90000, 2), (400000, 1)])
+def test_push_of_a_sorted_store_matches_oracle(picgpu, orc, n, steps):
+    """Electron push of a cell-sorted store against the oracle, bit for bit, over several pushes on an increasingly stale
+    partition (stragglers, holes, deaths) and over a range of cell populations."""
+    sph = [((0.0, 0.0, 0.0025), -100.0, 0.0007)]
+    w, g, x0, xm = _setup(picgpu, orc, spheres=sph)
+    ef = util.smooth_ef((w.ni, w.nj, w.nk), x0, xm, seed=5, amp=3e6)
+    w.upload(picgpu.F_EF, ef)
+    parts = util.random_particles(n, x0, xm, seed=40 + n, vth=2e6)
+    sp = picgpu.Species("e-", util.ME, -util.QE, w, 100.0)
+    sp.setParticles(parts); sp.sort()
+    cur = sp.getParticles()
+    for it in range(steps):
+        sp.advanceElectrons(5e-11)
+        want, alive = g.push_electrons(ef, -util.QE, util.ME, 5e-11, cur)
+        got = sp.getParticles()
+        assert sp.getNumParticles() == alive.sum() and alive.sum() < len(cur)
+        assert np.array_equal(util.sort_rows(got), util.sort_rows(want[alive]))
+        cur = got
+    sp.close(); w.close()
+
+
 def test_push_electrons_everything_dies_and_nothing_dies(picgpu, orc):
     w, g, x0, xm = _setup(picgpu, orc)
     ef = np.zeros((w.ni, w.nj, w.nk, 3))
