@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--moments", action="store_true", help="also run Species::sampleMoments every step (SURVEY 8f row 1)")
     ap.add_argument("--cpu_sample_nodes", type=int, default=49, help="nodes per axis of the CPU-baseline sub-volume (same dx, same particles per cell)")
     ap.add_argument("--skip_cpu_baseline", action="store_true")
+    ap.add_argument("--allreduce_density", action="store_true", help="multi-GPU: all-reduce the density accumulators (full grids everywhere) instead of a reduce-scatter onto the slabs")
     ap.add_argument("--poisson", choices=["auto", "replicated", "slab"], default="auto",
                     help="multi-GPU solve: every rank solves the whole grid, or planes split over the ranks with peer-memory halos (auto: slab when N > 1)")
     ap.add_argument("--init_max_it", type=int, default=20000, help="iteration cap of the initial vacuum solve (profiling runs use a small value)")
@@ -161,6 +162,7 @@ def run_ours(args):
 
     wl = workload(args.mesh, args.particles)
     m = wl["mesh"]
+    nv_total = m ** 3
     w = pg.World(m, m, m, wl["x0"], wl["xm"])
     w.setTime(wl["dt"], 1 << 30)
     for c, phi, sides in wl["rects"]:
@@ -217,6 +219,14 @@ def run_ours(args):
         sp.computeNumberDensity()
         sp.setDensityScale(mg.common_scale(sp.densityScale(), world, reduce_min))
     fixed_views = {sp.name: mg.fixed_view(torch, sp, pg.SF_DEN_FIXED) for sp in order} if world > 1 else {}
+    # Slab Poisson reads rho only on this rank's planes: reduce-scatter the accumulators onto the slabs (in place: rank r's output is
+    # the r-th chunk of its own input) and finalize / sum charges there only.  Needs equal chunks = planes divisible by the ranks.
+    slab_range, scatter_chunks, density_mode = None, None, "all-reduce (full grids on every rank)"
+    if world > 1 and poisson_mode.startswith("slab") and m % world == 0 and not args.allreduce_density:
+        slab_range = sol.slabRange()
+        scatter_chunks = {name: list(v.chunk(world)) for name, v in fixed_views.items()}
+        assert slab_range == (rank * (nv_total // world), (rank + 1) * (nv_total // world))
+        density_mode = "reduce-scatter onto the Poisson slabs (density and rho finalised on the owned planes only)"
     setup_s = time.time() - t0
 
     counts = {}
@@ -252,8 +262,11 @@ def run_ours(args):
                     sp.advanceNonElectron(neu, neu, wl["dt"])
                 sp.depositPartial()
                 with torch.cuda.stream(stream):
-                    dist.all_reduce(fixed_views[sp.name])                        # int64 sum over NVLink
-                sp.finalizeDensity()
+                    if scatter_chunks is not None:                              # each rank only needs the sums on the planes it solves on
+                        dist.reduce_scatter_tensor(scatter_chunks[sp.name][rank], fixed_views[sp.name])
+                    else:
+                        dist.all_reduce(fixed_views[sp.name])                   # int64 sum over NVLink
+                sp.finalizeDensity(slab_range)
                 sp.computeMacroParticlesCount()
             if args.moments:
                 sp.sampleMoments()
@@ -263,7 +276,7 @@ def run_ours(args):
         if ts > 5:
             for sp in order:
                 sp.updateAverages()
-        w.computeChargeDensity(order)
+        w.computeChargeDensity(order, slab_range)
         sol.solveGS()
         sol.computeEF()
         stamp("fields", t0)
@@ -375,6 +388,8 @@ def run_ours(args):
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
         if world == 1 and m == 256 and abs(args.particles - 1e9) < 1 and dom in ncu_names:
             ent = tj["kernels"][ncu_names[dom]]
+            if dom == "push_heavy":
+                ent = ent[:2]                                     # one launch per heavy species (O, O+), like alg_bytes_per_launch
             traffic = float(np.mean([e["dram_bytes"] for e in ent]))
             traffic_src = "profiles/ncu_traffic_r1.json (%s, mean of %d captured launches)" % (ncu_names[dom], len(ent))
     except Exception:
@@ -421,7 +436,7 @@ def run_ours(args):
                           "steps_per_sort": 1 if mcc else args.sort_every, "mcc": mcc is not None, "moments": bool(args.moments),
                           "poisson": {"max_it": args.s_max_it, "tol": args.s_tol, "mode": poisson_mode, "iterations_per_step": its / args.steps,
                                       "initial_solve_iterations": init_iters},
-                          "parallelism": "particles split by index over %d GPU(s); int64 density all-reduce; Poisson %s" % (world, poisson_mode.split(" ")[0]),
+                          "parallelism": "particles split by index over %d GPU(s); int64 density %s; Poisson %s" % (world, density_mode if world > 1 else "on one GPU", poisson_mode.split(" ")[0]),
                           "l2_policy": "inputs larger than L2 (%.1f GB of particle arrays per GPU vs 126 MB L2)" % (sum(per_rank_counts.values()) * 56 / 1e9)},
                "poisson_ms_per_step": poisson_ms, "gpu_launches": int(launches), "device_reallocs_in_timed_region": int(reallocs_timed), "clocks": clk, "roofline": roofline, "kernels": kernels, "e2e": e2e,
                "setup_s": round(setup_s, 1)}

@@ -98,7 +98,8 @@ struct picg_solver_s {
     double phi0 = 0, n0 = 0, Te0 = 1;
     int bc_mode = 0;
     double* partial = nullptr;         // residual partial sums
-    unsigned char* cls = nullptr;      // node class per node (poisson.cu), rebuilt at the start of every solve
+    unsigned char* cls = nullptr;      // node class per colour-compact node (poisson.cu), rebuilt at the start of every solve
+    double* rho_split = nullptr;       // rho per colour-compact node: a colour half-sweep reads its own half with unit stride
     // multi-GPU slab decomposition (poisson.cu): planes [i0, i1) of the slowest index belong to this rank; halo planes,
     // residual sums and the final all-gather go through peer memory (CUDA IPC), signalled by flags in the mailboxes
     int slab_rank = 0, slab_world = 1, slab_i0 = 0, slab_i1 = 0;

@@ -11,10 +11,10 @@
 using namespace picg;
 
 // den = (fixed * 2^-S) / node_vol, 0 where node_vol == 0; tracks max and overflow (negative) nodes.
-__global__ void __launch_bounds__(256) k_finalize_den(int nv, const i64* __restrict__ fixed, const double* __restrict__ vol,
+__global__ void __launch_bounds__(256) k_finalize_den(int u_begin, int u_end, const i64* __restrict__ fixed, const double* __restrict__ vol,
                                                       double inv_scale, double* __restrict__ den, SpeciesCounters* ctr) {
     i64 mx = 0; unsigned neg = 0;
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < nv; u += gridDim.x * blockDim.x) {
+    for (int u = u_begin + blockIdx.x * blockDim.x + threadIdx.x; u < u_end; u += gridDim.x * blockDim.x) {
         i64 f = fixed[u];
         mx = max(mx, f); neg += f < 0;
         double d = __dmul_rn((double)f, inv_scale);
@@ -71,12 +71,15 @@ __global__ void k_gas_properties(int nv, const double* __restrict__ n_sum, const
 
 namespace picg {
 int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals, picg_species_s* spherium, int sputtering, size_t n_snapshot);   // step.cu
+int launch_finalize(picg_species_s* s, size_t u_begin = 0, size_t u_end = (size_t)-1);
 static int pow2_floor_log(i64 v) { int l = -1; while (v > 0) { v >>= 1; l++; } return l; }
 
-int launch_finalize(picg_species_s* s) {
+int launch_finalize(picg_species_s* s, size_t u_begin, size_t u_end) {
     const Grid& g = s->w->g;
+    u_end = std::min(u_end, (size_t)g.nv);
+    if (u_begin >= u_end) return PICG_OK;
     LAUNCH(K_MISC, k_reset_den_stats, 1, 1, 0, s->ctr); CHECK_LAUNCH();
-    LAUNCH(K_FINALIZE_DEN, k_finalize_den, std::min(div_up(g.nv, 256), g_sm_count * 8), 256, 0, g.nv, s->den_fixed, s->w->node_vol,
+    LAUNCH(K_FINALIZE_DEN, k_finalize_den, std::min(div_up(u_end - u_begin, 256), g_sm_count * 8), 256, 0, (int)u_begin, (int)u_end, s->den_fixed, s->w->node_vol,
            std::ldexp(1.0, -s->S), s->den, s->ctr);
     CHECK_LAUNCH();
     return PICG_OK;
@@ -131,6 +134,10 @@ int picg_species_density_scale(picg_species_t s, int* S) { REQUIRE_ARG(s && S, "
 int picg_species_finalize_density(picg_species_t s) {
     REQUIRE_DEVICE(); REQUIRE_ARG(s, "picg_species_finalize_density: null species");
     return launch_finalize(s);
+}
+int picg_species_finalize_density_range(picg_species_t s, size_t node_begin, size_t node_end) {
+    REQUIRE_DEVICE(); REQUIRE_ARG(s && node_begin <= node_end, "picg_species_finalize_density_range: bad argument");
+    return launch_finalize(s, node_begin, node_end);
 }
 
 int picg_species_sample_moments(picg_species_t s) {

@@ -1,5 +1,5 @@
 // PotentialSolver on the device: red-black SOR with the reference's node classes, residual, E = -grad(phi).
-//   k_sor_color   : one colour half-sweep of PotentialSolver::solveGS     ch4/v3/src/PotentialSolver.cpp:86-121
+//   k_sor_row / k_sor_slab : one colour half-sweep of PotentialSolver::solveGS     ch4/v3/src/PotentialSolver.cpp:86-121
 //   k_residual    : the convergence check (every 25 iterations)           :124-159
 //   k_compute_ef  : PotentialSolver::computeEF                             :354-408
 // The reference sweeps lexicographically (Gauss-Seidel); red-black ordering visits the same node
@@ -37,11 +37,19 @@ __device__ __forceinline__ size_t face_neighbor(const Grid& g, int cls, size_t u
     switch (cls) { case 1: return u + si; case 2: return u - si; case 3: return u + sj; case 4: return u - sj; case 5: return u + 1; default: return u - 1; }
 }
 
-// node classes precomputed once per solve (1 byte per node) so that the sweeps do no index arithmetic or branching on geometry
-__global__ void __launch_bounds__(256) k_node_classes(Grid g, int bc_mode, const int* __restrict__ object_id, unsigned char* __restrict__ cls) {
+// Colour-compact copies made once per solve.  In row (i,j) the nodes of colour c are k = (i+j+c)&1, +2, ...; node k is element
+// row*hk + (k>>1) of colour c's half (hk = ceil(nk/2)).  A half-sweep then reads the node class (1 byte: no index arithmetic or
+// geometry branches in the sweeps) and rho of its own colour with unit stride instead of every other value of whole sectors.
+__global__ void __launch_bounds__(256) k_node_classes(Grid g, int bc_mode, const int* __restrict__ object_id, const double* __restrict__ rho,
+                                                      unsigned char* __restrict__ cls, double* __restrict__ rho_split) {
+    const int hk = (g.nk + 1) >> 1;
+    const size_t half = (size_t)g.ni * g.nj * hk;
     for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < (size_t)g.nv; u += (size_t)gridDim.x * blockDim.x) {
         int k = (int)(u % g.nk); size_t row = u / g.nk; int j = (int)(row % g.nj), i = (int)(row / g.nj);
-        cls[u] = (unsigned char)node_class(g, bc_mode, object_id[u], i, j, k);
+        const int color = (i + j + k) & 1;                                      // k == (i+j+color)&1 mod 2
+        const size_t c = (size_t)color * half + row * hk + (k >> 1);
+        cls[c] = (unsigned char)node_class(g, bc_mode, object_id[u], i, j, k);
+        rho_split[c] = rho[u];
     }
 }
 // One colour half-sweep, one block per (i,j) row: no divisions, coalesced along k, class byte instead of geometry tests.
@@ -50,14 +58,16 @@ __global__ void __launch_bounds__(128) k_sor_row(Grid g, SorParams sp, int color
     const int j = blockIdx.x, i = blockIdx.y;
     const size_t si = (size_t)g.nj * g.nk, sj = g.nk;
     const size_t row = ((size_t)i * g.nj + j) * g.nk;
+    const int hk = (g.nk + 1) >> 1;
+    const size_t crow = (size_t)color * ((size_t)g.ni * g.nj * hk) + ((size_t)i * g.nj + j) * hk;     // this row in the colour-compact arrays
     for (int k = 2 * threadIdx.x + ((i + j + color) & 1); k < g.nk; k += 2 * blockDim.x) {
         const size_t u = row + k;
-        const int c = cls[u];
+        const int c = cls[crow + (k >> 1)];
         if (c == 0) continue;
         if (c < 7) { phi[u] = phi[face_neighbor(g, c, u)]; continue; }
         const double p = phi[u];
         const double ne = (sp.n0 != 0.0) ? sp.n0 * exp((p - sp.phi0) / sp.Te0) : 0.0;
-        const double nw = ((rho[u] - sp.qe * ne) * sp.inv_eps0 + (phi[u - si] + phi[u + si]) * sp.inv_d2x + (phi[u - sj] + phi[u + sj]) * sp.inv_d2y +
+        const double nw = ((rho[crow + (k >> 1)] - sp.qe * ne) * sp.inv_eps0 + (phi[u - si] + phi[u + si]) * sp.inv_d2x + (phi[u - sj] + phi[u + sj]) * sp.inv_d2y +
                            (phi[u - 1] + phi[u + 1]) * sp.inv_d2z) * sp.inv_twos;
         phi[u] = p + sp.w * (nw - p);
     }
@@ -102,9 +112,11 @@ __global__ void __launch_bounds__(128) k_sor_slab(Grid g, SorParams sp, int colo
     double* peer = to_left ? S.left_phi : S.right_phi;
     const size_t si = (size_t)g.nj * g.nk, sj = g.nk;
     const size_t row = ((size_t)i * g.nj + j) * g.nk;
+    const int hk = (g.nk + 1) >> 1;
+    const size_t crow = (size_t)color * ((size_t)g.ni * g.nj * hk) + ((size_t)i * g.nj + j) * hk;     // this row in the colour-compact arrays
     for (int k = 2 * threadIdx.x + ((i + j + color) & 1); k < g.nk; k += 2 * blockDim.x) {
         const size_t u = row + k;
-        const int c = cls[u];
+        const int c = cls[crow + (k >> 1)];
         if (c == 0) continue;
         double nv_;
         if (c < 7) nv_ = phi[face_neighbor(g, c, u)];
@@ -113,7 +125,7 @@ __global__ void __launch_bounds__(128) k_sor_slab(Grid g, SorParams sp, int colo
             const double ne = (sp.n0 != 0.0) ? sp.n0 * exp((p - sp.phi0) / sp.Te0) : 0.0;
             // the halo plane is written by the neighbour GPU: read it from L2 (ld.cg), never from a possibly stale L1 line
             const double lo_i = to_left ? __ldcg(phi + u - si) : phi[u - si], hi_i = to_right ? __ldcg(phi + u + si) : phi[u + si];
-            const double nw = ((rho[u] - sp.qe * ne) * sp.inv_eps0 + (lo_i + hi_i) * sp.inv_d2x + (phi[u - sj] + phi[u + sj]) * sp.inv_d2y +
+            const double nw = ((rho[crow + (k >> 1)] - sp.qe * ne) * sp.inv_eps0 + (lo_i + hi_i) * sp.inv_d2x + (phi[u - sj] + phi[u + sj]) * sp.inv_d2y +
                                (phi[u - 1] + phi[u + 1]) * sp.inv_d2z) * sp.inv_twos;
             nv_ = p + sp.w * (nw - p);
         }
@@ -181,28 +193,6 @@ __global__ void k_slab_gather_wait(const u64* __restrict__ mbox, int rank, int w
     for (int r = 0; r < world; r++) if (r != rank) spin_until(mbox + MB_GATHER + r, tag);
 }
 
-__global__ void __launch_bounds__(256) k_sor_color(Grid g, SorParams sp, int color, double* __restrict__ phi, const double* __restrict__ rho,
-                                                   const int* __restrict__ object_id) {
-    const int hk = (g.nk + 1) >> 1;
-    const size_t total = (size_t)g.ni * g.nj * hk;
-    const size_t si = (size_t)g.nj * g.nk, sj = g.nk;
-    for (size_t h = blockIdx.x * (size_t)blockDim.x + threadIdx.x; h < total; h += (size_t)gridDim.x * blockDim.x) {
-        int t = (int)(h % hk); size_t row = h / hk;
-        int j = (int)(row % g.nj), i = (int)(row / g.nj);
-        int k = 2 * t + ((i + j + color) & 1);
-        if (k >= g.nk) continue;
-        size_t u = row * g.nk + k;
-        int cls = node_class(g, sp.bc_mode, object_id[u], i, j, k);
-        if (cls == 0) continue;
-        if (cls < 7) { phi[u] = phi[face_neighbor(g, cls, u)]; continue; }
-        double p = phi[u];
-        double ne = (sp.n0 != 0.0) ? sp.n0 * exp((p - sp.phi0) / sp.Te0) : 0.0;
-        double nw = ((rho[u] - sp.qe * ne) * sp.inv_eps0 + (phi[u - si] + phi[u + si]) * sp.inv_d2x + (phi[u - sj] + phi[u + sj]) * sp.inv_d2y +
-                     (phi[u - 1] + phi[u + 1]) * sp.inv_d2z) * sp.inv_twos;
-        phi[u] = p + sp.w * (nw - p);
-    }
-}
-
 __global__ void __launch_bounds__(256) k_residual(Grid g, SorParams sp, const double* __restrict__ phi, const double* __restrict__ rho,
                                                   const int* __restrict__ object_id, double* __restrict__ partial, size_t u_begin, size_t u_end) {
     __shared__ double sm[256];
@@ -260,8 +250,13 @@ static const int kResidualBlocks = 1024;
 
 static int prepare_classes(picg_solver_s* s) {
     const Grid& g = s->w->g;
-    if (!s->cls) { cudaError_t e = cudaMalloc(&s->cls, (size_t)g.nv); if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(node classes)", __FILE__, __LINE__); }
-    LAUNCH(K_MISC, k_node_classes, std::min(div_up(g.nv, 256), g_sm_count * 8), 256, 0, g, s->bc_mode, s->w->object_id, s->cls); CHECK_LAUNCH();
+    const size_t half = (size_t)g.ni * g.nj * ((g.nk + 1) >> 1);
+    if (!s->cls) {
+        cudaError_t e = cudaMalloc(&s->cls, 2 * half);
+        if (e == cudaSuccess) e = cudaMalloc(&s->rho_split, 2 * half * 8);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(colour-compact classes / rho)", __FILE__, __LINE__);
+    }
+    LAUNCH(K_MISC, k_node_classes, std::min(div_up(g.nv, 256), g_sm_count * 8), 256, 0, g, s->bc_mode, s->w->object_id, s->w->rho, s->cls, s->rho_split); CHECK_LAUNCH();
     return PICG_OK;
 }
 static SlabArgs slab_args(picg_solver_s* s, unsigned seq_off) {
@@ -279,11 +274,11 @@ static int enqueue_iterations(picg_solver_s* s, const SorParams& p, unsigned n, 
     for (unsigned h = 0; h < 2 * n; h++) {
         const int color = h & 1;
         if (timed) {
-            if (slab) LAUNCH(K_SOR, k_sor_slab, grid, 128, 0, g, p, color, s->w->phi, s->w->rho, s->cls, slab_args(s, h + 1));
-            else LAUNCH(K_SOR, k_sor_row, grid, 128, 0, g, p, color, s->w->phi, s->w->rho, s->cls);
+            if (slab) LAUNCH(K_SOR, k_sor_slab, grid, 128, 0, g, p, color, s->w->phi, s->rho_split, s->cls, slab_args(s, h + 1));
+            else LAUNCH(K_SOR, k_sor_row, grid, 128, 0, g, p, color, s->w->phi, s->rho_split, s->cls);
         } else {
-            if (slab) k_sor_slab<<<grid, 128, 0, g_stream>>>(g, p, color, s->w->phi, s->w->rho, s->cls, slab_args(s, h + 1));
-            else k_sor_row<<<grid, 128, 0, g_stream>>>(g, p, color, s->w->phi, s->w->rho, s->cls);
+            if (slab) k_sor_slab<<<grid, 128, 0, g_stream>>>(g, p, color, s->w->phi, s->rho_split, s->cls, slab_args(s, h + 1));
+            else k_sor_row<<<grid, 128, 0, g_stream>>>(g, p, color, s->w->phi, s->rho_split, s->cls);
         }
         CHECK_LAUNCH();
     }
@@ -378,7 +373,7 @@ int picg_solver_destroy(picg_solver_t s) {
     drop_graphs(s);
     for (int r = 0; r < (int)s->peer_phi.size(); r++) if (r != s->slab_rank) { cudaIpcCloseMemHandle(s->peer_phi[r]); cudaIpcCloseMemHandle(s->peer_mbox[r]); }
     cudaFree(s->peer_phi_dev); cudaFree(s->peer_mbox_dev); cudaFree(s->mbox);
-    cudaFree(s->partial); cudaFree(s->cls); delete s; return PICG_OK;
+    cudaFree(s->partial); cudaFree(s->cls); cudaFree(s->rho_split); delete s; return PICG_OK;
 }
 
 // Slab decomposition over `world` ranks on one node.  (1) every rank exports 128 bytes (the CUDA IPC handles of its phi and of
@@ -390,6 +385,14 @@ int picg_solver_slab_export(picg_solver_t s, void* handle128) {
     cudaIpcMemHandle_t h;
     CUDA_TRY(cudaIpcGetMemHandle(&h, s->w->phi)); memcpy(handle128, &h, 64);
     CUDA_TRY(cudaIpcGetMemHandle(&h, s->mbox)); memcpy((char*)handle128 + 64, &h, 64);
+    return PICG_OK;
+}
+int picg_solver_slab_range(picg_solver_t s, size_t* node_begin, size_t* node_end) {
+    REQUIRE_ARG(s && node_begin && node_end, "picg_solver_slab_range: null argument");
+    const Grid& g = s->w->g;
+    const size_t plane = (size_t)g.nj * g.nk;
+    if (s->slab_world > 1) { *node_begin = s->slab_i0 * plane; *node_end = s->slab_i1 * plane; }
+    else { *node_begin = 0; *node_end = (size_t)g.nv; }
     return PICG_OK;
 }
 int picg_solver_slab_enable(picg_solver_t s, int rank, int world, const void* handles) {

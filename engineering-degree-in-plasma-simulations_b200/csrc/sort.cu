@@ -344,7 +344,7 @@ int species_exact_lists(picg_species_s* s) {
         LAUNCH(K_SORT_KEYS, k_iota_u32, mgrid, 256, 0, cnt, va); CHECK_LAUNCH();
         LAUNCH(K_SORT_KEYS, k_copy_u32, mgrid, 256, 0, cnt, m_cell, tmp); CHECK_LAUNCH();          // keep m_cell intact? (not needed later) -> sort a copy
         ka = tmp;
-        rc = radix_sort_pairs(cnt, mcap, bits, ka, va, kb, vb, counts, std::min(nblocks, div_up(std::max<size_t>((size_t)n_live_movers, 1), SORT_TILE))); if (rc) return rc;
+        rc = radix_sort_pairs(cnt, mcap, bits, ka, va, kb, vb, counts, std::min(std::min(nblocks, 128), div_up(std::max<size_t>((size_t)n_live_movers, 1), SORT_TILE))); if (rc) return rc;   // few blocks: the scan of the count table is a single block
         CUDA_TRY(cudaMemsetAsync(queue, 0, 4, g_stream));
         LAUNCH(K_CELL_START, k_cell_start_sparse, mgrid, 256, 0, cnt, ka, g.nc, s->in_start, queue); CHECK_LAUNCH();
         LAUNCH(K_CELL_START, k_cell_start_long, g_sm_count * 2, 256, 0, queue, s->in_start); CHECK_LAUNCH();
@@ -360,7 +360,7 @@ int species_exact_lists(picg_species_s* s) {
         int mgrid2 = std::max(1, std::min(div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), 256), g_sm_count * 4));
         LAUNCH(K_SORT_KEYS, k_iota_u32, mgrid2, 256, 0, cnt, va); CHECK_LAUNCH();
         int hbits = 1; while ((1ull << hbits) < (u64)g.nc + 1) hbits++;
-        rc = radix_sort_pairs(cnt, mcap, hbits, ka, va, kb, vb, counts, std::min(nblocks, div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), SORT_TILE))); if (rc) return rc;
+        rc = radix_sort_pairs(cnt, mcap, hbits, ka, va, kb, vb, counts, std::min(std::min(nblocks, 128), div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), SORT_TILE))); if (rc) return rc;
         CUDA_TRY(cudaMemsetAsync(queue, 0, 4, g_stream));
         LAUNCH(K_CELL_START, k_cell_start_sparse, mgrid2, 256, 0, cnt, ka, g.nc, s->out_start, queue); CHECK_LAUNCH();
         LAUNCH(K_CELL_START, k_cell_start_long, g_sm_count * 2, 256, 0, queue, s->out_start); CHECK_LAUNCH();

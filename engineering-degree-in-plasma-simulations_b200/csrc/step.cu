@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(128) k_heavy_impacts(Grid g, StepArgs A, Heavy
 }
 
 namespace picg {
-int launch_finalize(picg_species_s* s);
+int launch_finalize(picg_species_s* s, size_t u_begin = 0, size_t u_end = (size_t)-1);
 int calibrate_scale(picg_species_s* s, bool count_cells);
 int check_scale_after(picg_species_s* s);
 

@@ -9,8 +9,8 @@ using namespace picg;
 // ---------------------------------------------------------------- kernels
 // World::computeChargeDensity (World.cpp:193-200): rho = 0; rho += q_s * den_s, species in call order.
 struct ChargeArgs { int n; const double* den[8]; double q[8]; };
-__global__ void __launch_bounds__(256) k_charge_density(int nv, ChargeArgs a, double* __restrict__ rho) {
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < nv; u += gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) k_charge_density(int u_begin, int u_end, ChargeArgs a, double* __restrict__ rho) {
+    for (int u = u_begin + blockIdx.x * blockDim.x + threadIdx.x; u < u_end; u += gridDim.x * blockDim.x) {
         double r = 0.0;
         for (int s = 0; s < a.n; s++) r = __dadd_rn(r, __dmul_rn(a.q[s], a.den[s][u]));
         rho[u] = r;
@@ -221,9 +221,7 @@ int picg_world_upload(picg_world_t w, int field, const double* host) {
     return PICG_OK;
 }
 
-int picg_world_charge_density(picg_world_t w, const picg_species_t* species, int n) {
-    REQUIRE_DEVICE();
-    REQUIRE_ARG(w && (species || n == 0), "picg_world_charge_density: null argument");
+static int charge_density_range(picg_world_t w, const picg_species_t* species, int n, size_t u_begin, size_t u_end) {
     ChargeArgs a; a.n = 0;
     for (int s = 0; s < n; s++) {
         REQUIRE_ARG(species[s] && species[s]->w == w, "picg_world_charge_density: species does not belong to this world");
@@ -231,10 +229,21 @@ int picg_world_charge_density(picg_world_t w, const picg_species_t* species, int
         REQUIRE_ARG(a.n < 8, "picg_world_charge_density: more than 8 charged species");
         a.den[a.n] = species[s]->den; a.q[a.n] = species[s]->charge; a.n++;
     }
-    int nv = w->g.nv;
-    int grid = std::min(div_up(nv, 256), g_sm_count * 8);
-    LAUNCH(K_CHARGE_DENSITY, k_charge_density, grid, 256, 0, nv, a, w->rho); CHECK_LAUNCH();
+    u_end = std::min(u_end, (size_t)w->g.nv);
+    if (u_begin >= u_end) return PICG_OK;
+    int grid = std::min(div_up(u_end - u_begin, 256), g_sm_count * 8);
+    LAUNCH(K_CHARGE_DENSITY, k_charge_density, grid, 256, 0, (int)u_begin, (int)u_end, a, w->rho); CHECK_LAUNCH();
     return PICG_OK;
+}
+int picg_world_charge_density(picg_world_t w, const picg_species_t* species, int n) {
+    REQUIRE_DEVICE();
+    REQUIRE_ARG(w && (species || n == 0), "picg_world_charge_density: null argument");
+    return charge_density_range(w, species, n, 0, (size_t)-1);
+}
+int picg_world_charge_density_range(picg_world_t w, const picg_species_t* species, int n, size_t node_begin, size_t node_end) {
+    REQUIRE_DEVICE();
+    REQUIRE_ARG(w && (species || n == 0) && node_begin <= node_end, "picg_world_charge_density_range: bad argument");
+    return charge_density_range(w, species, n, node_begin, node_end);
 }
 
 int picg_world_potential_energy(picg_world_t w, double* pe) {

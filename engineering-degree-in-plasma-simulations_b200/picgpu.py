@@ -185,9 +185,12 @@ class World:
     node_vol = property(lambda self: self.download(F_NODE_VOL))
     object_id = property(lambda self: self.download(F_OBJECT_ID))
 
-    def computeChargeDensity(self, species):
+    def computeChargeDensity(self, species, node_range=None):
         arr = (C.c_void_p * len(species))(*[s.h for s in species])
-        _chk(lib().picg_world_charge_density(self.h, arr, len(species)))
+        if node_range is None:
+            _chk(lib().picg_world_charge_density(self.h, arr, len(species)))
+        else:                                               # multi-GPU: only the planes this rank solves on
+            _chk(lib().picg_world_charge_density_range(self.h, arr, len(species), C.c_size_t(node_range[0]), C.c_size_t(node_range[1])))
 
     def getPE(self):
         pe = C.c_double(0)
@@ -269,8 +272,11 @@ class Species:
     def depositPartial(self):
         _chk(lib().picg_species_deposit_density_partial(self.h))
 
-    def finalizeDensity(self):
-        _chk(lib().picg_species_finalize_density(self.h))
+    def finalizeDensity(self, node_range=None):
+        if node_range is None:
+            _chk(lib().picg_species_finalize_density(self.h))
+        else:
+            _chk(lib().picg_species_finalize_density_range(self.h, C.c_size_t(node_range[0]), C.c_size_t(node_range[1])))
 
     def densityScale(self):
         s = C.c_int(0)
@@ -370,6 +376,12 @@ class PotentialSolver:
 
     def computeEF(self):
         _chk(lib().picg_solver_compute_ef(self.h))
+
+    def slabRange(self):
+        """Node range [begin, end) of the planes this rank solves on (the whole grid when slabs are off)."""
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        _chk(lib().picg_solver_slab_range(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def enableSlabs(self, rank, world, all_gather_bytes):
         """Multi-GPU slab decomposition of the solve.  all_gather_bytes(b: bytes) -> list of `world` bytes objects (rank order)."""

@@ -94,6 +94,8 @@ PICG_API int picg_world_download(picg_world_t w, int field, double* host);
 PICG_API int picg_world_upload(picg_world_t w, int field, const double* host);
 /* World::computeChargeDensity  World.cpp:193-200 : rho = sum_s charge_s * den_s over charged species */
 PICG_API int picg_world_charge_density(picg_world_t w, const picg_species_t* species, int n);
+/* the same on the nodes [node_begin, node_end) only (multi-GPU: the planes this rank solves on) */
+PICG_API int picg_world_charge_density_range(picg_world_t w, const picg_species_t* species, int n, size_t node_begin, size_t node_end);
 /* World::getPE  World.cpp:108-118 */
 PICG_API int picg_world_potential_energy(picg_world_t w, double* pe);
 /* device pointers for zero-copy interop (torch.distributed all-reduce of the grids) */
@@ -165,6 +167,7 @@ PICG_API int picg_species_download_field(picg_species_t s, int field, void* host
 PICG_API int picg_species_device_ptr(picg_species_t s, int field, void** dptr, size_t* bytes);
 /* multi-GPU: after all-reducing DEN_FIXED across ranks, turn it into den (divide by 2^S and node_vol) */
 PICG_API int picg_species_finalize_density(picg_species_t s);
+PICG_API int picg_species_finalize_density_range(picg_species_t s, size_t node_begin, size_t node_end);
 /* multi-GPU: deposit into the fixed-point accumulator only (no finalize) */
 PICG_API int picg_species_deposit_density_partial(picg_species_t s);
 
@@ -190,6 +193,9 @@ PICG_API int picg_solver_compute_ef(picg_solver_t s);
  * world x 128 bytes to enable (a collective: every rank must call both).  Every rank must then make the same solver calls. */
 PICG_API int picg_solver_slab_export(picg_solver_t s, void* handle128);
 PICG_API int picg_solver_slab_enable(picg_solver_t s, int rank, int world, const void* handles);
+/* the node range [begin, end) of this rank's planes (the whole grid when slabs are off): the solve reads rho only there, so a
+ * multi-GPU loop may reduce-scatter the density accumulators onto the slabs and finalize / sum charges on the owned range only */
+PICG_API int picg_solver_slab_range(picg_solver_t s, size_t* node_begin, size_t* node_end);
 
 /* -------------------------------------------------------- MC_MEX_Ionization */
 /* MC_MEX_Ionization(neutrals, ions, electrons, world, table)  Interactions.cpp:476-539; the cross-section table

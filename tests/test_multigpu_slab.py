@@ -70,6 +70,59 @@ def _worker(rank, world, port, out_dir, shape):
     dist.destroy_process_group()
 
 
+def _density_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    pg = importlib.import_module(PKG + ".picgpu"); mg = importlib.import_module(PKG + ".multigpu")
+    pg.init(rank)
+    ni, nj, nk = 4 * world, 9, 13                                      # planes divisible by the ranks: equal reduce-scatter chunks
+    x0, xm, rects = util.discharge_geometry(ni, nj, nk)
+    w = util.build_world(pg.World, ni, nj, nk, x0, xm, rects, dt=1e-10)
+    parts = util.random_particles(60001, x0, xm, seed=19, mpw=(1.0, 5e3))          # identical on every rank
+    lo = sum(mg.split_count(len(parts), r, world) for r in range(rank))
+    mine = parts[lo:lo + mg.split_count(len(parts), rank, world)]
+    ion_all = pg.Species("O+", 16 * util.AMU, util.QE, w, 100.0); ele_all = pg.Species("e-", util.ME, -util.QE, w, 100.0)
+    ion = pg.Species("O+", 16 * util.AMU, util.QE, w, 100.0); ele = pg.Species("e-", util.ME, -util.QE, w, 100.0)
+    S = 30
+    for sp, p in ((ion_all, parts), (ele_all, parts[::-1]), (ion, mine), (ele, mine[::-1])):
+        sp.setParticles(p); sp.sort(); sp.setDensityScale(S)
+    ion_all.computeNumberDensity(); ele_all.computeNumberDensity()
+    w.computeChargeDensity([ion_all, ele_all])
+    den_ref, rho_ref = ion_all.den.copy(), w.rho.copy()
+    nv = ni * nj * nk
+    rng_ = (rank * (nv // world), (rank + 1) * (nv // world))
+    for sp in (ion, ele):
+        sp.depositPartial()
+        v = mg.fixed_view(torch, sp, pg.SF_DEN_FIXED)
+        with torch.cuda.stream(torch.cuda.ExternalStream(pg.stream_ptr(), device=rank)):
+            dist.reduce_scatter_tensor(list(v.chunk(world))[rank], v)             # in place: the r-th chunk of the own input
+        sp.finalizeDensity(rng_)
+    w.upload(pg.F_RHO, np.zeros((ni, nj, nk)))
+    w.computeChargeDensity([ion, ele], rng_)
+    ok = np.array_equal(ion.den.reshape(-1)[rng_[0]:rng_[1]], den_ref.reshape(-1)[rng_[0]:rng_[1]])
+    ok &= np.array_equal(w.rho.reshape(-1)[rng_[0]:rng_[1]], rho_ref.reshape(-1)[rng_[0]:rng_[1]])
+    ok &= not w.rho.reshape(-1)[:rng_[0]].any() and not w.rho.reshape(-1)[rng_[1]:].any()      # nothing written outside the owned planes
+    np.save(os.path.join(out_dir, f"dok_{rank}.npy"), np.array([int(ok)]))
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_reduce_scatter_onto_slabs_matches_single_gpu_density(tmp_path):
+    """Particles split by index over the ranks, int64 accumulators reduce-scattered in place onto the Poisson slabs, density and
+    charge density finalised on the owned planes only: bit-identical there to the single-GPU deposit of all particles."""
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs on the node")
+    mp.spawn(_density_worker, args=(world, 29800 + (os.getpid() % 2000), str(tmp_path)), nprocs=world, join=True)
+    assert all(np.load(tmp_path / f"dok_{r}.npy")[0] == 1 for r in range(world))
+
+
 @pytest.mark.parametrize("shape", [(12, 9, 13), (33, 16, 20)])
 def test_slab_solve_is_bit_identical_to_the_replicated_solve(tmp_path, shape):
     import torch
