@@ -62,7 +62,7 @@ struct picg_species_s {
     picg_world_s* w;
     double mass, charge, mpw0;
     uint32_t id = 0;                   // index within its world; decorrelates the species' RNG streams
-    uint32_t n_load_calls = 0, n_heavy_calls = 0;   // call counters that address the Philox streams (reproducible per species)
+    uint32_t n_load_calls = 0, n_heavy_calls = 0, n_merge_calls = 0;   // call counters that address the Philox streams (reproducible per species)
     size_t cap = 0;                   // allocated particles per array
     size_t n_host = 0;                 // last count known to the host
     bool n_host_valid = true;

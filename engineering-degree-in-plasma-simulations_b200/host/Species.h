@@ -65,7 +65,7 @@ public:
     const std::vector<Particle>& getConstPartRef();
     const Particle& getConstPartRef(int i);
     void setParticles(const std::vector<Particle>& p);  // uploads a host particle set (raw store, no addParticle filtering)
-    void merge();                                        // not on the device yet
+    void merge();                                        // Species.cpp:1037-1145 -> picg_species_merge
     void sortByCell();
 };
 #endif

@@ -187,9 +187,14 @@ void Species::computeGasProperties() { check(picg_species_compute_gas_properties
 void Species::clearSamples() { check(picg_species_clear_samples(dev())); }
 void Species::computeMacroParticlesCount() { check(picg_species_count_per_cell(dev())); macro_part_count.invalidate(); }
 void Species::sortByCell() { check(picg_species_sort(dev())); sorted = true; }
-void Species::merge() {
-    static bool warned = false;
-    if (!warned) { std::cerr << "Species::merge: particle merging is not on the device path yet (SURVEY.md 8f row 2); call ignored\n"; warned = true; }
+void Species::merge() {                                  // Species.cpp:1037-1145; same console report as the reference (:1038-1040, :1142-1143)
+    std::stringstream out;
+    out << "Merging " << name << "\nBefore merge: particles size: " << getNumParticles() << ", energy: " << getKE() << ", momentum: " << getMomentum() << "\n";
+    uint64_t n0 = 0, n1 = 0, st[4] = {0, 0, 0, 0};
+    check(picg_species_merge(dev(), &n0, &n1, st));
+    if (n1 != n0) sorted = false;
+    out << name << " after merge: particles size: " << n1 << ", energy: " << getKE() << ", momentum: " << getMomentum() << "\n";
+    std::cout << out.str();
 }
 const std::vector<Particle>& Species::getConstPartRef() {
     size_t n = getNumParticles(), got = 0;

@@ -269,6 +269,13 @@ class Species:
     def computeNumberDensity(self):
         _chk(lib().picg_species_deposit_density(self.h))
 
+    def merge(self):
+        """Species::merge (Species.cpp:1037-1145).  Returns (n_before, n_after, (merged bins, removed, dropped, cells too large))."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        st = (C.c_uint64 * 4)()
+        _chk(lib().picg_species_merge(self.h, C.byref(a), C.byref(b), st))
+        return a.value, b.value, tuple(int(v) for v in st)
+
     def depositPartial(self):
         _chk(lib().picg_species_deposit_density_partial(self.h))
 

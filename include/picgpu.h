@@ -154,6 +154,11 @@ PICG_API int picg_set_mover_fraction(double f);
  * appended tail is scanned), full scans of the store, and fall-backs to a full radix sort. */
 PICG_API int picg_mover_stats(uint64_t* from_deposit, uint64_t* full_scans, uint64_t* resorts);
 PICG_API int picg_species_sort(picg_species_t s);
+/* Species::merge()  Species.cpp:1037-1145 (+ sortVelocitiesInCell :981-1035): in every cell with >= 10 particles, the particles of a
+ * 15^3 velocity bin that holds more than two are replaced by two (weight, momentum and per-axis energy of the bin kept).
+ * stats (optional, 4 words): merged bins, particles removed, new particles dropped by addParticle's filter, cells left unmerged
+ * because they hold more than 1024 particles. */
+PICG_API int picg_species_merge(picg_species_t s, uint64_t* n_before, uint64_t* n_after, uint64_t stats[4]);
 /* diagnostics: getMicroCount, getMomentum, getKE  Species.cpp:726-755 */
 PICG_API int picg_species_diagnostics(picg_species_t s, double* micro_count, double momentum[3], double* ke);
 
