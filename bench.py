@@ -12,7 +12,9 @@ off and the Poisson solve live (as in ch2/ch3/ch4-v1): MC ionisation (cell sort 
 included), push of every species, number-density deposit + per-cell macro-particle count, charge density,
 red-black SOR solve (warm start, reference tolerance) and E = -grad(phi).
 Particles are split evenly across the N GPUs (strong scaling); every GPU deposits onto a full-grid fixed-point
-accumulator, the accumulators are summed with an NCCL all-reduce, Poisson is solved redundantly.
+accumulator; the accumulators are reduce-scattered (NCCL) onto the slabs of the Poisson solve, whose halo planes, residual
+sum and final all-gather go through NVLink peer memory inside the sweep kernels (--poisson replicated / --allreduce_density
+select the simpler variants).
 """
 import argparse
 import importlib
