@@ -96,7 +96,7 @@ __device__ __forceinline__ void atomic_max_pos_double(double* addr, double v) { 
 
 // stats: [0] candidates [1] collisions [2] ionisations [3] skipped (electron heavier than neutral)
 //        [5] dropped because a product store was full (collision skipped untouched)
-__global__ void __launch_bounds__(128) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, CellLists Ln,
+__global__ void __launch_bounds__(128, 6) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, CellLists Ln,
                                              CellLists Le, double* __restrict__ wsv, u64* __restrict__ stats, double dt,
                                              uint64_t seed, uint32_t stream, uint32_t call) {
     const double W_max = wsv[0];

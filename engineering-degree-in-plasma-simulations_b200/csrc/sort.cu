@@ -55,31 +55,36 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_upsweep(const u64* __rest
     }
 }
 
-// single-block exclusive scan over m = 256*blocks entries
-__global__ void __launch_bounds__(1024) k_sort_scan(unsigned* __restrict__ counts, int m) {
+// Exclusive scan of the [256][blocks] count table (digit-major), blocks <= 1024.  One thread block per digit scans its row and
+// publishes the row total; the second kernel adds the exclusive prefix of the totals of the lower digits.
+__global__ void __launch_bounds__(1024) k_sort_scan_rows(unsigned* __restrict__ counts, int nblocks, unsigned* __restrict__ totals) {
     __shared__ unsigned warp_tot[32];
-    __shared__ unsigned carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < m; base += 1024) {
-        int t = base + threadIdx.x;
-        unsigned v = t < m ? counts[t] : 0, x = v;
-        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) warp_tot[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned wv = warp_tot[lane], wx = wv;
-            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, wx, o); if (lane >= o) wx += y; }
-            warp_tot[lane] = wx - wv;
-        }
-        __syncthreads();
-        unsigned excl = carry + warp_tot[warp] + x - v;
-        if (t < m) counts[t] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
+    unsigned* row = counts + (size_t)blockIdx.x * nblocks;
+    const unsigned v = (int)threadIdx.x < nblocks ? row[threadIdx.x] : 0;
+    unsigned x = v;
+    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned wv = warp_tot[lane], wx = wv;
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, wx, o); if (lane >= o) wx += y; }
+        warp_tot[lane] = wx - wv;
+        if (lane == 31) totals[blockIdx.x] = wx;
     }
+    __syncthreads();
+    if ((int)threadIdx.x < nblocks) row[threadIdx.x] = warp_tot[warp] + x - v;
+}
+__global__ void __launch_bounds__(1024) k_sort_scan_add(unsigned* __restrict__ counts, int nblocks, const unsigned* __restrict__ totals) {
+    __shared__ unsigned base;
+    if (threadIdx.x < 32) {                                   // sum of the totals of the digits below this one
+        unsigned s = 0;
+        for (int d = threadIdx.x; d < (int)blockIdx.x; d += 32) s += totals[d];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) base = s;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nblocks) counts[(size_t)blockIdx.x * nblocks + threadIdx.x] += base;
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_downsweep(const u64* __restrict__ n_ptr, const unsigned* __restrict__ keys_in,
@@ -237,7 +242,8 @@ static int radix_sort_pairs(const u64* n_ptr, size_t n_upper, int key_bits, unsi
     for (int pass = 0; pass < passes; pass++) {
         int shift = pass * 8;
         LAUNCH(K_SORT_HIST, k_sort_upsweep, nblocks, SORT_THREADS, 0, n_ptr, keysA, shift, counts); CHECK_LAUNCH();
-        LAUNCH(K_SORT_SCAN, k_sort_scan, 1, 1024, 0, counts, 256 * nblocks); CHECK_LAUNCH();
+        LAUNCH(K_SORT_SCAN, k_sort_scan_rows, 256, 1024, 0, counts, nblocks, counts + (size_t)256 * nblocks); CHECK_LAUNCH();
+        LAUNCH(K_SORT_SCAN, k_sort_scan_add, 256, 1024, 0, counts, nblocks, counts + (size_t)256 * nblocks); CHECK_LAUNCH();
         LAUNCH(K_SORT_SCATTER, k_sort_downsweep, nblocks, SORT_THREADS, 0, n_ptr, keysA, valsA, keysB, valsB, shift, counts); CHECK_LAUNCH();
         std::swap(keysA, keysB); std::swap(valsA, valsB);
     }
@@ -261,9 +267,9 @@ int sort_species(picg_species_s* s) {
     s->n_upper = s->n_host;
     size_t cap = std::max<size_t>(s->n_upper, 1);
     if (cap >= 0xffffffffull) return set_error(PICG_ERR_ARG, "picg_species_sort: more than 2^32-1 particles per GPU are not supported");
-    int nblocks = std::max(1, std::min(div_up(cap, SORT_TILE), g_sm_count * 4));
+    int nblocks = std::max(1, std::min(std::min(div_up(cap, SORT_TILE), g_sm_count * 4), 1024));
     size_t capa = (cap + 63) & ~(size_t)63;
-    size_t bytes = capa * 16 + (size_t)256 * nblocks * 4 + 256;
+    size_t bytes = capa * 16 + (size_t)256 * nblocks * 4 + 256 * 4 + 256;
     int rc = ensure_scratch(s->w, bytes); if (rc) return rc;
     rc = ensure_u32(s->home, s->home_cap, s->cap); if (rc) return rc;
     rc = ensure_u32(s->in_start, s->lists_cap, (size_t)g.nc + 1); if (rc) return rc;
@@ -313,9 +319,9 @@ int species_exact_lists(picg_species_s* s) {
     // mover triples (slot / current cell / home cell) live in the species (a deposit pass may have listed them already);
     // radix ping-pong buffers in the scratch arena
     size_t mcapa = (mcap_alloc + 63) & ~(size_t)63;
-    int nblocks = std::max(1, std::min(div_up(mcap, SORT_TILE), g_sm_count * 4));
+    int nblocks = std::max(1, std::min(std::min(div_up(mcap, SORT_TILE), g_sm_count * 4), 1024));
     const size_t queue_words = 4 + 3 * ((size_t)g.nc / 32 + 64);                 // long-gap queue of k_cell_start_sparse
-    size_t bytes = mcapa * 4 * 4 + (size_t)256 * nblocks * 4 + 256 + queue_words * 4;
+    size_t bytes = mcapa * 4 * 4 + (size_t)256 * nblocks * 4 + 256 * 4 + 256 + queue_words * 4;
     rc = ensure_scratch(s->w, bytes); if (rc) return rc;
     rc = ensure_u32(s->mv_in, s->mv_cap, mcapa * 2); if (rc) return rc;     // [0,mcapa): slots ordered by current cell, [mcapa, 2 mcapa): slots ordered by home cell
     s->mv_stride = mcapa;
@@ -323,7 +329,7 @@ int species_exact_lists(picg_species_s* s) {
     unsigned* m_slot = s->mv_trip; unsigned* m_cell = m_slot + s->mv_trip_cap; unsigned* m_home = m_cell + s->mv_trip_cap;
     unsigned* kB = (unsigned*)s->w->scratch; unsigned* vA = kB + mcapa; unsigned* vB = vA + mcapa; unsigned* tmp = vB + mcapa;
     unsigned* counts = tmp + mcapa;
-    unsigned* queue = counts + (size_t)256 * nblocks + 64;
+    unsigned* queue = counts + (size_t)256 * nblocks + 256 + 64;
     u64* cnt = &s->ctr->n_movers;                                            // device-side mover count
     const int tail_only = s->movers_fresh ? 1 : 0;                           // the last deposit pass listed the partition's movers: only the appended tail is left
     if (!tail_only) CUDA_TRY(cudaMemsetAsync(cnt, 0, 8, g_stream));
@@ -344,7 +350,7 @@ int species_exact_lists(picg_species_s* s) {
         LAUNCH(K_SORT_KEYS, k_iota_u32, mgrid, 256, 0, cnt, va); CHECK_LAUNCH();
         LAUNCH(K_SORT_KEYS, k_copy_u32, mgrid, 256, 0, cnt, m_cell, tmp); CHECK_LAUNCH();          // keep m_cell intact? (not needed later) -> sort a copy
         ka = tmp;
-        rc = radix_sort_pairs(cnt, mcap, bits, ka, va, kb, vb, counts, std::min(std::min(nblocks, 128), div_up(std::max<size_t>((size_t)n_live_movers, 1), SORT_TILE))); if (rc) return rc;   // few blocks: the scan of the count table is a single block
+        rc = radix_sort_pairs(cnt, mcap, bits, ka, va, kb, vb, counts, std::min(nblocks, div_up(std::max<size_t>((size_t)n_live_movers, 1), SORT_TILE))); if (rc) return rc;
         CUDA_TRY(cudaMemsetAsync(queue, 0, 4, g_stream));
         LAUNCH(K_CELL_START, k_cell_start_sparse, mgrid, 256, 0, cnt, ka, g.nc, s->in_start, queue); CHECK_LAUNCH();
         LAUNCH(K_CELL_START, k_cell_start_long, g_sm_count * 2, 256, 0, queue, s->in_start); CHECK_LAUNCH();
@@ -360,7 +366,7 @@ int species_exact_lists(picg_species_s* s) {
         int mgrid2 = std::max(1, std::min(div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), 256), g_sm_count * 4));
         LAUNCH(K_SORT_KEYS, k_iota_u32, mgrid2, 256, 0, cnt, va); CHECK_LAUNCH();
         int hbits = 1; while ((1ull << hbits) < (u64)g.nc + 1) hbits++;
-        rc = radix_sort_pairs(cnt, mcap, hbits, ka, va, kb, vb, counts, std::min(std::min(nblocks, 128), div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), SORT_TILE))); if (rc) return rc;
+        rc = radix_sort_pairs(cnt, mcap, hbits, ka, va, kb, vb, counts, std::min(nblocks, div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), SORT_TILE))); if (rc) return rc;
         CUDA_TRY(cudaMemsetAsync(queue, 0, 4, g_stream));
         LAUNCH(K_CELL_START, k_cell_start_sparse, mgrid2, 256, 0, cnt, ka, g.nc, s->out_start, queue); CHECK_LAUNCH();
         LAUNCH(K_CELL_START, k_cell_start_long, g_sm_count * 2, 256, 0, queue, s->out_start); CHECK_LAUNCH();
