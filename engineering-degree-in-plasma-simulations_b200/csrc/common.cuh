@@ -123,6 +123,13 @@ struct picg_mcc_s {
     size_t last_appends[3] = {0, 0, 0};   // neutrals, electrons, ions appended by the previous apply (capacity estimate)
 };
 
+struct picg_dsmc_s {
+    picg_species_s *sp1, *sp2; picg_world_s* w;      // sp2 == sp1: collisions within one species
+    double* svm = nullptr;             // device: [0] sigma_v_rel_max in force, [1] largest value sampled by the current call
+    u64* stats = nullptr;              // device: candidates, collisions
+    u64 step = 0;
+};
+
 struct picg_source_s {
     picg_species_s* sp; picg_world_s* w;
     double v_drift, den, T; int face;
@@ -153,7 +160,7 @@ enum KernelId {
     K_PUSH_ELECTRONS = 0, K_PUSH_DEPOSIT, K_PUSH_REFLECT, K_PUSH_HEAVY, K_COMPACT, K_DEPOSIT, K_FINALIZE_DEN,
     K_CHARGE_DENSITY, K_SOR, K_RESIDUAL, K_COMPUTE_EF, K_SORT_KEYS, K_SORT_HIST, K_SORT_SCAN, K_SORT_SCATTER,
     K_SORT_PERMUTE, K_CELL_START, K_MCC, K_SOURCE, K_ADD_PARTICLES, K_MOMENTS, K_COUNT_CELLS, K_TRANSPOSE,
-    K_DIAG, K_MISC, K_PUSH_HEAVY_DEPOSIT, K_HEAVY_IMPACTS, K_NUM_KERNELS
+    K_DIAG, K_MISC, K_PUSH_HEAVY_DEPOSIT, K_HEAVY_IMPACTS, K_DSMC, K_NUM_KERNELS
 };
 
 #define CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return picg::cuda_fail(_e, #expr, __FILE__, __LINE__); } while (0)

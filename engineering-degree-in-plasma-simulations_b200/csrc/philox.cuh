@@ -9,7 +9,7 @@
 #pragma once
 #include <stdint.h>
 
-enum RngPurpose { RNG_LOADER = 1, RNG_SOURCE = 2, RNG_HEAVY = 3, RNG_MCC = 4, RNG_MERGE = 5 };
+enum RngPurpose { RNG_LOADER = 1, RNG_SOURCE = 2, RNG_HEAVY = 3, RNG_MCC = 4, RNG_MERGE = 5, RNG_DSMC = 6 };
 
 #if defined(__CUDACC__)
 #define PHILOX_HD __host__ __device__ __forceinline__

@@ -1,5 +1,6 @@
-// Facade of ch4/v3/src/Interactions.h: the Interaction interface and MC_MEX_Ionization, the one interaction the
-// v3 main loop instantiates (main.cpp:122).  apply(dt) runs the per-cell Monte-Carlo kernel (csrc/mcc.cu).
+// Facade of ch4/v3/src/Interactions.h: the Interaction interface, MC_MEX_Ionization (the one interaction the v3 main
+// loop instantiates, main.cpp:122; per-cell Monte-Carlo kernel csrc/mcc.cu) and DSMC_MEX (the neutral-neutral NTC
+// collisions of the ch4/v1 and ch4/v2-SPHERE mains, ch4/v2/main.cpp:266; csrc/dsmc.cu).
 #ifndef INTERACTIONS_H
 #define INTERACTIONS_H
 #include <memory>
@@ -12,6 +13,20 @@ class Interaction {
 public:
     virtual void apply(type_calc dt) noexcept = 0;
     virtual ~Interaction() noexcept = default;
+};
+
+class DSMC_MEX : public Interaction {
+protected:
+    Species &species1, &species2;
+    World& world;
+    std::shared_ptr<picg_dsmc_s> handle;
+    picg_dsmc_stats last{};
+
+public:
+    DSMC_MEX(Species& species, World& world) noexcept;                     // collisions within one species (Interactions.cpp:143-157)
+    DSMC_MEX(Species& species1, Species& species2, World& world);          // throws std::invalid_argument when the mpw0 differ (:158-176)
+    void apply(type_calc dt) noexcept override;
+    const picg_dsmc_stats& stats() const { return last; }
 };
 
 class MC_MEX_Ionization : public Interaction {

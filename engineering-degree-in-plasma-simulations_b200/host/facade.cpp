@@ -271,6 +271,22 @@ void MC_MEX_Ionization::apply(type_calc dt) noexcept {
     if (last.collisions) { ions.setSorted(false); electrons.setSorted(false); neutrals.setSorted(false); }       // Interactions.cpp:751-754
 }
 
+// ------------------------------------------------------------------ DSMC_MEX
+DSMC_MEX::DSMC_MEX(Species& sp, World& w) noexcept : species1(sp), species2(sp), world(w) {
+    picg_dsmc_t h = nullptr;
+    if (picg_dsmc_create(sp.dev(), nullptr, w.dev(), &h) != PICG_OK) { std::cerr << "DSMC_MEX: " << picg_last_error() << std::endl; return; }
+    handle = std::shared_ptr<picg_dsmc_s>(h, [](picg_dsmc_s* p) { picg_dsmc_destroy(p); });
+}
+DSMC_MEX::DSMC_MEX(Species& s1, Species& s2, World& w) : species1(s1), species2(s2), world(w) {
+    picg_dsmc_t h = nullptr;
+    check(picg_dsmc_create(s1.dev(), s2.dev(), w.dev(), &h));                                                  // Interactions.cpp:160-162
+    handle = std::shared_ptr<picg_dsmc_s>(h, [](picg_dsmc_s* p) { picg_dsmc_destroy(p); });
+}
+void DSMC_MEX::apply(type_calc dt) noexcept {
+    if (!handle) return;
+    if (picg_dsmc_apply(handle.get(), dt, &last) != PICG_OK) std::cerr << "DSMC_MEX::apply: " << picg_last_error() << std::endl;
+}
+
 // ------------------------------------------------------------------ Output (minimal)
 namespace Output {
 static std::ofstream f_diag;

@@ -438,6 +438,41 @@ class MC_MEX_Ionization:
         return sc, si
 
 
+class DsmcStats(C.Structure):
+    _fields_ = [("candidates", C.c_uint64), ("collisions", C.c_uint64), ("sigma_v_max", C.c_double)]
+
+
+class DSMC_MEX:
+    """DSMC_MEX (ch4/v3/src/Interactions.h:42-66): DSMC_MEX(species, world) or DSMC_MEX(species1, species2, world)."""
+
+    def __init__(self, species1, species2_or_world, world=None):
+        if world is None:
+            species2, world = None, species2_or_world
+        else:
+            species2 = species2_or_world
+        self.h = C.c_void_p()
+        _chk(lib().picg_dsmc_create(species1.h, species2.h if species2 is not None else None, world.h, C.byref(self.h)))
+        self.stats = DsmcStats()
+
+    def close(self):
+        if self.h:
+            lib().picg_dsmc_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def apply(self, dt):
+        _chk(lib().picg_dsmc_apply(self.h, C.c_double(dt), C.byref(self.stats)))
+        return self.stats
+
+    def setSigmaVMax(self, v):
+        _chk(lib().picg_dsmc_set_sigma_v_max(self.h, C.c_double(v)))
+
+    def sigma(self, v_rel):
+        v = np.ascontiguousarray(v_rel, dtype=np.float64)
+        out = np.empty_like(v)
+        _chk(lib().picg_dsmc_sigma(self.h, int(v.size), _dp(v), _dp(out)))
+        return out
+
+
 _FACES = {"x-": 0, "-x": 0, "x+": 1, "+x": 1, "y-": 2, "-y": 2, "y+": 3, "+y": 3, "z-": 4, "-z": 4, "z+": 5, "+z": 5}
 
 

@@ -49,6 +49,7 @@ typedef struct picg_world_s*   picg_world_t;
 typedef struct picg_species_s* picg_species_t;
 typedef struct picg_solver_s*  picg_solver_t;
 typedef struct picg_mcc_s*     picg_mcc_t;
+typedef struct picg_dsmc_s*    picg_dsmc_t;
 typedef struct picg_source_s*  picg_source_t;
 
 /* ------------------------------------------------------------------ runtime */
@@ -216,6 +217,19 @@ PICG_API int picg_mcc_set_wsv_max(picg_mcc_t m, double v);
 /* debug / tests: lengths of the exact per-cell particle lists the collision kernel uses (0 neutrals, 1 electrons) */
 PICG_API int picg_mcc_list_counts(picg_mcc_t m, int which, double* cells);
 PICG_API int picg_mcc_sigma(picg_mcc_t m, int n, const double* E_eV, double* sigma_coll, double* sigma_ion); /* evaluateSigmaColl/Ion :541-566 */
+
+/* ----------------------------------------------------------------- DSMC_MEX */
+/* DSMC_MEX(species, world) / DSMC_MEX(species1, species2, world)  Interactions.cpp:143-176: Bird NTC collisions with the
+ * variable-hard-sphere cross-section between macro-particles of equal weight.  species2 == NULL (or == species1): collisions
+ * within one species.  Different mpw0 -> PICG_ERR_ARG (the reference's std::invalid_argument, :160-162). */
+PICG_API int picg_dsmc_create(picg_species_t species1, picg_species_t species2 /*may be NULL*/, picg_world_t w, picg_dsmc_t* out);
+PICG_API int picg_dsmc_destroy(picg_dsmc_t m);
+typedef struct { uint64_t candidates, collisions; double sigma_v_max; } picg_dsmc_stats;
+/* Interaction::apply(dt) -> DSMC_MEX::applyOneSpecies / applyTwoSpecies  Interactions.cpp:183-265 (collide :267-285).
+ * stats == NULL: nothing is read back and the call does not synchronise. */
+PICG_API int picg_dsmc_apply(picg_dsmc_t m, double dt, picg_dsmc_stats* stats /*may be NULL*/);
+PICG_API int picg_dsmc_set_sigma_v_max(picg_dsmc_t m, double v);                             /* sigma_v_rel_max  Interactions.h:58 */
+PICG_API int picg_dsmc_sigma(picg_dsmc_t m, int n, const double* v_rel, double* sigma);      /* evaluateSigma :178-181 */
 
 /* ------------------------------------------------------------------- Source */
 /* ColdBeamSource / WarmBeamSource  Source.cpp:3-191; face: 0 x- 1 x+ 2 y- 3 y+ 4 z- 5 z+ ; T<=0 => cold */

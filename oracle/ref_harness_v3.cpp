@@ -218,6 +218,27 @@ API int refv3_mcc_collide(MC_MEX_Ionization* m, double* vn, double* ve, double* 
     return ion;
 }
 
+// --------------------------------------------------------------------- DSMC_MEX
+namespace {
+struct DsmcAccess : public DSMC_MEX {
+    using DSMC_MEX::evaluateSigma; using DSMC_MEX::sigma_v_rel_max; using DSMC_MEX::collide;
+};
+}
+API DSMC_MEX* refv3_dsmc_create(Species* s1, Species* s2, World* w) {              // v3/Interactions.cpp:143-176
+    try { return s2 ? new DSMC_MEX(*s1, *s2, *w) : new DSMC_MEX(*s1, *w); }
+    catch (const std::exception& e) { std::cerr << "refv3_dsmc_create: " << e.what() << "\n"; return nullptr; }
+}
+API void refv3_dsmc_destroy(DSMC_MEX* m) { delete m; }
+API void refv3_dsmc_apply(DSMC_MEX* m, double dt) { m->apply(dt); }                // :183-265
+API double refv3_dsmc_sigma(DSMC_MEX* m, double v_rel) { return static_cast<DsmcAccess*>(m)->evaluateSigma(v_rel); }
+API double refv3_dsmc_get_sigma_v_max(DSMC_MEX* m) { return static_cast<DsmcAccess*>(m)->sigma_v_rel_max; }
+API void   refv3_dsmc_set_sigma_v_max(DSMC_MEX* m, double v) { static_cast<DsmcAccess*>(m)->sigma_v_rel_max = v; }
+API void refv3_dsmc_collide(DSMC_MEX* m, double* v1, double* v2) {                 // :267-285
+    type_calc3 a(v1[0], v1[1], v1[2]), b(v2[0], v2[1], v2[2]);
+    static_cast<DsmcAccess*>(m)->collide(a, b);
+    for (int i = 0; i < 3; i++) { v1[i] = a[i]; v2[i] = b[i]; }
+}
+
 // -------------------------------------------------------------------- Sources
 API Source* refv3_source_cold(Species* s, World* w, double v_drift, double den, const char* face) {
     return new ColdBeamSource(*s, *w, v_drift, den, face);

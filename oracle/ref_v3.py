@@ -21,10 +21,10 @@ def lib():
     global _lib
     if _lib is None:
         l = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
-        for f in ("refv3_world_create", "refv3_species_create", "refv3_solver_create", "refv3_mcc_create", "refv3_source_cold", "refv3_source_warm"):
+        for f in ("refv3_world_create", "refv3_species_create", "refv3_solver_create", "refv3_mcc_create", "refv3_dsmc_create", "refv3_source_cold", "refv3_source_warm"):
             getattr(l, f).restype = C.c_void_p
         for f in ("refv3_rnd", "refv3_world_get_pe", "refv3_species_ke", "refv3_species_micro_count", "refv3_mcc_sigma_coll", "refv3_mcc_sigma_ion",
-                  "refv3_mcc_get_wsv_max"):
+                  "refv3_mcc_get_wsv_max", "refv3_dsmc_sigma", "refv3_dsmc_get_sigma_v_max"):
             getattr(l, f).restype = C.c_double
         for f in ("refv3_species_count", "refv3_species_sort_counts"):
             getattr(l, f).restype = C.c_size_t
@@ -264,6 +264,42 @@ class MC_MEX_Ionization:
         c = (C.c_double * 3)()
         ion = lib().refv3_mcc_collide(_h(self.h), a, b, c, C.c_double(sigma_coll))
         return bool(ion), np.array(list(a)), np.array(list(b)), np.array(list(c))
+
+
+class DSMC_MEX:
+    """DSMC_MEX(species, world) / DSMC_MEX(species1, species2, world) of the compiled reference (v3/Interactions.cpp:143-285)."""
+
+    def __init__(self, species1, species2_or_world, world=None):
+        if world is None:
+            species2, world = None, species2_or_world
+        else:
+            species2 = species2_or_world
+        self.h = lib().refv3_dsmc_create(_h(species1.h), _h(species2.h) if species2 is not None else None, _h(world.h))
+        if not self.h:
+            raise ValueError("reference DSMC_MEX constructor threw")
+
+    def close(self):
+        if self.h:
+            lib().refv3_dsmc_destroy(_h(self.h))
+            self.h = None
+
+    def apply(self, dt):
+        lib().refv3_dsmc_apply(_h(self.h), C.c_double(dt))
+
+    def sigma(self, v_rel):
+        return np.array([lib().refv3_dsmc_sigma(_h(self.h), C.c_double(float(v))) for v in np.atleast_1d(v_rel)])
+
+    def getSigmaVMax(self):
+        return lib().refv3_dsmc_get_sigma_v_max(_h(self.h))
+
+    def setSigmaVMax(self, v):
+        lib().refv3_dsmc_set_sigma_v_max(_h(self.h), C.c_double(v))
+
+    def collide(self, v1, v2):
+        a = (C.c_double * 3)(*v1)
+        b = (C.c_double * 3)(*v2)
+        lib().refv3_dsmc_collide(_h(self.h), a, b)
+        return np.array(list(a)), np.array(list(b))
 
 
 class Source:
