@@ -35,7 +35,7 @@ PKG = "engineering-degree-in-plasma-simulations_b200"
 
 AMU, QE, ME, NA = 1.660538921e-27, 1.602176565e-19, 9.10938215e-31, 6.02214076e23
 # algorithmic bytes (SURVEY.md 8d / DESIGN.md): per particle or per node, per launch of the kernel
-ALG_BYTES_PER_PARTICLE = {"push_electrons": 96, "push_heavy": 96, "push_electrons_deposit": 104, "push_heavy_deposit": 104, "deposit_density": 32}
+ALG_BYTES_PER_PARTICLE = {"push_electrons": 96, "push_heavy": 96, "push_neutral": 72, "push_electrons_deposit": 104, "push_heavy_deposit": 104, "deposit_density": 32}
 ALG_BYTES_PER_NODE = {"sor_redblack": 12.5, "sor_tiled": 25.0, "compute_ef": 32, "charge_density": 24, "finalize_density": 24}
 
 
@@ -366,7 +366,9 @@ def run_ours(args):
         if name == "push_electrons_deposit" or name == "push_electrons":
             alg = ALG_BYTES_PER_PARTICLE[name] * per_rank_counts["e-"]
         elif name == "push_heavy":
-            alg = 96 * 0.5 * (per_rank_counts["O"] + per_rank_counts["O+"])       # launches alternate between the two heavy species
+            alg = 96 * per_rank_counts["O+"] if "push_neutral" in kt else 96 * 0.5 * (per_rank_counts["O"] + per_rank_counts["O+"])
+        elif name == "push_neutral":                                               # drift only: pos + vel read, pos written (no kick for charge 0)
+            alg = 72 * per_rank_counts["O"]
         elif name == "count_per_cell":
             alg = 24 * float(np.mean(list(per_rank_counts.values())))
         elif name in ALG_BYTES_PER_NODE:
@@ -385,13 +387,11 @@ def run_ours(args):
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this workload (profiles/capture.sh ->
     # profiles/ncu_traffic.py); only quoted when the run IS that workload (same mesh, particle count, one GPU)
     traffic, traffic_src = None, None
-    ncu_names = {"push_heavy": "k_run<1, 1, 0, 0>", "push_electrons": "k_run<1, 0, 0, 0>", "sor_redblack": "k_sor_row"}
+    ncu_names = {"push_heavy": "k_run<1, 1, 0, 0, 0>", "push_neutral": "k_run<1, 1, 0, 0, 1>", "push_electrons": "k_run<1, 0, 0, 0, 0>", "sor_redblack": "k_sor_row"}
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
         if world == 1 and m == 256 and abs(args.particles - 1e9) < 1 and dom in ncu_names:
             ent = tj["kernels"][ncu_names[dom]]
-            if dom == "push_heavy":
-                ent = ent[:2]                                     # one launch per heavy species (O, O+), like alg_bytes_per_launch
             traffic = float(np.mean([e["dram_bytes"] for e in ent]))
             traffic_src = "profiles/ncu_traffic_r1.json (%s, mean of %d captured launches)" % (ncu_names[dom], len(ent))
     except Exception:

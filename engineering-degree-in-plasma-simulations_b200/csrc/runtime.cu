@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace picg {
@@ -12,6 +13,11 @@ int g_sm_count = PICG_SM_COUNT_FALLBACK;
 uint64_t g_seed = 0x5EED0000ull;
 int g_rank = 0, g_world_size = 1;
 uint64_t g_reallocs = 0;
+void note_realloc(const char* what, size_t bytes) {
+    static const bool trace = getenv("PICG_TRACE_REALLOC") && atoi(getenv("PICG_TRACE_REALLOC")) != 0;
+    g_reallocs++;
+    if (trace) fprintf(stderr, "[picgpu] device allocation #%llu: %s, %.1f MB\n", (unsigned long long)g_reallocs, what, bytes / 1e6);
+}
 bool g_capturing = false;
 static thread_local char g_err[1024] = "";
 static uint64_t g_launches = 0;
@@ -62,7 +68,7 @@ int ensure_scratch(picg_world_s* w, size_t bytes) {
     cudaError_t e = cudaMalloc(&w->scratch, want);
     if (e != cudaSuccess) { e = cudaMalloc(&w->scratch, bytes); want = bytes; }
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)", __FILE__, __LINE__);
-    w->scratch_bytes = want; g_reallocs++;
+    w->scratch_bytes = want; note_realloc("scratch arena", want);
     return PICG_OK;
 }
 }  // namespace picg
@@ -73,7 +79,7 @@ static const char* kKernelNames[K_NUM_KERNELS] = {
     "push_electrons", "push_electrons_deposit", "push_reflect", "push_heavy", "compact", "deposit_density",
     "finalize_density", "charge_density", "sor_redblack", "residual_l2", "compute_ef", "sort_keys", "sort_hist",
     "sort_scan", "sort_scatter", "sort_permute", "cell_start", "mc_ionize", "source_inject", "add_particles",
-    "sample_moments", "count_per_cell", "transpose", "diagnostics", "misc", "push_heavy_deposit", "heavy_impacts", "dsmc_collide"};
+    "sample_moments", "count_per_cell", "transpose", "diagnostics", "misc", "push_heavy_deposit", "heavy_impacts", "dsmc_collide", "push_neutral"};
 
 extern "C" {
 

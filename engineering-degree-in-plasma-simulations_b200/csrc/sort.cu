@@ -257,7 +257,7 @@ static int ensure_u32(unsigned*& p, size_t& cap, size_t want) {
     if (p) { cudaStreamSynchronize(g_stream); cudaFree(p); p = nullptr; cap = 0; }
     cudaError_t e = cudaMalloc(&p, want * 4);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(u32)", __FILE__, __LINE__);
-    cap = want; g_reallocs++; return PICG_OK;
+    cap = want; note_realloc("u32 list buffer", want * 4); return PICG_OK;
 }
 
 // Sorts species s by cell.  Scratch: keysA | keysB | idxA | idxB | counts.

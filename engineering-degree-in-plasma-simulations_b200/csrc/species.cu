@@ -2,6 +2,7 @@
 // reference's AoS Particle record, addParticle semantics, diagnostics, node-field bookkeeping.
 // Replaces the storage side of ch4/v3/src/Species.{h,cpp}.
 #include "common.cuh"
+#include "push.cuh"
 #include <cstring>
 #include <algorithm>
 
@@ -131,9 +132,12 @@ int species_ensure_capacity(picg_species_s* s, size_t cap) {
     cudaStreamSynchronize(g_stream);
     for (int c = 0; c < 7; c++) { cudaFree(s->a[c]); s->a[c] = na[c]; }
     cudaFree(s->spare); s->spare = na[7];
-    g_reallocs++;
+    note_realloc("particle store", newcap * 64);
     s->cap = newcap;
-    return PICG_OK;
+    // the shared scratch arena is sized for a full store as well (radix sort: 16 B per particle; push: dead / hole lists +
+    // the heavy push's impact list), so that it does not have to grow - free + allocate of GBs, tens of ms - while the
+    // population grows into the reserved capacity
+    return ensure_scratch(s->w, std::max(newcap * 16 + (1u << 20), compact_scratch_bytes(newcap) + newcap * 4 + 64));
 }
 }  // namespace picg
 

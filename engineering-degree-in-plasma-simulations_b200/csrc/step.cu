@@ -71,7 +71,10 @@ __device__ __forceinline__ void store_run(double* base, u64 p0, bool full, u64 l
     }
 }
 
-template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT>
+// DRIFT: the species is neutral (charge == 0), so the kick `v += E * (dt*q/m)` adds E*0 = 0 (Species.cpp:187-188): the E gather
+// and the velocity write-back are skipped (72 B per particle instead of 96).  Same values as the reference for every finite E
+// (a -0.0 velocity component would become +0.0 there and stays -0.0 here: equal under ==).
+template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT, bool DRIFT = false>
 __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, HeavyArgs H) {
     __shared__ unsigned s_lo[DEPOSIT ? RUN_WARPS : 1][RUN_WINDOW * 4], s_hi[DEPOSIT ? RUN_WARPS : 1][RUN_WINDOW * 4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -108,9 +111,12 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
             const bool ok = p >= lo && p < n;
             bool dead = false, impact = false;
             if (PUSH && ok) {
-                double ex, ey, ez;
-                gather_ef(g, A.ef, x_to_l(x[r], g.x0[0], g.inv_dx[0]), x_to_l(y[r], g.x0[1], g.inv_dx[1]), x_to_l(z[r], g.x0[2], g.inv_dx[2]), ex, ey, ez);
-                double un = __dadd_rn(u[r], __dmul_rn(ex, A.qm_dt)), vn = __dadd_rn(v[r], __dmul_rn(ey, A.qm_dt)), wn = __dadd_rn(w[r], __dmul_rn(ez, A.qm_dt));
+                double un = u[r], vn = v[r], wn = w[r];
+                if (!DRIFT) {
+                    double ex, ey, ez;
+                    gather_ef(g, A.ef, x_to_l(x[r], g.x0[0], g.inv_dx[0]), x_to_l(y[r], g.x0[1], g.inv_dx[1]), x_to_l(z[r], g.x0[2], g.inv_dx[2]), ex, ey, ez);
+                    un = __dadd_rn(un, __dmul_rn(ex, A.qm_dt)); vn = __dadd_rn(vn, __dmul_rn(ey, A.qm_dt)); wn = __dadd_rn(wn, __dmul_rn(ez, A.qm_dt));
+                }
                 double xn = x[r], yn = y[r], zn = z[r];
                 if (!HEAVY) {
                     xn = __dadd_rn(xn, __dmul_rn(un, A.dt)); yn = __dadd_rn(yn, __dmul_rn(vn, A.dt)); zn = __dadd_rn(zn, __dmul_rn(wn, A.dt));
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
         // results back to the store (dead slots keep their old contents; the compaction fills them)
         if (PUSH) {
             store_run<RL>(A.a[0], p0, full, lo, n, x); store_run<RL>(A.a[1], p0, full, lo, n, y); store_run<RL>(A.a[2], p0, full, lo, n, z);
-            store_run<RL>(A.a[3], p0, full, lo, n, u); store_run<RL>(A.a[4], p0, full, lo, n, v); store_run<RL>(A.a[5], p0, full, lo, n, w);
+            if (!DRIFT) { store_run<RL>(A.a[3], p0, full, lo, n, u); store_run<RL>(A.a[4], p0, full, lo, n, v); store_run<RL>(A.a[5], p0, full, lo, n, w); }
         }
         // end of the run: the register sums go to the warp's window, the window to the global grid
         if (DEPOSIT) {
@@ -211,11 +217,11 @@ int launch_finalize(picg_species_s* s, size_t u_begin = 0, size_t u_end = (size_
 int calibrate_scale(picg_species_s* s, bool count_cells);
 int check_scale_after(picg_species_s* s);
 
-template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT>
+template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT, bool DRIFT = false>
 static int launch_variant(const Grid& g, const StepArgs& A, const HeavyArgs& H, size_t n_upper, int kid) {
     constexpr int chunk = 32 * (PUSH ? RUN_LEN_PUSH : RUN_LEN_SCAN) * RUN_WARPS;
     int grid = std::max(1, std::min(div_up(std::max<size_t>(n_upper, 1), chunk), g_sm_count * 2 * 4));
-    LAUNCH(kid, (k_run<PUSH, HEAVY, DEPOSIT, COUNT>), grid, RUN_THREADS, 0, g, A, H);
+    LAUNCH(kid, (k_run<PUSH, HEAVY, DEPOSIT, COUNT, DRIFT>), grid, RUN_THREADS, 0, g, A, H);
     CHECK_LAUNCH();
     return PICG_OK;
 }
@@ -251,10 +257,12 @@ int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals
         nu = nu - s->part_n;
     }
     if (mode & 2) CUDA_TRY(cudaMemsetAsync(&s->ctr->n_impact, 0, 8, g_stream));
+    static const bool no_drift_path = getenv("PICG_NO_DRIFT_PATH") && atoi(getenv("PICG_NO_DRIFT_PATH")) != 0;   // A/B switch: neutrals through the kick + gather
     int rc = PICG_OK;
     switch (mode) {
         case 1:  rc = launch_variant<true, false, false, false>(g, A, H, nu, K_PUSH_ELECTRONS); break;
-        case 3:  rc = launch_variant<true, true, false, false>(g, A, H, nu, K_PUSH_HEAVY); break;
+        case 3:  rc = (A.qm_dt == 0.0 && !no_drift_path) ? launch_variant<true, true, false, false, true>(g, A, H, nu, K_PUSH_NEUTRAL)
+                                                          : launch_variant<true, true, false, false>(g, A, H, nu, K_PUSH_HEAVY); break;
         case 4:  rc = launch_variant<false, false, true, false>(g, A, H, nu, K_DEPOSIT); break;
         case 12: rc = launch_variant<false, false, true, true>(g, A, H, nu, K_DEPOSIT); break;
         case 8:  rc = launch_variant<false, false, false, true>(g, A, H, nu, K_COUNT_CELLS); break;

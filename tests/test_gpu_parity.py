@@ -418,3 +418,28 @@ def test_against_compiled_reference(picgpu, ref):
     assert util.norm_err(wg.rho, wr.get(1)) < 1e-12
     for o in (er, sr, wr, eg, sg, wg):
         o.close()
+
+
+def test_neutral_push_is_a_pure_drift_and_matches_the_reference(picgpu, ref):
+    """charge == 0: the device skips the E gather and the velocity write-back (k_run<.., DRIFT>); the reference adds
+    E*(dt*0/m) = 0 (Species.cpp:187-188).  Same particles bit for bit, in a non-zero field, with deaths at the box faces."""
+    ni, nj, nk = 11, 9, 13
+    x0, xm, rects = util.discharge_geometry(ni, nj, nk)
+    wr = util.build_world(ref.World, ni, nj, nk, x0, xm, rects)
+    wg = util.build_world(picgpu.World, ni, nj, nk, x0, xm, rects)
+    ef = util.smooth_ef((ni, nj, nk), x0, xm, seed=5, amp=3e6)
+    wr.set(3, ef); wg.upload(picgpu.F_EF, ef)
+    # inside the gap, too slow to reach an electrode in one step (no stochastic re-emission), fast enough to leave through x/y
+    parts = util.random_particles(50000, x0, xm, seed=43, vth=3e3, mpw=(5e11, 5e11), lo_frac=(0, 0, 0.35), hi_frac=(1, 1, 0.65))
+    nr = ref.Species("O", 16 * util.AMU, 0.0, wr, 5e11); nr.setParticles(parts)
+    ng = picgpu.Species("O", 16 * util.AMU, 0.0, wg, 5e11); ng.setParticles(parts)
+    picgpu.timers_reset(); picgpu.timers_enable(True)
+    for _ in range(2):
+        nr.advanceNonElectron(nr, nr, 4e-8); ng.advanceNonElectron(ng, ng, 4e-8)
+    picgpu.timers_enable(False)
+    assert "push_neutral" in picgpu.timers_read() and "push_heavy" not in picgpu.timers_read()      # the drift kernel is what ran
+    got, want = util.sort_rows(ng.getParticles()), util.sort_rows(nr.getParticles())
+    assert 0 < len(want) < len(parts)
+    assert np.array_equal(got, want)
+    for o in (nr, wr, ng, wg):
+        o.close()
