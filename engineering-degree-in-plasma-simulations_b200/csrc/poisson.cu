@@ -41,8 +41,7 @@ __device__ __forceinline__ size_t face_neighbor(const Grid& g, int cls, size_t u
 // row*hk + (k>>1) of colour c's half (hk = ceil(nk/2)).  A half-sweep then reads the node class (1 byte: no index arithmetic or
 // geometry branches in the sweeps) and rho of its own colour with unit stride instead of every other value of whole sectors.
 __global__ void __launch_bounds__(256) k_node_classes(Grid g, int bc_mode, const int* __restrict__ object_id, const double* __restrict__ rho,
-                                                      unsigned char* __restrict__ cls, double* __restrict__ rho_split,
-                                                      const double* __restrict__ phi, double* __restrict__ phi_split) {
+                                                      unsigned char* __restrict__ cls, double* __restrict__ rho_split) {
     const int hk = (g.nk + 1) >> 1;
     const size_t half = (size_t)g.ni * g.nj * hk;
     for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < (size_t)g.nv; u += (size_t)gridDim.x * blockDim.x) {
@@ -51,50 +50,6 @@ __global__ void __launch_bounds__(256) k_node_classes(Grid g, int bc_mode, const
         const size_t c = (size_t)color * half + row * hk + (k >> 1);
         cls[c] = (unsigned char)node_class(g, bc_mode, object_id[u], i, j, k);
         rho_split[c] = rho[u];
-        if (phi_split) phi_split[c] = phi[u];
-    }
-}
-// phi back from the colour-compact layout to Field order (before a residual check and at the end of a solve)
-__global__ void __launch_bounds__(256) k_phi_unsplit(Grid g, const double* __restrict__ phi_split, double* __restrict__ phi) {
-    const int hk = (g.nk + 1) >> 1;
-    const size_t half = (size_t)g.ni * g.nj * hk;
-    for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < (size_t)g.nv; u += (size_t)gridDim.x * blockDim.x) {
-        int k = (int)(u % g.nk); size_t row = u / g.nk; int j = (int)(row % g.nj), i = (int)(row / g.nj);
-        phi[u] = phi_split[(size_t)((i + j + k) & 1) * half + row * hk + (k >> 1)];
-    }
-}
-// One colour half-sweep on the colour-compact phi (single GPU).  Node k = 2m+p of row (i,j), p = (i+j+color)&1, is element m of
-// its colour's row; its four i/j neighbours are element m of the neighbouring rows of the OTHER colour, its k neighbours are
-// elements m-1+p and m+p of the same row of the other colour: every access of the sweep has unit stride, so a half-sweep
-// moves its own colour (read + write), the other colour (read), rho and the class byte of its own colour - 16.5 B/node
-// instead of whole sectors of an interleaved array of which every other value is used.  Same update, same operands, same
-// bits as k_sor_row.
-__global__ void __launch_bounds__(128) k_sor_split(Grid g, SorParams sp, int color, double* __restrict__ phi_split, const double* __restrict__ rho,
-                                                   const unsigned char* __restrict__ cls) {
-    const int j = blockIdx.x, i = blockIdx.y;
-    const int hk = (g.nk + 1) >> 1;
-    const size_t half = (size_t)g.ni * g.nj * hk;
-    const size_t si = (size_t)g.nj * hk, sj = hk;
-    const size_t row = ((size_t)i * g.nj + j) * hk;
-    const int p = (i + j + color) & 1;
-    double* __restrict__ A = phi_split + (size_t)color * half + row;              // this colour, this row
-    const double* __restrict__ B = phi_split + (size_t)(1 - color) * half + row;  // the other colour, this row
-    const size_t crow = (size_t)color * half + row;
-    const int n_own = (g.nk - p + 1) >> 1;                                        // nodes of this colour in the row
-    for (int m = threadIdx.x; m < n_own; m += blockDim.x) {
-        const int c = cls[crow + m];
-        if (c == 0) continue;
-        if (c < 7) {                                                              // zero-gradient face: copy the inward neighbour (face_neighbor)
-            double v;
-            switch (c) { case 1: v = B[m + si]; break; case 2: v = B[m - si]; break; case 3: v = B[m + sj]; break; case 4: v = B[m - sj]; break;
-                         case 5: v = B[m + p]; break; default: v = B[m - 1 + p]; break; }
-            A[m] = v; continue;
-        }
-        const double ph = A[m];
-        const double ne = (sp.n0 != 0.0) ? sp.n0 * exp((ph - sp.phi0) / sp.Te0) : 0.0;
-        const double nw = ((rho[crow + m] - sp.qe * ne) * sp.inv_eps0 + (B[m - si] + B[m + si]) * sp.inv_d2x + (B[m - sj] + B[m + sj]) * sp.inv_d2y +
-                           (B[m - 1 + p] + B[m + p]) * sp.inv_d2z) * sp.inv_twos;
-        A[m] = ph + sp.w * (nw - ph);
     }
 }
 // One colour half-sweep, one block per (i,j) row: no divisions, coalesced along k, class byte instead of geometry tests.
@@ -293,32 +248,15 @@ static SorParams make_params(const picg_solver_s* s) {
 }
 static const int kResidualBlocks = 1024;
 
-static bool use_split(const picg_solver_s* s) {
-    static const bool off = getenv("PICG_NO_SPLIT_PHI") && atoi(getenv("PICG_NO_SPLIT_PHI")) != 0;      // A/B switch, see DESIGN.md
-    return s->slab_world <= 1 && !off;
-}
 static int prepare_classes(picg_solver_s* s) {
     const Grid& g = s->w->g;
     const size_t half = (size_t)g.ni * g.nj * ((g.nk + 1) >> 1);
     if (!s->cls) {
         cudaError_t e = cudaMalloc(&s->cls, 2 * half);
         if (e == cudaSuccess) e = cudaMalloc(&s->rho_split, 2 * half * 8);
-        if (e == cudaSuccess) e = cudaMalloc(&s->phi_split, 2 * half * 8);
-        if (e == cudaSuccess) e = cudaMemsetAsync(s->phi_split, 0, 2 * half * 8, g_stream);      // pad elements of odd-nk rows are never used; keep them defined
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(colour-compact classes / rho / phi)", __FILE__, __LINE__);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(colour-compact classes / rho)", __FILE__, __LINE__);
     }
-    // single GPU: the sweeps run on a colour-compact copy of phi as well (slab mode keeps phi in Field order: the peers write into it)
-    s->split_live = use_split(s);
-    LAUNCH(K_MISC, k_node_classes, std::min(div_up(g.nv, 256), g_sm_count * 8), 256, 0, g, s->bc_mode, s->w->object_id, s->w->rho, s->cls, s->rho_split,
-           s->w->phi, s->split_live ? s->phi_split : nullptr); CHECK_LAUNCH();
-    return PICG_OK;
-}
-// phi in Field order is stale while the sweeps run on the colour-compact copy: bring it back (no-op when it is current)
-static int sync_phi(picg_solver_s* s) {
-    if (!s->split_live || !s->split_dirty) return PICG_OK;
-    const Grid& g = s->w->g;
-    LAUNCH(K_MISC, k_phi_unsplit, std::min(div_up(g.nv, 256), g_sm_count * 8), 256, 0, g, s->phi_split, s->w->phi); CHECK_LAUNCH();
-    s->split_dirty = false;
+    LAUNCH(K_MISC, k_node_classes, std::min(div_up(g.nv, 256), g_sm_count * 8), 256, 0, g, s->bc_mode, s->w->object_id, s->w->rho, s->cls, s->rho_split); CHECK_LAUNCH();
     return PICG_OK;
 }
 static SlabArgs slab_args(picg_solver_s* s, unsigned seq_off) {
@@ -331,22 +269,19 @@ static SlabArgs slab_args(picg_solver_s* s, unsigned seq_off) {
 // n iterations = 2n colour half-sweeps enqueued back to back (plain launches; `timed` adds the per-kernel bookkeeping)
 static int enqueue_iterations(picg_solver_s* s, const SorParams& p, unsigned n, bool timed) {
     const Grid& g = s->w->g;
-    const bool slab = s->slab_world > 1, split = s->split_live;
+    const bool slab = s->slab_world > 1;
     dim3 grid(g.nj, slab ? s->slab_i1 - s->slab_i0 : g.ni);
     for (unsigned h = 0; h < 2 * n; h++) {
         const int color = h & 1;
         if (timed) {
             if (slab) LAUNCH(K_SOR, k_sor_slab, grid, 128, 0, g, p, color, s->w->phi, s->rho_split, s->cls, slab_args(s, h + 1));
-            else if (split) LAUNCH(K_SOR, k_sor_split, grid, 128, 0, g, p, color, s->phi_split, s->rho_split, s->cls);
             else LAUNCH(K_SOR, k_sor_row, grid, 128, 0, g, p, color, s->w->phi, s->rho_split, s->cls);
         } else {
             if (slab) k_sor_slab<<<grid, 128, 0, g_stream>>>(g, p, color, s->w->phi, s->rho_split, s->cls, slab_args(s, h + 1));
-            else if (split) k_sor_split<<<grid, 128, 0, g_stream>>>(g, p, color, s->phi_split, s->rho_split, s->cls);
             else k_sor_row<<<grid, 128, 0, g_stream>>>(g, p, color, s->w->phi, s->rho_split, s->cls);
         }
         CHECK_LAUNCH();
     }
-    if (split && n) s->split_dirty = true;
     if (slab) { k_slab_advance<<<1, 1, 0, g_stream>>>(s->mbox, 2 * n); CHECK_LAUNCH(); }
     return PICG_OK;
 }
