@@ -18,6 +18,7 @@ namespace picg { int species_exact_lists(picg_species_s* s); }
 
 struct DsmcParams {
     double mass1, mass2, sum_mass, dv, mpw0, rank_scale;
+    int world, rank;
     double pi_c0_c0, c1_m_half, c2, c3;
 };
 // evaluateSigma (:178-181): pi * c0 * c0 * pow(c2 / (v_rel*v_rel), c1 - 0.5) / c3
@@ -51,8 +52,11 @@ __global__ void __launch_bounds__(128, 6) k_dsmc(Grid g, DsmcParams P, Store s1,
         CellView vb = va;
         if (TWO) { vb = cell_view(L2, c); np2 = vb.np; if (np1 < 1 || np2 < 1) continue; }      // :238
         else if (np1 < 2) continue;                                                               // :194
-        double frac = 0.5 * np1 * np2 * P.mpw0 * sv_max * dt / P.dv * P.rank_scale;               // :196 / :240 (x G ranks)
+        // :196 / :240.  Multi-GPU: the cell's candidate count is estimated from the local populations (x G^2), rounded once
+        // like the reference's and dealt out to the ranks (n/G each, the n%G left over to a rotating subset), see mcc.cu
+        double frac = 0.5 * np1 * np2 * P.mpw0 * sv_max * dt / P.dv * P.rank_scale;
         int n_groups = (int)(frac + 0.5);
+        if (P.world > 1) n_groups = n_groups / P.world + ((unsigned)(c + (int)call + P.rank) % (unsigned)P.world < (unsigned)(n_groups % P.world) ? 1 : 0);
         if (n_groups <= 0) continue;
         PhiloxStream r; r.init(seed, stream, (u64)c, call);
         for (int t = 0; t < n_groups; t++) {
@@ -95,7 +99,7 @@ static DsmcParams make_params(const picg_dsmc_s* m) {
     const Grid& g = m->w->g;
     P.dv = g.dx[0] * g.dx[1] * g.dx[2];                                                     // World::getCellVolume
     P.mpw0 = m->sp1->mpw0;
-    P.rank_scale = (double)g_world_size;
+    P.rank_scale = (double)g_world_size * (double)g_world_size; P.world = g_world_size; P.rank = g_rank;
     const double c0 = 4.07e-10, c1 = 0.77;                                                  // :151-154 Bird's reference parameters at 273.15 K
     P.pi_c0_c0 = 3.141592653 * c0 * c0;
     P.c1_m_half = c1 - 0.5;

@@ -21,6 +21,7 @@ namespace picg { int sort_species(picg_species_s* s); int species_exact_lists(pi
 
 struct MccParams {
     double m_n, m_e, sum_mass, E_rel_eV, E_ele_eV, two_qe_me, c0, c1, c2, B_inc, E_ion_eV, inv_dv, rank_scale;
+    int world, rank;
     int n_tab; const double* tab_E; const double* tab_s;
 };
 // evaluateSigmaColl (:541-558): std::map lower_bound + linear interpolation, clamped to the end values
@@ -107,8 +108,12 @@ __global__ void __launch_bounds__(128, 6) k_mcc(Grid g, MccParams P, Store neu, 
         CellView vn = cell_view(Ln, c); int np_n0 = vn.np;
         if (np_n0 <= 0) continue;
         int np_n = np_n0;
-        double frac = np_n * np_e * W_max * dt * P.inv_dv * P.rank_scale;               // :646 (x G ranks)
+        // :646.  Multi-GPU: the particles of a cell are spread over G ranks, so the cell's candidate count is estimated
+        // from the local populations (x G^2), rounded ONCE like the reference's and dealt out to the ranks: n/G each, the n%G left
+        // over to a rotating subset.  Rounding per rank instead would lose every cell whose share is below one half.
+        double frac = np_n * np_e * W_max * dt * P.inv_dv * P.rank_scale;
         int n_groups = (int)(frac + 0.5);
+        if (P.world > 1) n_groups = n_groups / P.world + ((unsigned)(c + (int)call + P.rank) % (unsigned)P.world < (unsigned)(n_groups % P.world) ? 1 : 0);
         if (n_groups > np_n) n_groups = np_n - 1;                                         // :649-653
         if (n_groups <= 0) continue;
         PhiloxStream r; r.init(seed, stream, (u64)c, call);
@@ -182,7 +187,7 @@ static MccParams make_params(const picg_mcc_s* m) {
     P.E_ion_eV = m->E_ion_J / 1.602176565e-19;                                            // :499
     const Grid& g = m->w->g;
     P.inv_dv = 1 / (g.dx[0] * g.dx[1] * g.dx[2]);                                         // :500-501
-    P.rank_scale = (double)g_world_size;
+    P.rank_scale = (double)g_world_size * (double)g_world_size; P.world = g_world_size; P.rank = g_rank;
     P.n_tab = m->n_table; P.tab_E = m->tab_E; P.tab_s = m->tab_s;
     return P;
 }

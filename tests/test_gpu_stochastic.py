@@ -296,3 +296,39 @@ def test_thermal_loader_statistics(picgpu, ref):
     sg, sr = np.linalg.norm(g[:, 3:6], axis=1), np.linalg.norm(r[:, 3:6], axis=1)
     assert abs(sg.mean() - sr.mean()) < 6 * sr.std() / np.sqrt(len(sr))
     assert np.all(g[:, 6] == 1e5)
+
+
+def test_mc_candidates_are_dealt_out_over_ranks(picgpu):
+    """Multi-GPU rule, emulated on one device: G ranks each hold every G-th particle.  A cell's candidate count is
+    estimated from the local populations (x G^2), rounded once like the reference's (Interactions.cpp:646-647) and dealt out
+    to the ranks.  In a regime of about one candidate per cell and step the ranks together must try as many pairs as a single
+    rank holding everything (rounding per rank would try almost none)."""
+    pg = picgpu
+    (ni, nj, nk, x0, xm, rects), neu, ele = _mcc_case(0)
+    E, sg = util.momentum_transfer_table()
+    E_ion = 1313.9 * 1000 / util.NA
+    dt, wsv = 2e-11, 5e11 * 8e-20 * 8e6
+
+    def run(rank, G):
+        pg.set_rank(rank, G); pg.seed(77)
+        w = util.build_world(pg.World, ni, nj, nk, x0, xm, rects, dt=dt)
+        sn = pg.Species("O", 16 * util.AMU, 0.0, w, 5e11, E_ion); si = pg.Species("O+", 16 * util.AMU, util.QE, w, 100.0); se = pg.Species("e-", util.ME, -util.QE, w, 100.0)
+        sn.setParticles(neu[rank::G]); se.setParticles(ele[rank::G])
+        m = pg.MC_MEX_Ionization(sn, si, se, w, E, sg); m.setWsvMax(wsv)
+        st = m.apply(dt)
+        out = (st.candidates, st.collisions)
+        for o in (m, sn, si, se, w):
+            o.close()
+        return out
+
+    try:
+        one = run(0, 1)
+        G = 4
+        parts = [run(r, G) for r in range(G)]
+    finally:
+        pg.set_rank(0, 1)
+    cells = (ni - 1) * (nj - 1) * (nk - 1)
+    assert 0.5 * cells < one[0] < 3 * cells                          # the regime the rule matters in: ~1 candidate per cell
+    tot = sum(p[0] for p in parts)
+    assert 0.85 * one[0] < tot < 1.15 * one[0], (one, parts)
+    assert max(p[0] for p in parts) < 0.4 * one[0]                   # and they are spread over the ranks
