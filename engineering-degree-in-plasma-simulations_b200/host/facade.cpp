@@ -312,20 +312,13 @@ void diagOutput(World& world, std::vector<Species>& species) {                  
     f_diag << "," << pe << "," << (tot + pe) << "\n";
     if (world.getTs() % 25 == 0) f_diag.flush();
 }
-void fieldsOutput(World& world, std::vector<Species>& species, std::string name1) {                 // Outputs.cpp:9-123 (ASCII .vti)
+void fieldsOutput(World& world, std::vector<Species>& species, std::string name1) {                 // Outputs.cpp:9-123, binary (appended raw) .vti
     for (Species& sp : species) sp.computeGasProperties();                                          // :11-14
-    std::stringstream name; name << "results/fields" << name1 << "_" << std::setfill('0') << std::setw(5) << world.getTs() << ".vti";
-    std::ofstream out(name.str());
-    if (out.is_open()) {
-        type_calc3 x0 = world.getX0(), dx = world.getDx();
-        out << "<VTKFile type=\"ImageData\">\n<ImageData Origin=\"" << x0[0] << " " << x0[1] << " " << x0[2] << "\" Spacing=\"" << dx[0] << " " << dx[1] << " " << dx[2]
-            << "\" WholeExtent=\"0 " << world.ni - 1 << " 0 " << world.nj - 1 << " 0 " << world.nk - 1 << "\">\n<PointData>\n";
-        auto scalar = [&](const char* n, const Field<type_calc>& f) { out << "<DataArray Name=\"" << n << "\" NumberOfComponents=\"1\" format=\"ascii\" type=\"Float64\">\n" << f << "</DataArray>\n"; };
-        scalar("phi", world.phi); scalar("rho", world.rho);
-        out << "<DataArray Name=\"ef\" NumberOfComponents=\"3\" format=\"ascii\" type=\"Float64\">\n" << world.ef << "</DataArray>\n";
-        for (Species& sp : species) { scalar(("nd." + sp.name).c_str(), sp.den); scalar(("nd-avg." + sp.name).c_str(), sp.den_avg); scalar(("T." + sp.name).c_str(), sp.T); }
-        out << "</PointData>\n</ImageData>\n</VTKFile>\n";
-    }
+    std::stringstream name; name << "results/" << name1 << "fields_" << std::setfill('0') << std::setw(5) << world.getTs() << ".vti";   // :16-17
+    std::vector<picg_species_t> hs; std::vector<const char*> names;
+    for (Species& sp : species) { hs.push_back(sp.dev()); names.push_back(sp.name.c_str()); }
+    if (picg_write_fields_vti(name.str().c_str(), world.dev(), hs.data(), names.data(), (int)hs.size()) != PICG_OK)
+        std::cerr << "Could not write " << name.str() << ": " << picg_last_error() << std::endl;      // :22-25
     for (Species& sp : species) sp.clearSamples();                                                  // :119-121
 }
 void particlesOutput(World& world, std::vector<Species>& species, int base, std::string name1) {
@@ -338,6 +331,20 @@ void particlesOutput(World& world, std::vector<Species>& species, int base, std:
         for (size_t i = 0; i < p.size(); i += stride) out << p[i].pos[0] << "," << p[i].pos[1] << "," << p[i].pos[2] << "," << p[i].vel[0] << "," << p[i].vel[1] << "," << p[i].vel[2] << "," << p[i].macro_weight << "\n";
     }
 }
+static bool checkpoint_io(bool save, const std::string& path, World& world, std::vector<Species>& species) {
+    std::vector<picg_species_t> hs; for (Species& sp : species) hs.push_back(sp.dev());
+    picg_checkpoint_set set{}; set.world = world.dev(); set.species = hs.data(); set.n_species = (int)hs.size();
+    uint64_t ts = (uint64_t)world.getTs();
+    int rc = save ? picg_checkpoint_save(path.c_str(), &set, ts) : picg_checkpoint_load(path.c_str(), &set, &ts);
+    if (rc != PICG_OK) { std::cerr << (save ? "saveCheckpoint: " : "loadCheckpoint: ") << picg_last_error() << std::endl; return false; }
+    if (!save) {
+        world.deviceChanged(PICG_F_PHI); world.deviceChanged(PICG_F_RHO); world.deviceChanged(PICG_F_EF);
+        for (Species& sp : species) sp.setSorted(false);
+    }
+    return true;
+}
+bool saveCheckpoint(const std::string& path, World& world, std::vector<Species>& species) { return checkpoint_io(true, path, world, species); }
+bool loadCheckpoint(const std::string& path, World& world, std::vector<Species>& species) { return checkpoint_io(false, path, world, species); }
 std::ostream& operator<<(std::ostream& out, Output::modes& t) {
     static const char* n[] = {"none", "all", "screen", "fields", "particles", "diagnostics", "convergence"};
     return out << n[(int)t];

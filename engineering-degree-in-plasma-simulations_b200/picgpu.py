@@ -438,6 +438,44 @@ class MC_MEX_Ionization:
         return sc, si
 
 
+class _CheckpointSet(C.Structure):
+    _fields_ = [("world", C.c_void_p), ("species", C.POINTER(C.c_void_p)), ("n_species", C.c_int), ("mcc", C.POINTER(C.c_void_p)), ("n_mcc", C.c_int),
+                ("dsmc", C.POINTER(C.c_void_p)), ("n_dsmc", C.c_int), ("sources", C.POINTER(C.c_void_p)), ("n_sources", C.c_int)]
+
+
+def _handle_array(objs):
+    arr = (C.c_void_p * max(len(objs), 1))(*[o.h.value if isinstance(o.h, C.c_void_p) else o.h for o in objs])
+    return arr
+
+
+def _checkpoint_set(world, species, mcc, dsmc, sources):
+    keep = [_handle_array(list(x)) for x in (species, mcc, dsmc, sources)]
+    cs = _CheckpointSet(world.h, C.cast(keep[0], C.POINTER(C.c_void_p)), len(species), C.cast(keep[1], C.POINTER(C.c_void_p)), len(mcc),
+                        C.cast(keep[2], C.POINTER(C.c_void_p)), len(dsmc), C.cast(keep[3], C.POINTER(C.c_void_p)), len(sources))
+    return cs, keep
+
+
+def checkpoint_save(path, world, species, mcc=(), dsmc=(), sources=(), ts=0):
+    """picg_checkpoint_save: binary restart file of the loop state (fields, particle stores, averages, RNG stream positions)."""
+    cs, keep = _checkpoint_set(world, species, mcc, dsmc, sources)
+    _chk(lib().picg_checkpoint_save(os.fsencode(path), C.byref(cs), C.c_uint64(int(ts))))
+
+
+def checkpoint_load(path, world, species, mcc=(), dsmc=(), sources=()):
+    """picg_checkpoint_load into objects rebuilt as at start-up (same order); returns the stored time-step number."""
+    cs, keep = _checkpoint_set(world, species, mcc, dsmc, sources)
+    ts = C.c_uint64(0)
+    _chk(lib().picg_checkpoint_load(os.fsencode(path), C.byref(cs), C.byref(ts)))
+    return ts.value
+
+
+def write_fields_vti(path, world, species):
+    """Output::fieldsOutput (ch4/v3/src/Outputs.cpp:9-123) as binary VTK ImageData (appended raw)."""
+    hs = _handle_array(list(species))
+    names = (C.c_char_p * max(len(species), 1))(*[sp.name.encode() for sp in species])
+    _chk(lib().picg_write_fields_vti(os.fsencode(path), world.h, C.cast(hs, C.POINTER(C.c_void_p)), names, len(species)))
+
+
 class DsmcStats(C.Structure):
     _fields_ = [("candidates", C.c_uint64), ("collisions", C.c_uint64), ("sigma_v_max", C.c_double)]
 

@@ -238,6 +238,29 @@ PICG_API int picg_source_destroy(picg_source_t src);
 /* Source::sample()  Source.cpp:99-103,187-191 */
 PICG_API int picg_source_sample(picg_source_t src, size_t* injected /*may be NULL*/);
 
+/* ------------------------------------------------------- outputs and restart */
+/* Output::fieldsOutput  Outputs.cpp:9-123: the same VTK ImageData file (arrays NodeVol, ObjectID, NodeType, phi, rho, nd.<sp>,
+ * avg_nd.<sp>, vel.<sp>, T.<sp>, ef as PointData and mpc.<sp> as CellData, in that order, all Float64, points in VTK order = i
+ * fastest) with the data as one appended raw binary block instead of ASCII.  names[k] is Species::name of species[k].  The
+ * caller runs computeGasProperties / clearSamples around it like the reference (:11-14, :119-121). */
+PICG_API int picg_write_fields_vti(const char* path, picg_world_t w, const picg_species_t* species, const char* const* names, int n);
+/* Restart files (the reference has none).  A checkpoint holds what the time loop carries from step to step: phi, rho, ef; per
+ * species the particle store, den, den_avg (+ sample count), the moment sums, the fixed-point scale and the positions of its
+ * RNG streams; W_sigma_v_rel_max / sigma_v_rel_max and the call counters of the interactions; the call counters of the sources;
+ * the seed.  The caller rebuilds World (mesh, objects), Species, interactions and sources as at start-up and passes them in the
+ * same order to load; mesh, species constants and counts are checked (PICG_ERR_ARG).  Deterministic kernels (push, deposit,
+ * fields) continue bit for bit; stochastic kernels continue on the same streams (the cell partition is rebuilt, so the order of
+ * a cell's particle list - hence the pairs drawn - may differ from the uninterrupted run). */
+typedef struct {
+    picg_world_t world;
+    const picg_species_t* species; int n_species;
+    const picg_mcc_t* mcc; int n_mcc;
+    const picg_dsmc_t* dsmc; int n_dsmc;
+    const picg_source_t* sources; int n_sources;
+} picg_checkpoint_set;
+PICG_API int picg_checkpoint_save(const char* path, const picg_checkpoint_set* set, uint64_t user_ts /* e.g. World::getTs() */);
+PICG_API int picg_checkpoint_load(const char* path, const picg_checkpoint_set* set, uint64_t* user_ts /*may be NULL*/);
+
 #ifdef __cplusplus
 }
 #endif
