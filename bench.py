@@ -229,6 +229,7 @@ def run_ours(args):
         scatter_chunks = {name: list(v.chunk(world)) for name, v in fixed_views.items()}
         assert slab_range == (rank * (nv_total // world), (rank + 1) * (nv_total // world))
         density_mode = "reduce-scatter onto the Poisson slabs (density and rho finalised on the owned planes only)"
+    comm_stream = torch.cuda.Stream(device=local) if world > 1 else None
     setup_s = time.time() - t0
 
     counts = {}
@@ -249,32 +250,36 @@ def run_ours(args):
         if mcc is not None:
             mcc.apply(wl["dt"])
             t0 = stamp("mcc", t0)
+        pending = []
         for sp in order:
+            if sp is ele:
+                sp.advanceElectrons(wl["dt"])
+            else:
+                sp.advanceNonElectron(neu, neu, wl["dt"])
             if world == 1:
-                if sp is ele:
-                    sp.advanceElectrons(wl["dt"])
-                else:
-                    sp.advanceNonElectron(neu, neu, wl["dt"])
                 sp.computeNumberDensity()
                 sp.computeMacroParticlesCount()
             else:
-                if sp is ele:
-                    sp.advanceElectrons(wl["dt"])
-                else:
-                    sp.advanceNonElectron(neu, neu, wl["dt"])
                 sp.depositPartial()
-                with torch.cuda.stream(stream):
+                sp.computeMacroParticlesCount()
+                # int64 sum over NVLink on a side stream: it overlaps the next species' push; the finalize waits for it below
+                ev = torch.cuda.Event(); ev.record(stream)
+                comm_stream.wait_event(ev)
+                with torch.cuda.stream(comm_stream):
                     if scatter_chunks is not None:                              # each rank only needs the sums on the planes it solves on
                         dist.reduce_scatter_tensor(scatter_chunks[sp.name][rank], fixed_views[sp.name])
                     else:
-                        dist.all_reduce(fixed_views[sp.name])                   # int64 sum over NVLink
-                sp.finalizeDensity(slab_range)
-                sp.computeMacroParticlesCount()
+                        dist.all_reduce(fixed_views[sp.name])
+                    done = torch.cuda.Event(); done.record(comm_stream)
+                pending.append((sp, done))
             if args.moments:
                 sp.sampleMoments()
             if mcc is None and args.sort_every and ts % args.sort_every == 0:
                 sp.sort()
             t0 = stamp("species " + sp.name, t0)
+        for sp, done in pending:
+            stream.wait_event(done)
+            sp.finalizeDensity(slab_range)
         if ts > 5:
             for sp in order:
                 sp.updateAverages()

@@ -373,7 +373,7 @@ int picg_solver_destroy(picg_solver_t s) {
     drop_graphs(s);
     for (int r = 0; r < (int)s->peer_phi.size(); r++) if (r != s->slab_rank) { cudaIpcCloseMemHandle(s->peer_phi[r]); cudaIpcCloseMemHandle(s->peer_mbox[r]); }
     cudaFree(s->peer_phi_dev); cudaFree(s->peer_mbox_dev); cudaFree(s->mbox);
-    cudaFree(s->partial); cudaFree(s->cls); cudaFree(s->rho_split); delete s; return PICG_OK;
+    cudaFree(s->partial); cudaFree(s->cls); cudaFree(s->rho_split); cudaFree(s->pcg_work); delete s; return PICG_OK;
 }
 
 // Slab decomposition over `world` ranks on one node.  (1) every rank exports 128 bytes (the CUDA IPC handles of its phi and of

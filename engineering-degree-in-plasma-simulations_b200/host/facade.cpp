@@ -232,6 +232,15 @@ bool PotentialSolver::solveGS() {
     if (!conv) std::cerr << "GS SOR failed to converge, L2 = " << last_L2 << " tolerance = " << tolerance << " time step = " << world.getTs() << std::endl;   // :162-165
     return conv != 0;
 }
+bool PotentialSolver::solveNRPCG() {                                                                // PotentialSolver.cpp:178-240
+    world.syncToDevice();
+    int conv = 0; unsigned nr = 0, pcg = 0; double norm = 0;
+    check(picg_solver_solve_nrpcg(handle.get(), 1, PCG_max_solver_it, &conv, &nr, &pcg, &norm));
+    world.deviceChanged(PICG_F_PHI);
+    last_iterations = pcg; last_L2 = norm;
+    if (!conv) std::cerr << "NR+PCG failed to converge, norm = " << norm << " tolerance = " << 1e-3 << " time step = " << world.getTs() << std::endl;   // :236-238
+    return conv != 0;
+}
 void PotentialSolver::computeEF() { world.syncToDevice(); check(picg_solver_compute_ef(handle.get())); world.deviceChanged(PICG_F_EF); }
 std::ostream& operator<<(std::ostream& out, SolverType& t) { return out << (t == GS ? "GS" : t == PCG ? "PCG" : "QN"); }
 std::istream& operator>>(std::istream& in, SolverType& t) {

@@ -376,6 +376,13 @@ class PotentialSolver:
     def iterate(self, n):
         _chk(lib().picg_solver_iterate(self.h, C.c_uint(int(n))))
 
+    def solveNRPCG(self, xz_swap=True):
+        """PotentialSolver::solveNRPCG (ch4/v3/src/PotentialSolver.cpp:178-240); xz_swap=True is the reference's matrix (SURVEY B1)."""
+        conv, nr, pcg, norm = C.c_int(0), C.c_uint(0), C.c_uint(0), C.c_double(0)
+        _chk(lib().picg_solver_solve_nrpcg(self.h, int(bool(xz_swap)), C.c_uint(0), C.byref(conv), C.byref(nr), C.byref(pcg), C.byref(norm)))
+        self.nr_iterations, self.pcg_iterations, self.norm = nr.value, pcg.value, norm.value
+        return bool(conv.value)
+
     def residual(self):
         l2 = C.c_double(0)
         _chk(lib().picg_solver_residual(self.h, C.byref(l2)))

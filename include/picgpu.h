@@ -193,6 +193,11 @@ PICG_API int picg_solver_iterate(picg_solver_t s, unsigned n);
 PICG_API int picg_solver_residual(picg_solver_t s, double* L2);
 /* computeEF  PotentialSolver.cpp:354-408 */
 PICG_API int picg_solver_compute_ef(picg_solver_t s);
+/* PotentialSolver::solveNRPCG  PotentialSolver.cpp:178-240 (Newton-Raphson, <= 20 steps, NR_TOL 1e-3) with solvePCGlinear :242-313
+ * (Jacobi-preconditioned CG, <= pcg_max_it iterations, vec::norm(g) < tol) and the solveGSlinear fallback :315-347, matrix-free on the
+ * device.  xz_swap != 0 reproduces buildMatrix's REGULAR rows as written (inv_d2z on the i-neighbours, inv_d2x on the k-neighbours,
+ * :457-463: the reference's PCG results on meshes with dx != dz); 0 uses the operator solveGS relaxes.  Single GPU only. */
+PICG_API int picg_solver_solve_nrpcg(picg_solver_t s, int xz_swap, unsigned pcg_max_it /* 0: the solver's max_it; the GS fallback gets 20x */, int* converged, unsigned* nr_iterations, unsigned* pcg_iterations, double* norm);
 /* multi-GPU (one process per GPU, one node): split the planes of the slowest index over `world` ranks.  Halo planes, the
  * residual sum and the final all-gather of phi go through peer memory (CUDA IPC over NVLink), inside the sweep kernels.
  * export: 128 bytes per rank (IPC handles of phi and of the mailbox); the caller all-gathers them and passes the table of

@@ -228,6 +228,10 @@ class PotentialSolver:
     def solveGS(self):
         return bool(lib().refv3_solver_solve_gs(_h(self.h)))
 
+    def solve(self):
+        """PotentialSolver::solve(): dispatches on the solver type (PCG -> solveNRPCG, v3/PotentialSolver.cpp:55-67)."""
+        return bool(lib().refv3_solver_solve(_h(self.h)))
+
     def computeEF(self):
         lib().refv3_solver_compute_ef(_h(self.h))
 
