@@ -1,0 +1,71 @@
+"""BASELINE config 2 end to end: the ch3 ion beam past a charged sphere with Boltzmann electrons (ch3/v1/main.cpp:48-110),
+on a coarser mesh and with the beam column pre-filled (the reference needs 170 steps to bring it to the sphere), against the compiled
+reference step by step.
+
+Loop per step (ch3/v1/main.cpp:88-101): inject the beam on the z- face -> push (kick, drift, delete in the sphere / out of
+bounds) -> number density -> charge density -> non-linear Poisson (n0 exp((phi-phi0)/Te0) electrons, GS/SOR) -> E.
+The source's random positions are drawn once with numpy and handed to both sides through addParticle (filter + half-step
+rewind), so the run is deterministic.  The reference sweeps lexicographically and the device red-black: both are run to a
+tight residual and share the fixed point, hence the north-star bound (1e-6 relative) instead of bit equality.
+"""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = [pytest.mark.gpu, pytest.mark.reference]
+
+NI, NJ, NK = 21, 21, 41
+X0, XM = np.array([-0.1, -0.1, 0.0]), np.array([0.1, 0.1, 0.4])
+DT, STEPS, PER_STEP, PREFILL = 1e-7, 12, 400, 20000
+MPW0, NDI, V_DRIFT = 4e2, 1e10, 7000.0
+
+
+def _build(mod):
+    w = util.build_world(mod.World, NI, NJ, NK, X0, XM, spheres=[((0.0, 0.0, 0.15), -100.0, 0.05)], dt=DT, num_ts=400)
+    sp = mod.Species("O+", 16 * util.AMU, util.QE, w, MPW0)
+    return w, sp
+
+
+def _batches():
+    rng = np.random.default_rng(2024)
+    out = []
+    for step in range(STEPS):
+        n = PER_STEP + (PREFILL if step == 0 else 0)
+        b = np.zeros((n, 7))
+        b[:, 0] = X0[0] + rng.random(n) * (XM[0] - X0[0]); b[:, 1] = X0[1] + rng.random(n) * (XM[1] - X0[1]); b[:, 2] = X0[2]
+        if step == 0:                                        # the beam column that 170 steps of injection would have built: it reaches into the sphere
+            b[PER_STEP:, 2] = rng.random(PREFILL) * 0.12     # (candidates inside the sphere are rejected by addParticle, Species.cpp:424-428)
+        b[:, 5] = V_DRIFT; b[:, 6] = MPW0
+        out.append(b)
+    return out
+
+
+def test_ch3_beam_past_sphere_matches_reference(picgpu, ref):
+    pg = picgpu
+    wr, ir = _build(ref); wg, ig = _build(pg)
+    sr = ref.PotentialSolver(wr, 20000, 1e-9, ref.PotentialSolver.GS); sr.setReferenceValues(0.0, NDI, 1.5)
+    sg = pg.PotentialSolver(wg, 20000, 1e-9); sg.setReferenceValues(0.0, NDI, 1.5)
+    assert sr.solveGS() and sg.solveGS()                     # main.cpp:82-83
+    sr.computeEF(); sg.computeEF()
+    assert util.norm_err(wg.phi, wr.get(0)) < 1e-6
+    for b in _batches():
+        for row in b:
+            ir.addParticle(row)                              # ColdBeamSource::sample -> Species::addParticle
+        ig.addParticles(b)
+        ir.advanceElectrons(DT); ig.advanceElectrons(DT)     # == ch3 Species::advance (ch3/v1/Species.cpp:28-45)
+        ir.computeNumberDensity(); ig.computeNumberDensity()
+        wr.computeChargeDensity([ir]); wg.computeChargeDensity([ig])
+        assert sr.solveGS() and sg.solveGS()
+        sr.computeEF(); sg.computeEF()
+    pr, pgp = util.sort_rows(ir.getParticles()), util.sort_rows(ig.getParticles())
+    assert 0.5 * (PREFILL + STEPS * PER_STEP) < len(pr) < PREFILL + STEPS * PER_STEP - 100     # the sphere rejected / absorbed some
+    assert abs(len(pr) - len(pgp)) <= 2                      # a particle grazing a surface may fall on either side at 1e-9
+    assert util.norm_err(wg.phi, wr.get(0)) < 1e-6
+    assert util.norm_err(wg.ef, wr.get(3)) < 1e-5
+    assert util.norm_err(ig.den, ir.get(0)) < 1e-5
+    if len(pr) == len(pgp):
+        scale = np.array([0.2, 0.2, 0.4, V_DRIFT, V_DRIFT, V_DRIFT, MPW0])
+        assert np.max(np.abs(pr - pgp) / scale) < 1e-6
+    for o in (ir, sr, wr, ig, sg, wg):
+        o.close()
