@@ -217,6 +217,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return int(t.item())
 
+    def reduce_max(v):
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for sp in order:
         sp.computeNumberDensity()
         sp.setDensityScale(mg.common_scale(sp.densityScale(), world, reduce_min))
@@ -248,7 +253,9 @@ def run_ours(args):
             ele.addParticles(inject)
             t0 = stamp("inject", t0)
         if mcc is not None:
-            mcc.apply(wl["dt"])
+            st = mcc.apply(wl["dt"])
+            if world > 1:                                   # the acceptance ceiling must be the same on every rank
+                mcc.setWsvMax(mg.common_ceiling(st.w_sigma_v_max, reduce_max))
             t0 = stamp("mcc", t0)
         pending = []
         for sp in order:
@@ -362,6 +369,7 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     per_rank_counts = {sp.name: sp.getNumParticles() for sp in order}
+    part_sizes = {sp.name: sp.partitionSize() for sp in order}
     nv = m ** 3
     kernels = {}
     for name, (tot_ms, n_l) in kt.items():
@@ -379,10 +387,14 @@ def run_ours(args):
         elif name in ALG_BYTES_PER_NODE:
             alg = ALG_BYTES_PER_NODE[name] * nv
         if name == "deposit_density":
-            # a deposit may take two launches (cell-partition kernel + thread-run kernel on the appended tail): account per step
-            alg_step = 32 * float(sum(per_rank_counts.values()))
+            # the cell-group kernel, one launch per species and step, over the part of the store the cell partition covers; the
+            # particles appended since the last sort are deposited by the thread-run kernel ("deposit_tail", timed on its own)
+            covered = {k: min(per_rank_counts[k], part_sizes[k]) if part_sizes[k] else per_rank_counts[k] for k in per_rank_counts}
+            alg_step = 32 * float(sum(covered.values()))
             entry["alg_GB_per_step"] = round(alg_step / 1e9, 4)
             alg = alg_step * args.steps / n_l                                      # average per launch, for the common fields below
+        if name == "deposit_tail":
+            alg = 32 * float(sum(max(per_rank_counts[k] - part_sizes[k], 0) for k in per_rank_counts if part_sizes[k])) * args.steps / n_l
         if alg:
             entry["alg_GB_per_launch"] = round(alg / 1e9, 4)
             entry["GBps"] = round(alg / (avg * 1e-3) / 1e9, 1)
@@ -392,17 +404,18 @@ def run_ours(args):
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this workload (profiles/capture.sh ->
     # profiles/ncu_traffic.py); only quoted when the run IS that workload (same mesh, particle count, one GPU)
     traffic, traffic_src = None, None
-    ncu_names = {"push_heavy": "k_run<1, 1, 0, 0, 0>", "push_neutral": "k_run<1, 1, 0, 0, 1>", "push_electrons": "k_run<1, 0, 0, 0, 0>", "sor_redblack": "k_sor_row"}
+    ncu_names = {"deposit_density": "k_cell_deposit", "push_heavy": "k_run<1, 1, 0, 0, 0>", "push_neutral": "k_run<1, 1, 0, 0, 1>", "push_electrons": "k_run<1, 0, 0, 0, 0>", "sor_redblack": "k_sor_row"}
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1b.json")))
         if world == 1 and m == 256 and abs(args.particles - 1e9) < 1 and dom in ncu_names:
-            ent = tj["kernels"][ncu_names[dom]]
+            ent = [e for k, v in tj["kernels"].items() if k.startswith(ncu_names[dom]) for e in v]    # deposit: all lane-group variants
             traffic = float(np.mean([e["dram_bytes"] for e in ent]))
-            traffic_src = "profiles/ncu_traffic_r1.json (%s, mean of %d captured launches)" % (ncu_names[dom], len(ent))
+            traffic_src = "profiles/ncu_traffic_r1b.json (%s, mean of %d captured launches)" % (ncu_names[dom], len(ent))
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac_of_peak"],
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "alg_bytes_per_launch": kernels[dom]["alg_GB_per_launch"] * 1e9}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "alg_bytes_per_launch": kernels[dom]["alg_GB_per_launch"] * 1e9,
+                "note": "peak is the measured COPY bandwidth (1 read : 1 write); a stream that reads more than it writes can exceed it (push_neutral reads 48 B and writes 24 B per particle)"}
     poisson_ms = sum(kernels[k]["ms_total"] for k in ("sor_redblack", "sor_tiled", "residual_l2", "compute_ef") if k in kernels) / args.steps
 
     # ---- end to end through the C ABI with host buffers (pinned): inject + diagnostics + rho download every step

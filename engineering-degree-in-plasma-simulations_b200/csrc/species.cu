@@ -202,6 +202,12 @@ int picg_species_reserve(picg_species_t s, size_t capacity) {
     return species_ensure_capacity(s, capacity);
 }
 
+int picg_species_partition_size(picg_species_t s, size_t* n) {
+    REQUIRE_ARG(s && n, "picg_species_partition_size: null argument");
+    *n = s->part_valid ? s->part_n : 0;
+    return PICG_OK;
+}
+
 int picg_species_count(picg_species_t s, size_t* n) {
     REQUIRE_DEVICE(); REQUIRE_ARG(s && n, "picg_species_count: null argument");
     int rc = species_refresh_count(s);

@@ -263,8 +263,9 @@ int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals
         case 1:  rc = launch_variant<true, false, false, false>(g, A, H, nu, K_PUSH_ELECTRONS); break;
         case 3:  rc = (A.qm_dt == 0.0 && !no_drift_path) ? launch_variant<true, true, false, false, true>(g, A, H, nu, K_PUSH_NEUTRAL)
                                                           : launch_variant<true, true, false, false>(g, A, H, nu, K_PUSH_HEAVY); break;
-        case 4:  rc = launch_variant<false, false, true, false>(g, A, H, nu, K_DEPOSIT); break;
-        case 12: rc = launch_variant<false, false, true, true>(g, A, H, nu, K_DEPOSIT); break;
+        // the thread-run kernel on the tail appended beyond the cell partition is timed on its own (the cell-group kernel did the rest)
+        case 4:  rc = launch_variant<false, false, true, false>(g, A, H, nu, A.tail_from ? K_DEPOSIT_TAIL : K_DEPOSIT); break;
+        case 12: rc = launch_variant<false, false, true, true>(g, A, H, nu, A.tail_from ? K_DEPOSIT_TAIL : K_DEPOSIT); break;
         case 8:  rc = launch_variant<false, false, false, true>(g, A, H, nu, K_COUNT_CELLS); break;
         case 5:  rc = launch_variant<true, false, true, false>(g, A, H, nu, K_PUSH_DEPOSIT); break;
         case 13: rc = launch_variant<true, false, true, true>(g, A, H, nu, K_PUSH_DEPOSIT); break;

@@ -4,7 +4,8 @@ Partitioning: particles are split evenly by index across the G ra
 deposits its particles into a full-grid int64 fixed-point accumulator; the accumulators are summed with one all-reduce
 per species (NCCL over NVLink on the GPU box, gloo in the CPU tests) and only then turned into densities.  Because the
 accumulators are integers, the reduced grid is bit-identical to a single-GPU deposit of all particles, for any G and any
-reduction order.  Poisson is solved redundantly; Monte-Carlo collisions stay per rank with the candidate count scaled by G.
+reduction order.  Poisson is solved on slabs (csrc/poisson.cu) or redundantly; Monte-Carlo collisions stay per rank, a cell's
+candidates are dealt out to the ranks (candidate_share).
 
 This module holds the host-side rules that must agree on every rank; it contains no compute.
 """
@@ -23,10 +24,20 @@ def common_scale(S_local, world, reduce_min):
     return int(reduce_min(int(S_local))) - int(math.ceil(math.log2(world))) if world > 1 else int(S_local)
 
 
-def mcc_candidate_scale(world):
-    """MC ionisation runs on each rank's own particles; the per-cell candidate count is bilinear in the local counts, so it
-    is multiplied by G to keep the collision frequency unbiased (csrc/mcc.cu rank_scale)."""
-    return float(world)
+def candidate_share(frac_local, cell, call, rank, world):
+    """Monte-Carlo candidates rank `rank` tries in `cell` (csrc/mcc.cu, csrc/dsmc.cu use the same rule).  Cells are not owned by a
+    GPU: the cell's candidate count is estimated from the LOCAL populations (frac_local is the reference's
+    expression on them, bilinear in the counts, hence x G^2), rounded once with the reference's int(x + 0.5)
+    (Interactions.cpp:646-647) and dealt out: n // G to every rank, the n % G left over to a subset that rotates with the cell
+    and the call number.  Rounding each rank's share instead would drop every cell whose share is below one half."""
+    n_tot = int(frac_local * world * world + 0.5)
+    return n_tot // world + (1 if (cell + call + rank) % world < n_tot % world else 0)
+
+
+def common_ceiling(value, reduce_max):
+    """W_sigma_v_rel_max / sigma_v_rel_max must be the same on every rank (it normalises the acceptance probability): the
+    all-reduce(MAX) of the per-rank values after every apply.  reduce_max(float) -> float."""
+    return float(reduce_max(float(value)))
 
 
 class CudaArray:

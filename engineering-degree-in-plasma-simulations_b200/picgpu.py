@@ -220,6 +220,11 @@ class Species:
     def reserve(self, n):
         _chk(lib().picg_species_reserve(self.h, C.c_size_t(int(n))))
 
+    def partitionSize(self):
+        n = C.c_size_t(0)
+        _chk(lib().picg_species_partition_size(self.h, C.byref(n)))
+        return n.value
+
     def getNumParticles(self):
         n = C.c_size_t(0)
         _chk(lib().picg_species_count(self.h, C.byref(n)))

@@ -107,6 +107,9 @@ PICG_API int picg_world_device_ptr(picg_world_t w, int field, void** dptr, size_
 PICG_API int picg_species_create(picg_world_t w, double mass, double charge, double mpw0, picg_species_t* out);
 PICG_API int picg_species_destroy(picg_species_t s);
 PICG_API int picg_species_reserve(picg_species_t s, size_t capacity);
+/* number of leading store slots the cell partition of the last sort covers (0: none); particles appended since lie beyond it and
+ * take the generic deposit kernel ("deposit_tail" in the timers).  Diagnostics for bench.py's byte accounting. */
+PICG_API int picg_species_partition_size(picg_species_t s, size_t* n);
 /* Species::getNumParticles  Species.cpp:44-46 */
 PICG_API int picg_species_count(picg_species_t s, size_t* n);
 /* raw store access == Species::getPartRef() / getConstPartRef()  Species.cpp:820-828 */

@@ -69,4 +69,18 @@ def test_rank_rules():
     assert mg.common_scale(20, 1, lambda v: v) == 20
     assert mg.common_scale(20, 8, lambda v: v - 1) == 16    # min over ranks (19) minus log2(8)
     assert mg.common_scale(20, 3, lambda v: v) == 18
-    assert mg.mcc_candidate_scale(8) == 8.0
+    assert mg.common_ceiling(0.25, lambda v: max(v, 0.5)) == 0.5
+
+
+def test_candidate_shares_add_up_to_the_single_rank_count():
+    """The device rule of csrc/mcc.cu / dsmc.cu, restated in multigpu.candidate_share: with equal local populations the ranks'
+    shares add up to the reference's rounded count on the whole cell, for any world size, cell and call number."""
+    mg = importlib.import_module(PKG + ".multigpu")
+    rng = np.random.default_rng(1)
+    for world in (1, 2, 3, 4, 8):
+        for frac_total in list(rng.uniform(0.0, 6.0, 40)) + [0.49, 0.5, 0.51, 1.5, 7.5]:
+            frac_local = frac_total / (world * world)            # bilinear in the local counts: (np_n/G)(np_e/G)
+            for cell, call in ((0, 1), (5, 2), (123456, 77)):
+                shares = [mg.candidate_share(frac_local, cell, call, r, world) for r in range(world)]
+                assert sum(shares) == int(frac_local * world * world + 0.5)
+                assert max(shares) - min(shares) <= 1
