@@ -1,4 +1,4 @@
-"""SOR half-sweep micro-benchmark at 256^3 (scratch tool): python scratch/sor_bench.py [iterations]"""
+"""SOR half-sweep micro-benchmark at 256^3 (scratch tool): python profiles/sor_bench.py [iterations]"""
 import sys, importlib, os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import bench
