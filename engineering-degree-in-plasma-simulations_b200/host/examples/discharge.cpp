@@ -25,6 +25,7 @@ int main(int argc, char* argv[]) {
     unsigned seed = parseArgument(args, "--seed", 1234u);
     int n_ele = parseArgument(args, "--electrons", 20000);
     std::string table = parseArgument(args, "--table", std::string("data/Oxygen_momentum_transfer.txt"));
+    bool extras = parseArgument(args, "--extras", false);      // after the loop: DSMC_MEX, binary field output, checkpoint round trip, NR-PCG
     rnd = Rnd(seed);
 
     std::unique_ptr<World> world = std::make_unique<World>(21, 21, 31, type_calc3{-0.004, -0.004, 0.0}, type_calc3{0.004, 0.004, 0.005});
@@ -74,6 +75,28 @@ int main(int argc, char* argv[]) {
         std::cout << "STEP " << world->getTs();
         for (Species& sp : species) std::cout << " " << sp.name << " " << sp.getNumParticles() << " " << std::setprecision(17) << sp.getKE();
         std::cout << " PE " << world->getPE() << " phi_mid " << world->phi[10][10][15] << " rho_mid " << world->rho[10][10][15] << " it " << solver.iterations() << "\n";
+    }
+    if (extras) {
+        // neutral-neutral collisions (the ch4/v2-SPHERE interaction, ch4/v2/main.cpp:266)
+        DSMC_MEX dsmc(neutral_oxygen, *world);
+        type_calc ke0 = neutral_oxygen.getKE();
+        dsmc.apply(1e-6);
+        std::cout << "EXTRA dsmc candidates " << dsmc.stats().candidates << " collisions " << dsmc.stats().collisions << " ke_ratio " << std::setprecision(17)
+                  << neutral_oxygen.getKE() / ke0 << "\n";
+        // binary .vti (needs results/, like the reference) and a checkpoint round trip
+        Output::fieldsOutput(*world, species, "extra_");
+        std::vector<size_t> before; for (Species& sp : species) before.push_back(sp.getNumParticles());
+        type_calc phi_mid = world->phi[10][10][15];
+        bool ok = Output::saveCheckpoint("results/run.ckp", *world, species);
+        electrons.advanceElectrons(dt);                         // change the state, then restore it
+        world->phi = 0;
+        ok = ok && Output::loadCheckpoint("results/run.ckp", *world, species);
+        bool same = true; for (size_t k = 0; k < species.size(); k++) same = same && species[k].getNumParticles() == before[k];
+        std::cout << "EXTRA checkpoint ok " << ok << " counts_restored " << same << " phi_restored " << (world->phi[10][10][15] == phi_mid) << "\n";
+        // the reference's other solver
+        PotentialSolver pcg(*world, 500, 1e-4, PCG);
+        pcg.setReferenceValues(0, 0, 1e20);
+        std::cout << "EXTRA nrpcg converged " << pcg.solveNRPCG() << " phi_mid " << world->phi[10][10][15] << "\n";
     }
     std::cout << "Simulation took " << world->getWallTime() << " seconds." << std::endl;
     return 0;

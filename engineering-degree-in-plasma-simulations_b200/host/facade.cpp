@@ -344,6 +344,7 @@ static bool checkpoint_io(bool save, const std::string& path, World& world, std:
     std::vector<picg_species_t> hs; for (Species& sp : species) hs.push_back(sp.dev());
     picg_checkpoint_set set{}; set.world = world.dev(); set.species = hs.data(); set.n_species = (int)hs.size();
     uint64_t ts = (uint64_t)world.getTs();
+    world.syncToDevice();                                      // pending host-side edits of phi / rho / ef go to the device first (save: they belong to the state; load: they are overwritten)
     int rc = save ? picg_checkpoint_save(path.c_str(), &set, ts) : picg_checkpoint_load(path.c_str(), &set, &ts);
     if (rc != PICG_OK) { std::cerr << (save ? "saveCheckpoint: " : "loadCheckpoint: ") << picg_last_error() << std::endl; return false; }
     if (!save) {

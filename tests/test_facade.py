@@ -144,3 +144,24 @@ def test_reference_main_runs_on_the_device():
     assert len(diag) == 1 + 13                                            # header + num_ts+1 steps
     last = diag[-1].split(",")
     assert int(last[0]) == 12 and np.isfinite([float(x) for x in last[1:]]).all()
+
+
+@pytest.mark.gpu
+def test_example_extras_dsmc_vti_checkpoint_nrpcg():
+    """The C++ facade paths of the SURVEY 8f rows at run time: DSMC_MEX::apply, Output::fieldsOutput (binary .vti),
+    Output::saveCheckpoint / loadCheckpoint, PotentialSolver::solveNRPCG."""
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "results"))
+        out = subprocess.run([EXAMPLE, "--num_ts", "2", "--electrons", "20000", "--seed", "5", "--dt", "2e-11", "--table", "/nonexistent/table.txt", "--extras", "1"],
+                             cwd=d, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        extra = {l.split()[1]: l.split()[2:] for l in out.stdout.splitlines() if l.startswith("EXTRA")}
+        vti = [f for f in os.listdir(os.path.join(d, "results")) if f.endswith(".vti")]
+        assert vti and os.path.getsize(os.path.join(d, "results", vti[0])) > 21 * 21 * 31 * 8 * 10       # binary arrays, not an empty shell
+        head = open(os.path.join(d, "results", vti[0]), "rb").read(4000).decode(errors="replace")
+        assert 'Name="nd.O+"' in head and 'format="appended"' in head
+        assert os.path.getsize(os.path.join(d, "results", "run.ckp")) > 2e5 * 56
+    assert int(extra["dsmc"][1]) > 0 and 0 < int(extra["dsmc"][3]) <= int(extra["dsmc"][1])
+    assert abs(float(extra["dsmc"][5]) - 1.0) < 1e-9                                                      # elastic collisions keep the kinetic energy
+    assert extra["checkpoint"] == ["ok", "1", "counts_restored", "1", "phi_restored", "1"]
+    assert extra["nrpcg"][1] == "1"
