@@ -175,16 +175,40 @@ def run_ours(args):
     cold = pg.PotentialSolver(w, args.init_max_it, args.s_tol)   # initial vacuum solve (main.cpp:172-173)
     cold.setReferenceValues(0.0, 0.0, 1e20)
     poisson_mode = "replicated"
+    poisson_probe = None
     if world > 1 and args.poisson in ("auto", "slab"):
         def all_gather_bytes(b):
             t = torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
             out = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(out, t)
             return [o.cpu().numpy().tobytes() for o in out]
+
+        def probe(solver, iters=20):
+            """ms per SOR iteration of `solver`, device-timed, max over ranks (every rank must take the same decision)."""
+            solver.iterate(4)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            pg.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            e0.record(stream); solver.iterate(iters); e1.record(stream); pg.synchronize(); torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
         try:
-            cold.enableSlabs(rank, world, all_gather_bytes)
-            sol.enableSlabs(rank, world, all_gather_bytes)
-            poisson_mode = "slab (planes of i split over %d ranks; halos, residual sum and all-gather through NVLink peer memory)" % world
+            use_slabs = True
+            if args.poisson == "auto":
+                # north star: "solved either redundantly or slab-decomposed, whichever is faster at the given mesh size": measure both
+                # (the probe iterations are iterations of the initial vacuum solve, nothing is thrown away)
+                rep = pg.PotentialSolver(w, args.init_max_it, args.s_tol); rep.setReferenceValues(0.0, 0.0, 1e20)
+                slb = pg.PotentialSolver(w, args.init_max_it, args.s_tol); slb.setReferenceValues(0.0, 0.0, 1e20)
+                slb.enableSlabs(rank, world, all_gather_bytes)
+                poisson_probe = {"replicated_ms_per_iteration": round(probe(rep), 4), "slab_ms_per_iteration": round(probe(slb), 4)}
+                use_slabs = poisson_probe["slab_ms_per_iteration"] < poisson_probe["replicated_ms_per_iteration"]
+                rep.close(); slb.close()
+            if use_slabs:
+                cold.enableSlabs(rank, world, all_gather_bytes)
+                sol.enableSlabs(rank, world, all_gather_bytes)
+                poisson_mode = "slab (planes of i split over %d ranks; halos, residual sum and all-gather through NVLink peer memory)" % world
+            else:
+                poisson_mode = "replicated (measured faster than slabs at this mesh size)"
         except pg.PicgError as e:                              # no peer access on this node: every rank solves the whole grid
             if args.poisson == "slab":
                 raise
@@ -454,7 +478,7 @@ def run_ours(args):
                "config": {"workload": "synthetic %d^3 mesh, %.3g macro-particles (O/O+/e- = 2:1:1), full PIC-DSMC step, Poisson live" % (m, args.particles),
                           "mesh": [m, m, m], "particles_global": int(n_avg), "species": {k: int(v) for k, v in per_rank_counts.items()},
                           "steps_per_sort": 1 if mcc else args.sort_every, "mcc": mcc is not None, "moments": bool(args.moments),
-                          "poisson": {"max_it": args.s_max_it, "tol": args.s_tol, "mode": poisson_mode, "iterations_per_step": its / args.steps,
+                          "poisson": {"max_it": args.s_max_it, "tol": args.s_tol, "mode": poisson_mode, "probe": poisson_probe, "iterations_per_step": its / args.steps,
                                       "initial_solve_iterations": init_iters},
                           "parallelism": "particles split by index over %d GPU(s); int64 density %s; Poisson %s" % (world, density_mode if world > 1 else "on one GPU", poisson_mode.split(" ")[0]),
                           "l2_policy": "inputs larger than L2 (%.1f GB of particle arrays per GPU vs 126 MB L2)" % (sum(per_rank_counts.values()) * 56 / 1e9)},
