@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--poisson", choices=["auto", "replicated", "slab"], default="auto",
                     help="multi-GPU solve: every rank solves the whole grid, or planes split over the ranks with peer-memory halos (auto: slab when N > 1)")
     ap.add_argument("--init_max_it", type=int, default=20000, help="iteration cap of the initial vacuum solve (profiling runs use a small value)")
+    ap.add_argument("--subcycled_steps", type=int, default=10, help="steps of the reference's subcycled loop timed after the headline (0: skip)")
     ap.add_argument("--inject", type=int, default=1 << 20, help="e2e: electrons injected from pinned host memory per step")
     return ap.parse_args()
 
@@ -221,7 +222,10 @@ def run_ours(args):
     for s in wl["species"]:
         sp = pg.Species(s["name"], s["mass"], s["charge"], w, s["mpw0"], wl["E_ion"] if s["name"] == "O" else -666.0)
         per_rank = s["count"] // world + 1
-        sp.reserve(int(per_rank * 1.25) + args.inject * (args.steps + args.warmup + 8))       # no store may be re-allocated inside a timed region
+        # no store may be re-allocated inside a timed region: the neutral store grows by the split-off neutrals of the MC collisions
+        # (about 0.5 % per step of this workload), also over the steps of the subcycled loop
+        head = 1.25 + (0.6 if s["name"] == "O" and args.subcycled_steps else 0.0)
+        sp.reserve(int(per_rank * head) + args.inject * (args.steps + args.warmup + 8))
         sp.loadParticleBoxThermal(wl["box_c"], wl["box_s"], s["den"], s["T"])
         sp.sort()
         species[s["name"]] = sp
@@ -270,8 +274,10 @@ def run_ours(args):
             pg.synchronize(); prof[name] = prof.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
         return time.perf_counter()
 
-    def step(ts, inject=None):
-        """One pass of the v3 main-loop body (main.cpp:197-261) through the C ABI."""
+    def step(ts, inject=None, subcycling=False, advanced=None):
+        """One pass of the v3 main-loop body (main.cpp:197-261) through the C ABI.  subcycling: Config::SUBCYCLING of the reference
+        (main.cpp:211-236): electrons every step, ions every 10th step with 10 dt, neutrals every 100th step with 50 dt; a species that is
+        not advanced keeps its density.  advanced: list that receives the species advanced in this step."""
         t0 = time.perf_counter()
         if inject is not None:                              # Source::sample on the host side: H2D of this step's new particles
             ele.addParticles(inject)
@@ -283,10 +289,22 @@ def run_ours(args):
             t0 = stamp("mcc", t0)
         pending = []
         for sp in order:
+            dt_sp = wl["dt"]
+            if subcycling and sp is not ele:
+                if sp.charge != 0:
+                    if ts % 10 != 0:
+                        continue
+                    dt_sp = wl["dt"] * 10
+                else:
+                    if ts % 100 != 0:
+                        continue
+                    dt_sp = wl["dt"] * 50
+            if advanced is not None:
+                advanced.append(sp)
             if sp is ele:
-                sp.advanceElectrons(wl["dt"])
+                sp.advanceElectrons(dt_sp)
             else:
-                sp.advanceNonElectron(neu, neu, wl["dt"])
+                sp.advanceNonElectron(neu, neu, dt_sp)
             if world == 1:
                 sp.computeNumberDensity()
                 sp.computeMacroParticlesCount()
@@ -471,6 +489,40 @@ def run_ours(args):
            "kernel_ms_per_step": kt_e2e, "device_reallocs": int(pg.realloc_count() - reallocs1),
            "what": "C-ABI step with host buffers: H2D of injected electrons (pinned), D2H of per-species counters + diagnostics and of rho every step"}
 
+    # ---- the reference's subcycled loop (Config::SUBCYCLING + MERGING), reported separately: steps ts = 300, 301, ... so that
+    # the window starts with a Species::merge round (main.cpp:179-193: ts > 250 and ts % 50 == 0), an ion push and a neutral push; the default
+    # 10 steps hold 10 electron pushes, 1 ion push, 1 neutral push and 1 merge.  (The window cannot be long: in this synthetic discharge the
+    # electrons gain energy in the 8 kV gap, the MC collision rate rises to 3e7 per step within 30 steps and every non-ionising collision
+    # splits a neutral - the neutral store doubles in 30 steps.)  particle-steps = particles actually advanced
+    subcycled = None
+    if args.subcycled_steps > 0:
+        ts_sub = 300
+        merge_stats = []
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        adv_total = 0
+        ev0.record(stream)
+        for k in range(args.subcycled_steps):
+            adv = []
+            if (ts_sub + k) % 50 == 0:
+                for sp in order:
+                    merge_stats.append((sp.name,) + sp.merge()[:2])
+            step(ts_sub + k, subcycling=True, advanced=adv)
+            adv_total += sum(sp.getNumParticles() for sp in adv)
+            if os.environ.get("PICG_TRACE_SUBCYCLED") and rank == 0 and k % 5 == 0:
+                print("subcycled ts %d: %s mcc %s merges %s" % (ts_sub + k, {sp.name: sp.getNumParticles() for sp in order},
+                      (mcc.stats.candidates, mcc.stats.collisions, mcc.stats.ionizations, mcc.stats.w_sigma_v_max) if mcc else None, merge_stats[-3:]), file=sys.stderr)
+        ev1.record(stream)
+        barrier()
+        ms_sub = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms_sub], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_sub = float(t.item())
+            t = torch.tensor([adv_total], device="cuda", dtype=torch.int64); dist.all_reduce(t); adv_total = int(t.item())
+        subcycled = {"steps": args.subcycled_steps, "ms_per_step": ms_sub / args.subcycled_steps, "value": adv_total / (ms_sub * 1e-3), "unit": "particle-steps/s",
+                     "merges": [{"species": a, "before": int(b), "after": int(c)} for a, b, c in merge_stats],
+                     "what": "Config::SUBCYCLING + MERGING loop of the reference (main.cpp:179-236): electrons every step, ions every 10th (10 dt), neutrals every 100th (50 dt), "
+                             "Species::merge every 50th; MC ionisation, charge density, Poisson and E every step; particle-steps count the particles actually advanced"}
+
     out = None
     if rank == 0:
         out = {"metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -483,7 +535,7 @@ def run_ours(args):
                           "parallelism": "particles split by index over %d GPU(s); int64 density %s; Poisson %s" % (world, density_mode if world > 1 else "on one GPU", poisson_mode.split(" ")[0]),
                           "l2_policy": "inputs larger than L2 (%.1f GB of particle arrays per GPU vs 126 MB L2)" % (sum(per_rank_counts.values()) * 56 / 1e9)},
                "poisson_ms_per_step": poisson_ms, "gpu_launches": int(launches), "device_reallocs_in_timed_region": int(reallocs_timed), "clocks": clk, "roofline": roofline, "kernels": kernels, "e2e": e2e,
-               "setup_s": round(setup_s, 1)}
+               "subcycled": subcycled, "setup_s": round(setup_s, 1)}
         if not args.skip_cpu_baseline:
             out["cpu_baseline"] = cpu_reference_run(args, wl, steps=2, warmup=1)
         print(json.dumps(out))

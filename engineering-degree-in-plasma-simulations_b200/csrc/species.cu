@@ -116,22 +116,27 @@ int species_ensure_capacity(picg_species_s* s, size_t cap) {
     int rc = species_refresh_count(s); if (rc) return rc;
     size_t exact = (cap + 255) & ~(size_t)255;
     size_t newcap = (std::max(cap, s->cap + s->cap / 2) + 255) & ~(size_t)255;
-    double* na[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 7 particle arrays + the sort spare
+    // array by array (allocate, copy, free the old one): the peak is the old store plus ONE new array, not two whole stores
+    cudaStreamSynchronize(g_stream);
     for (int attempt = 0; attempt < 2; attempt++) {
-        cudaError_t e = cudaSuccess;
-        for (int c = 0; c < 8 && e == cudaSuccess; c++) e = cudaMalloc(&na[c], newcap * 8);
+        cudaError_t e = cudaSuccess; int c = 0;
+        for (; c < 8 && e == cudaSuccess; c++) {
+            double*& old = c < 7 ? s->a[c] : s->spare;
+            double* fresh = nullptr;
+            e = cudaMalloc(&fresh, newcap * 8);
+            if (e != cudaSuccess) break;
+            if (c < 7 && s->n_host && old) e = cudaMemcpyAsync(fresh, old, s->n_host * 8, cudaMemcpyDeviceToDevice, g_stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+            if (e != cudaSuccess) { cudaFree(fresh); break; }
+            cudaFree(old); old = fresh;
+        }
         if (e == cudaSuccess) break;
         cudaGetLastError();
-        for (int c = 0; c < 8; c++) { if (na[c]) cudaFree(na[c]); na[c] = nullptr; }
-        if (attempt == 1 || newcap == exact) return cuda_fail(e, "cudaMalloc(particles)", __FILE__, __LINE__);
+        // arrays [0, c) already have the larger size, the rest the old one: the store stays valid at its old capacity
+        if (attempt == 1 || newcap == exact || c > 0)
+            return set_error(PICG_ERR_OOM, "species store cannot grow from %zu to %zu particles (%zu live): %s; reserve the capacity up front (picg_species_reserve)", s->cap, newcap, s->n_host, cudaGetErrorString(e));
         newcap = exact;                                           // retry with the exact request
     }
-    for (int c = 0; c < 7; c++) {
-        if (s->n_host) cudaMemcpyAsync(na[c], s->a[c], s->n_host * 8, cudaMemcpyDeviceToDevice, g_stream);
-    }
-    cudaStreamSynchronize(g_stream);
-    for (int c = 0; c < 7; c++) { cudaFree(s->a[c]); s->a[c] = na[c]; }
-    cudaFree(s->spare); s->spare = na[7];
     note_realloc("particle store", newcap * 64);
     s->cap = newcap;
     // the shared scratch arena is sized for a full store as well (radix sort: 16 B per particle; push: dead / hole lists +

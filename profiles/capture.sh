@@ -3,7 +3,7 @@
 #   profiles/capture.sh <tag> <mesh> <particles>
 TAG=${1:-r1}; MESH=${2:-256}; NP=${3:-1e9}
 OUT=gpurun_out/$TAG; mkdir -p $OUT
-CMD="python bench.py --mesh $MESH --particles $NP --steps 2 --warmup 2 --skip_cpu_baseline --init_max_it 60"
+CMD="python bench.py --mesh $MESH --particles $NP --steps 2 --warmup 2 --skip_cpu_baseline --init_max_it 60 --subcycled_steps 0"
 # (1) every launch with its device time (cold-cache, serialised: compare SHARES, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches.csv $CMD > $OUT/launches.log 2>&1
 python profiles/launch_list.py $OUT/launches.csv "$CMD" > $OUT/launches.md
