@@ -44,14 +44,14 @@ int dev_to_file(Stage& st, const void* dev, size_t bytes) {
         const size_t m = std::min(kStageBytes, bytes - off);
         CUDA_TRY(cudaMemcpyAsync(st.host, (const char*)dev + off, m, cudaMemcpyDeviceToHost, g_stream));
         CUDA_TRY(cudaStreamSynchronize(g_stream));
-        if (fwrite(st.host, 1, m, st.f) != m) return set_error(PICG_ERR_ARG, "write failed (disk full?)");
+        if (fwrite(st.host, 1, m, st.f) != m) return set_error(PICG_ERR_IO, "write failed (disk full?)");
     }
     return PICG_OK;
 }
 int file_to_dev(Stage& st, void* dev, size_t bytes) {
     for (size_t off = 0; off < bytes; off += kStageBytes) {
         const size_t m = std::min(kStageBytes, bytes - off);
-        if (fread(st.host, 1, m, st.f) != m) return set_error(PICG_ERR_ARG, "checkpoint file is truncated");
+        if (fread(st.host, 1, m, st.f) != m) return set_error(PICG_ERR_IO, "checkpoint file is truncated");
         CUDA_TRY(cudaMemcpyAsync((char*)dev + off, st.host, m, cudaMemcpyHostToDevice, g_stream));
         CUDA_TRY(cudaStreamSynchronize(g_stream));
     }
@@ -59,7 +59,7 @@ int file_to_dev(Stage& st, void* dev, size_t bytes) {
 }
 int open_stage(Stage& st, const char* path, const char* mode) {
     st.f = fopen(path, mode);
-    if (!st.f) return set_error(PICG_ERR_ARG, "could not open %s", path);
+    if (!st.f) return set_error(PICG_ERR_IO, "could not open %s", path);
     cudaError_t e = cudaMallocHost(&st.host, kStageBytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost(io stage)", __FILE__, __LINE__);
     return PICG_OK;
@@ -119,7 +119,7 @@ int picg_write_fields_vti(const char* path, picg_world_t w, const picg_species_t
     }
     head += in_cells ? "</CellData>\n" : "</PointData>\n<CellData>\n</CellData>\n";
     head += "</Piece>\n</ImageData>\n<AppendedData encoding=\"raw\">\n_";
-    if (fwrite(head.data(), 1, head.size(), st.f) != head.size()) return set_error(PICG_ERR_ARG, "write failed: %s", path);
+    if (fwrite(head.data(), 1, head.size(), st.f) != head.size()) return set_error(PICG_ERR_IO, "write failed: %s", path);
     double* tmp = (double*)w->scratch;
     for (const VtkArray& a : arr) {
         const int ni = a.cell ? g.ci : g.ni, nj = a.cell ? g.cj : g.nj, nk = a.cell ? g.ck : g.nk;
@@ -129,11 +129,11 @@ int picg_write_fields_vti(const char* path, picg_world_t w, const picg_species_t
         else LAUNCH(K_MISC, k_to_vtk_order, grid, 256, 0, ni, nj, nk, a.comps, a.dptr, tmp);
         CHECK_LAUNCH();
         const uint64_t bytes = (uint64_t)cnt * a.comps * 8;
-        if (fwrite(&bytes, 8, 1, st.f) != 1) return set_error(PICG_ERR_ARG, "write failed: %s", path);
+        if (fwrite(&bytes, 8, 1, st.f) != 1) return set_error(PICG_ERR_IO, "write failed: %s", path);
         rc = dev_to_file(st, tmp, bytes); if (rc) return rc;
     }
     const char tail[] = "\n</AppendedData>\n</VTKFile>\n";
-    if (fwrite(tail, 1, sizeof tail - 1, st.f) != sizeof tail - 1) return set_error(PICG_ERR_ARG, "write failed: %s", path);
+    if (fwrite(tail, 1, sizeof tail - 1, st.f) != sizeof tail - 1) return set_error(PICG_ERR_IO, "write failed: %s", path);
     return PICG_OK;
 }
 
@@ -145,7 +145,7 @@ int picg_checkpoint_save(const char* path, const picg_checkpoint_set* set, uint6
     memcpy(h.magic, kMagic, 8); h.version = 1; h.user_ts = user_ts; h.seed = g_seed;
     h.ni = g.ni; h.nj = g.nj; h.nk = g.nk; for (int c = 0; c < 3; c++) { h.x0[c] = g.x0[c]; h.xm[c] = g.xm[c]; } h.dt = w->dt;
     h.n_species = (uint32_t)set->n_species; h.n_mcc = (uint32_t)set->n_mcc; h.n_dsmc = (uint32_t)set->n_dsmc; h.n_sources = (uint32_t)set->n_sources;
-    if (fwrite(&h, sizeof h, 1, st.f) != 1) return set_error(PICG_ERR_ARG, "write failed: %s", path);
+    if (fwrite(&h, sizeof h, 1, st.f) != 1) return set_error(PICG_ERR_IO, "write failed: %s", path);
     rc = dev_to_file(st, w->phi, nv * 8); if (rc) return rc;
     rc = dev_to_file(st, w->rho, nv * 8); if (rc) return rc;
     rc = dev_to_file(st, w->ef, nv * 24); if (rc) return rc;
@@ -157,7 +157,7 @@ int picg_checkpoint_save(const char* path, const picg_checkpoint_set* set, uint6
         r.n = s->n_host; r.mass = s->mass; r.charge = s->charge; r.mpw0 = s->mpw0; r.S = s->S; r.avg_samples = s->avg_samples;
         r.S_pinned = s->S_pinned; r.S_calibrated = s->S_calibrated;
         r.n_load_calls = s->n_load_calls; r.n_heavy_calls = s->n_heavy_calls; r.n_merge_calls = s->n_merge_calls;
-        if (fwrite(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_ARG, "write failed: %s", path);
+        if (fwrite(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_IO, "write failed: %s", path);
         for (int c = 0; c < 7; c++) { rc = dev_to_file(st, s->a[c], (size_t)r.n * 8); if (rc) return rc; }
         const double* f1[] = {s->den, s->den_avg, s->n_sum, s->nuu, s->nvv, s->nww};
         for (const double* f : f1) { rc = dev_to_file(st, f, nv * 8); if (rc) return rc; }
@@ -166,16 +166,16 @@ int picg_checkpoint_save(const char* path, const picg_checkpoint_set* set, uint6
     for (int k = 0; k < set->n_mcc; k++) {
         CkpScalar r; r.step = set->mcc[k]->step;
         CUDA_TRY(cudaMemcpyAsync(&r.value, set->mcc[k]->wsv, 8, cudaMemcpyDeviceToHost, g_stream)); CUDA_TRY(cudaStreamSynchronize(g_stream));
-        if (fwrite(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_ARG, "write failed: %s", path);
+        if (fwrite(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_IO, "write failed: %s", path);
     }
     for (int k = 0; k < set->n_dsmc; k++) {
         CkpScalar r; r.step = set->dsmc[k]->step;
         CUDA_TRY(cudaMemcpyAsync(&r.value, set->dsmc[k]->svm, 8, cudaMemcpyDeviceToHost, g_stream)); CUDA_TRY(cudaStreamSynchronize(g_stream));
-        if (fwrite(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_ARG, "write failed: %s", path);
+        if (fwrite(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_IO, "write failed: %s", path);
     }
     for (int k = 0; k < set->n_sources; k++) {
         CkpScalar r; r.value = 0; r.step = set->sources[k]->step;
-        if (fwrite(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_ARG, "write failed: %s", path);
+        if (fwrite(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_IO, "write failed: %s", path);
     }
     return PICG_OK;
 }
@@ -200,7 +200,7 @@ int picg_checkpoint_load(const char* path, const picg_checkpoint_set* set, uint6
         picg_species_s* s = set->species[k];
         REQUIRE_ARG(s && s->w == w, "picg_checkpoint_load: species of another world");
         CkpSpecies r;
-        if (fread(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_ARG, "checkpoint file is truncated");
+        if (fread(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_IO, "checkpoint file is truncated");
         if (r.mass != s->mass || r.charge != s->charge || r.mpw0 != s->mpw0) return set_error(PICG_ERR_ARG, "checkpoint species %d has other mass / charge / mpw0 than the species passed", k);
         rc = species_ensure_capacity(s, (size_t)r.n); if (rc) return rc;
         for (int c = 0; c < 7; c++) { rc = file_to_dev(st, s->a[c], (size_t)r.n * 8); if (rc) return rc; }
@@ -216,17 +216,17 @@ int picg_checkpoint_load(const char* path, const picg_checkpoint_set* set, uint6
         s->sorted_valid = false; s->part_valid = false; s->lists_valid = false; s->count_valid = false; s->movers_fresh = false; s->part_n = 0;
     }
     for (int k = 0; k < set->n_mcc; k++) {
-        CkpScalar r; if (fread(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_ARG, "checkpoint file is truncated");
+        CkpScalar r; if (fread(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_IO, "checkpoint file is truncated");
         set->mcc[k]->step = r.step;
         CUDA_TRY(cudaMemcpyAsync(set->mcc[k]->wsv, &r.value, 8, cudaMemcpyHostToDevice, g_stream)); CUDA_TRY(cudaStreamSynchronize(g_stream));
     }
     for (int k = 0; k < set->n_dsmc; k++) {
-        CkpScalar r; if (fread(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_ARG, "checkpoint file is truncated");
+        CkpScalar r; if (fread(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_IO, "checkpoint file is truncated");
         set->dsmc[k]->step = r.step;
         CUDA_TRY(cudaMemcpyAsync(set->dsmc[k]->svm, &r.value, 8, cudaMemcpyHostToDevice, g_stream)); CUDA_TRY(cudaStreamSynchronize(g_stream));
     }
     for (int k = 0; k < set->n_sources; k++) {
-        CkpScalar r; if (fread(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_ARG, "checkpoint file is truncated");
+        CkpScalar r; if (fread(&r, sizeof r, 1, st.f) != 1) return set_error(PICG_ERR_IO, "checkpoint file is truncated");
         set->sources[k]->step = r.step;
     }
     if (user_ts) *user_ts = h.user_ts;

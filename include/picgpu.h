@@ -42,7 +42,8 @@ typedef enum {
     PICG_ERR_ARG = -3,         /* invalid argument (maps to std::invalid_argument)*/
     PICG_ERR_OOM = -4,         /* device allocation failed                       */
     PICG_ERR_OVERFLOW = -5,    /* fixed-point density accumulator overflowed     */
-    PICG_ERR_STATE = -6        /* call not valid in the current state            */
+    PICG_ERR_STATE = -6,       /* call not valid in the current state            */
+    PICG_ERR_IO = -7           /* a file could not be opened, written or is truncated */
 } picg_status;
 
 typedef struct picg_world_s*   picg_world_t;
