@@ -28,7 +28,8 @@ __host__ __device__ __forceinline__ double dsmc_sigma(const DsmcParams& P, doubl
 // collide (:267-285): isotropic scattering in the centre-of-mass frame
 __device__ __forceinline__ void dsmc_collide(PhiloxStream& r, const DsmcParams& P, double v1[3], double v2[3]) {
     double cm[3], g[3];
-    for (int c = 0; c < 3; c++) { cm[c] = (P.mass1 * v1[c] + P.mass2 * v2[c]) / P.sum_mass; g[c] = v1[c] - v2[c]; }
+    const double inv_sum = 1.0 / P.sum_mass;                                  // Vec3::operator/(scalar) multiplies by the reciprocal (Vec3.h:180-192)
+    for (int c = 0; c < 3; c++) { cm[c] = (P.mass1 * v1[c] + P.mass2 * v2[c]) * inv_sum; g[c] = v1[c] - v2[c]; }
     double g_mag = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
     double cos_ksi = 2 * r.next() - 1;
     double sin_ksi = sqrt(1 - cos_ksi * cos_ksi);

@@ -312,3 +312,24 @@ void orc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+
+/* ---------------------------------------------------------------- DSMC_MEX (Interactions.cpp:143-285) */
+double orc_dsmc_sigma(double m1, double m2, double v_rel) {
+    const double m_reduced = m1 * m2 / (m1 + m2);                 /* :146 */
+    const double c0 = 4.07e-10, c1 = 0.77;                        /* :151-152 */
+    const double c2 = 2 * 1.380648e-23 * 273.15 / m_reduced;      /* :153, Const::k all.h:19 */
+    const double c3 = tgamma(2.5 - c1);                           /* :154 */
+    return 3.141592653 * c0 * c0 * pow(c2 / (v_rel * v_rel), c1 - 0.5) / c3;   /* :179 */
+}
+void orc_dsmc_collide(double m1, double m2, double r1, double r2, double v1[3], double v2[3]) {
+    const double sum_mass = m1 + m2;
+    double cm[3], g[3];
+    const double inv_sum = 1.0 / sum_mass;                        /* Vec3::operator/(scalar) multiplies by the reciprocal, Vec3.h:180-192 */
+    for (int c = 0; c < 3; c++) { cm[c] = (m1 * v1[c] + m2 * v2[c]) * inv_sum; g[c] = v1[c] - v2[c]; }   /* :268-270 */
+    const double g_mag = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    const double cos_ksi = 2 * r1 - 1;                            /* :273-275 */
+    const double sin_ksi = sqrt(1 - cos_ksi * cos_ksi);
+    const double eps = 2 * 3.141592653 * r2;
+    g[0] = g_mag * cos_ksi; g[1] = g_mag * sin_ksi * cos(eps); g[2] = g_mag * sin_ksi * sin(eps);          /* :278-280 */
+    for (int c = 0; c < 3; c++) { v1[c] = cm[c] + m2 / sum_mass * g[c]; v2[c] = cm[c] - m1 / sum_mass * g[c]; }   /* :282-283 */
+}

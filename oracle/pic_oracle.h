@@ -67,6 +67,11 @@ int  orc_solve_rb(const orc_grid* g, const int* object_id, const double* rho, do
 double orc_residual(const orc_grid* g, const int* object_id, const double* rho, const double* phi, double phi0, double n0, double Te0, int bc_mode);
 void orc_compute_ef(const orc_grid* g, const double* phi, double* ef);                                     /* PotentialSolver.cpp:354-408 */
 
+/* DSMC_MEX (Interactions.cpp:143-285): VHS cross-section of evaluateSigma (:178-181) for the reduced mass of m1, m2, and the
+ * isotropic centre-of-mass scattering of collide (:267-285) with the two uniform draws passed in (r1 -> cos_ksi, r2 -> eps). */
+double orc_dsmc_sigma(double m1, double m2, double v_rel);
+void orc_dsmc_collide(double m1, double m2, double r1, double r2, double v1[3], double v2[3]);
+
 /* Philox4x32-10 (counter-based RNG used by every stochastic device kernel) */
 void orc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 #endif

@@ -173,3 +173,17 @@ def philox4x32(ctr, key):
     o = (C.c_uint32 * 4)()
     lib().orc_philox4x32(c, k, o)
     return list(o)
+
+
+def dsmc_sigma(m1, m2, v_rel):
+    """DSMC_MEX::evaluateSigma (v3/Interactions.cpp:178-181)."""
+    lib().orc_dsmc_sigma.restype = C.c_double
+    return lib().orc_dsmc_sigma(C.c_double(m1), C.c_double(m2), C.c_double(v_rel))
+
+
+def dsmc_collide(m1, m2, r1, r2, v1, v2):
+    """DSMC_MEX::collide (v3/Interactions.cpp:267-285) with the two uniform draws given."""
+    a = (C.c_double * 3)(*v1)
+    b = (C.c_double * 3)(*v2)
+    lib().orc_dsmc_collide(C.c_double(m1), C.c_double(m2), C.c_double(r1), C.c_double(r2), a, b)
+    return np.array(list(a)), np.array(list(b))

@@ -175,3 +175,56 @@ def test_collisions_on_a_stale_partition_equal_a_fresh_sort(picgpu):
     pg.set_mover_fraction(0.1)
     assert res[0][0] == res[1][0] and res[0][2] == res[1][2]
     assert abs(res[0][1] - res[1][1]) < 6 * np.sqrt(res[1][1])
+
+
+def _philox_stream(orc, seed, stream_id, index, step):
+    """The device's PhiloxStream (csrc/philox.cuh): key = (lo32(seed) ^ stream, hi32(seed)), counter = (index lo, index hi, step, block);
+    a block yields two doubles of 53 bits, the one from words 3:2 first."""
+    k = [(seed & 0xffffffff) ^ stream_id, seed >> 32]
+    block = 0
+    while True:
+        out = orc.philox4x32([index & 0xffffffff, index >> 32, step, block], k)
+        block += 1
+        yield float(((int(out[3]) << 32) | int(out[2])) >> 11) * 2.0 ** -53
+        yield float(((int(out[1]) << 32) | int(out[0])) >> 11) * 2.0 ** -53
+
+
+def test_one_cell_pair_by_pair_against_the_restatement(picgpu, orc):
+    """Deterministic check below the ensemble level: one cell, the device's random stream replayed on the host (Philox restated in the
+    oracle), the reference's candidate loop (Interactions.cpp:185-223) run with the oracle's evaluateSigma / collide.  Same pairs, same
+    collisions; velocities agree to the last digits (device sin / cos / sqrt are within an ulp or two of libm's)."""
+    pg = picgpu
+    x0, xm = np.array([0.0, 0.0, 0.0]), np.array([2e-3, 2e-3, 2e-3])            # 3 nodes per axis (the minimum): 8 cells of 1 mm, all particles in cell 0
+    n, seed, dt, sv_max, mass = 40, 4242, 3e-9, 2e-15, 16 * util.AMU
+    p = util.random_particles(n, x0, 0.5 * xm, seed=3, vth=900.0, mpw=(MPW0, MPW0)); p[:, 6] = MPW0
+    w = util.build_world(pg.World, 3, 3, 3, x0, xm, dt=dt)
+    sp = pg.Species("O", mass, 0.0, w, MPW0)
+    sp.setParticles(p)
+    pg.seed(seed)
+    m = pg.DSMC_MEX(sp, w); m.setSigmaVMax(sv_max)
+    st = m.apply(dt)
+    got = sp.getParticles()
+    assert np.array_equal(got[:, [0, 1, 2, 6]], p[:, [0, 1, 2, 6]])             # one cell: the stable sort keeps the order
+    # host replay
+    r = _philox_stream(orc, seed, 6 + 16 * 0, 0, 1)                             # RNG_DSMC = 6, species 0, rank 0; cell 0, first call
+    v = p[:, 3:6].copy()
+    dv = 1e-3 * 1e-3 * 1e-3
+    n_groups = int(0.5 * n * n * MPW0 * sv_max * dt / dv + 0.5)
+    n_coll, sv_seen = 0, 0.0
+    for _ in range(n_groups):
+        a = int(next(r) * n); b = int(next(r) * n)
+        while a == b:
+            b = int(next(r) * n)
+        d = v[a] - v[b]
+        v_rel = float(np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]))
+        sv = orc.dsmc_sigma(mass, mass, v_rel) * v_rel
+        sv_seen = max(sv_seen, sv)
+        if sv / sv_max > next(r):
+            n_coll += 1
+            v[a], v[b] = orc.dsmc_collide(mass, mass, next(r), next(r), v[a], v[b])
+    assert n_groups > 30 and 0 < n_coll < n_groups
+    assert (st.candidates, st.collisions) == (n_groups, n_coll)
+    assert np.allclose(got[:, 3:6], v, rtol=1e-12, atol=1e-9)
+    assert abs(st.sigma_v_max - sv_seen) <= 1e-13 * sv_seen                     # the ceiling of the next call (:219-222)
+    for o in (m, sp, w):
+        o.close()

@@ -158,3 +158,27 @@ def test_red_black_shares_the_fixed_point(orc, ref):
     assert ca and cb
     assert util.norm_err(b, a) < 1e-6
     w.close()
+
+
+def test_dsmc_sigma_and_collide_bit_exact(orc, ref):
+    """DSMC_MEX: evaluateSigma and collide of the C restatement against the compiled reference; the two
+    uniform draws of a collision are read from the reference's seeded generator, which is then rewound."""
+    x0, xm, _ = util.discharge_geometry(7, 7, 9)
+    w = util.build_world(ref.World, 7, 7, 9, x0, xm)
+    m1, m2 = 16 * util.AMU, 32 * util.AMU
+    a = ref.Species("O", m1, 0.0, w, 1e13); b = ref.Species("O2", m2, 0.0, w, 1e13)
+    one = ref.DSMC_MEX(a, w); two = ref.DSMC_MEX(a, b, w)
+    v = np.exp(np.random.default_rng(6).uniform(np.log(1e-2), np.log(1e7), 300))
+    assert np.array_equal(one.sigma(v), np.array([orc.dsmc_sigma(m1, m1, x) for x in v]))
+    assert np.array_equal(two.sigma(v), np.array([orc.dsmc_sigma(m1, m2, x) for x in v]))
+    rng = np.random.default_rng(7)
+    for k in range(50):
+        v1, v2 = rng.normal(0, 900.0, 3), rng.normal(0, 400.0, 3)
+        ref.seed(1000 + k); r1, r2 = ref.rnd(), ref.rnd(); ref.seed(1000 + k)
+        for m, (ma, mb) in ((one, (m1, m1)), (two, (m1, m2))):
+            ref.seed(1000 + k)
+            want1, want2 = m.collide(v1, v2)
+            got1, got2 = orc.dsmc_collide(ma, mb, r1, r2, v1, v2)
+            assert np.array_equal(got1, want1) and np.array_equal(got2, want2)
+    for o in (one, two, a, b, w):
+        o.close()
