@@ -332,3 +332,44 @@ def test_mc_candidates_are_dealt_out_over_ranks(picgpu):
     tot = sum(p[0] for p in parts)
     assert 0.85 * one[0] < tot < 1.15 * one[0], (one, parts)
     assert max(p[0] for p in parts) < 0.4 * one[0]                   # and they are spread over the ranks
+
+
+def test_mc_ionization_one_cell_pair_by_pair(picgpu, orc):
+    """Deterministic check below the ensemble level.  One cell; the device's Philox stream is replayed on the host and drives
+    tests/mcc_restatement.py - the reference's candidate loop with collide / newVelocityElecton / cross-sections that are pinned bit
+    for bit against the compiled reference on CPU (test_oracle_vs_reference.py).  Same candidates, same collisions, same
+    ionisations, same products in the same order; values agree to the last digits (device libm vs host libm)."""
+    import mcc_restatement as R
+    from test_gpu_dsmc import _philox_stream
+    pg = picgpu
+    x0, xm = np.array([0.0, 0.0, 0.0]), np.array([2e-3, 2e-3, 2e-3])            # 3 nodes per axis: 8 cells of 1 mm, everything in cell 0
+    seed, dt, wsv = 987, 7e-11, 5e11 * 8e-20 * 8e6
+    E_ion = 1313.9 * 1000 / util.NA
+    rng = np.random.default_rng(12)
+    neu = util.random_particles(60, x0, 0.5 * xm, seed=31, vth=600.0, mpw=(5e11, 5e11)); neu[:, 6] = 5e11
+    ele = util.random_particles(30, x0, 0.5 * xm, seed=32, vth=1.0, mpw=(100.0, 100.0)); ele[:, 6] = 100.0
+    ele[:, 3:6] *= (np.sqrt(2 * rng.uniform(5.0, 150.0, 30) * util.QE / util.ME) / np.linalg.norm(ele[:, 3:6], axis=1))[:, None]
+    w = util.build_world(pg.World, 3, 3, 3, x0, xm, dt=dt)
+    sn = pg.Species("O", 16 * util.AMU, 0.0, w, 5e11, E_ion); si = pg.Species("O+", 16 * util.AMU, util.QE, w, 100.0); se = pg.Species("e-", util.ME, -util.QE, w, 100.0)
+    sn.setParticles(neu); se.setParticles(ele)
+    pg.seed(seed)
+    tE, tS = util.momentum_transfer_table()
+    m = pg.MC_MEX_Ionization(sn, si, se, w, tE, tS); m.setWsvMax(wsv)
+    st = m.apply(dt)
+    got_n, got_e, got_i = sn.getParticles(), se.getParticles(), si.getParticles()
+
+    M = R.MccModel(16 * util.AMU, util.ME, E_ion, tE, tS, 1e-3 * 1e-3 * 1e-3, 5e11, 100.0)
+    ln, le = [list(map(float, r)) for r in neu], [list(map(float, r)) for r in ele]
+    stream = _philox_stream(orc, seed, 4 + 16 * 0, 0, 1)                          # RNG_MCC = 4, neutral species 0, rank 0; cell 0, first call
+    cand, coll, ions, new_e, split, step_max = M.apply_cell(stream, ln, le, dt, wsv)
+    assert cand > 30 and coll > 5 and len(split) > 0                              # the case exercises the loop
+    assert (st.candidates, st.collisions, st.ionizations) == (cand, coll, len(ions))
+    want_n, want_e = np.array(ln + split), np.array(le + new_e)
+    assert got_n.shape == want_n.shape and got_e.shape == want_e.shape and len(got_i) == len(ions)
+    assert np.allclose(got_n, want_n, rtol=1e-11, atol=0, equal_nan=True)
+    assert np.allclose(got_e, want_e, rtol=1e-11, atol=1e-6, equal_nan=True)
+    if ions:
+        assert np.allclose(got_i, np.array(ions), rtol=1e-11, atol=0, equal_nan=True)
+    assert abs(st.w_sigma_v_max - step_max) <= 1e-12 * step_max                   # the ceiling of the next call (:751-756)
+    for o in (m, sn, si, se, w):
+        o.close()

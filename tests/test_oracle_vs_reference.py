@@ -182,3 +182,40 @@ def test_dsmc_sigma_and_collide_bit_exact(orc, ref):
             assert np.array_equal(got1, want1) and np.array_equal(got2, want2)
     for o in (one, two, a, b, w):
         o.close()
+
+
+def test_mcc_restatement_pinned_against_reference(ref, tmp_path):
+    """tests/mcc_restatement.py (the host replay used by the pair-by-pair GPU test) against the compiled reference:
+    evaluateSigmaColl / evaluateSigmaIon and collide (elastic and ionising branch) with the reference's own draws."""
+    import mcc_restatement as R
+    x0, xm, _ = util.discharge_geometry(7, 7, 9)
+    w = util.build_world(ref.World, 7, 7, 9, x0, xm)
+    E_ion = 1313.9 * 1000 / util.NA
+    sn = ref.Species("O", 16 * util.AMU, 0.0, w, 5e11, E_ion); si = ref.Species("O+", 16 * util.AMU, util.QE, w, 100.0); se = ref.Species("e-", util.ME, -util.QE, w, 100.0)
+    table = util.write_table(str(tmp_path / "Oxygen_momentum_transfer.txt"))
+    m = ref.MC_MEX_Ionization(sn, si, se, w, table)
+    tE, tS = util.momentum_transfer_table()
+    dx = (xm - x0) / (np.array([7, 7, 9]) - 1)
+    M = R.MccModel(16 * util.AMU, util.ME, E_ion, tE, tS, dx[0] * dx[1] * dx[2], 5e11, 100.0)
+    for E in np.exp(np.random.default_rng(1).uniform(np.log(1e-4), np.log(1e7), 400)):
+        assert M.sigma_coll(float(E)) == m.sigmaColl(float(E))
+        assert M.sigma_ion(float(E)) == m.sigmaIon(float(E))
+    assert M.w_max0 == m.getWsvMax()
+    rng = np.random.default_rng(2)
+    n_ion = 0
+    for k in range(300):
+        vn = rng.normal(0, 600.0, 3)
+        ve = rng.normal(0, 1.0, 3); ve *= np.sqrt(2 * rng.uniform(1.0, 200.0) * util.QE / util.ME) / np.linalg.norm(ve)      # 1..200 eV electrons
+        s_coll = M.sigma_coll(M.E_rel_eV * float(np.sum((vn - ve) ** 2)))
+        ref.seed(5000 + k); draws = [ref.rnd() for _ in range(8)]; ref.seed(5000 + k)
+        ion_r, vn_r, ve_r, vnew_r = m.collide(vn, ve, s_coll)
+        ion_p, ve_p, vnew_p = M.collide(iter(draws), [float(x) for x in vn], [float(x) for x in ve], s_coll)
+        assert ion_p == ion_r
+        assert np.array_equal(vn_r, vn)                                   # the neutral's velocity never changes (:885-947)
+        assert np.array_equal(np.array(ve_p), ve_r, equal_nan=True), k
+        if ion_r:
+            n_ion += 1
+            assert np.array_equal(np.array(vnew_p), vnew_r, equal_nan=True), k
+    assert 20 < n_ion < 280                                               # both branches exercised
+    for o in (m, sn, si, se, w):
+        o.close()
