@@ -373,3 +373,71 @@ def test_mc_ionization_one_cell_pair_by_pair(picgpu, orc):
     assert abs(st.w_sigma_v_max - step_max) <= 1e-12 * step_max                   # the ceiling of the next call (:751-756)
     for o in (m, sn, si, se, w):
         o.close()
+
+
+def test_loader_and_sources_replayed_particle_by_particle(picgpu, orc):
+    """The thermal loader and the beam sources with the device's Philox streams replayed on the host through
+    tests/sampler_restatement.py (sampleV3th pinned bit for bit against the compiled reference on CPU): the same candidates,
+    the same addParticle filter, the same particles (as multisets: the append order depends on atomics)."""
+    import sampler_restatement as S
+    from test_gpu_dsmc import _philox_stream
+    pg = picgpu
+    seed = 2718
+    # --- Species::loadParticleBoxThermal (Species.cpp:560-598) between the electrodes of the discharge geometry
+    ni, nj, nk = 11, 9, 13
+    x0, xm, rects = util.discharge_geometry(ni, nj, nk)
+    w = util.build_world(pg.World, ni, nj, nk, x0, xm, rects)
+    g = util.build_grid(orc, ni, nj, nk, x0, xm, rects)
+    pg.seed(seed)
+    sp = pg.Species("e-", util.ME, -util.QE, w, 1e5)
+    xc, L = 0.5 * (x0 + xm), xm - x0
+    sides = np.array([L[0], L[1], L[2] * 0.96])                             # reaches into both electrodes (each 0.05 Lz deep): some candidates are rejected
+    T, den = 3000.0, 6e15
+    sp.loadParticleBoxThermal(xc, sides, den, T)
+    got = util.sort_rows(sp.getParticles())
+    n = int(den * (sides[0] * sides[1] * sides[2]) / 1e5)
+    lo, hi = xc - sides / 2, xc + sides / 2
+    want = []
+    for t in range(n):
+        r = _philox_stream(orc, seed, 1 + 16 * 0, t, 1)                     # RNG_LOADER = 1, species 0; particle index, first load call
+        pos = [float(lo[a] + next(r) * (hi[a] - lo[a])) for a in range(3)]
+        vel = S.sample_v3th(r, T, util.ME)
+        if g.in_bounds(pos) and not g.in_object(pos):                       # Species::addParticle :420-434 (E == 0: the rewind is a no-op)
+            want.append(pos + vel + [1e5])
+    want = util.sort_rows(np.array(want))
+    assert 1000 < len(want) < n and got.shape == want.shape
+    assert np.array_equal(got[:, [0, 1, 2, 6]], want[:, [0, 1, 2, 6]])
+    assert np.allclose(got[:, 3:6], want[:, 3:6], rtol=1e-12, atol=1e-6)
+    sp.close(); w.close()
+    # --- WarmBeamSource / ColdBeamSource::sample (Source.cpp:38-103,111-191) on a "-" and a "+" face
+    x0, xm = np.array([-0.1, -0.1, 0.0]), np.array([0.1, 0.1, 0.4])
+    dxs = (xm - x0) / (np.array([ni, nj, nk]) - 1)
+    for face, axis, plus, Tsrc in (("-z", 2, False, 1000.0), ("+x", 0, True, None)):
+        w = util.build_world(pg.World, ni, nj, nk, x0, xm, dt=1e-7)
+        pg.seed(seed)
+        sp = pg.Species("O+", 16 * util.AMU, util.QE, w, 2e2)
+        src = pg.WarmBeamSource(sp, w, 7000.0, 1e10, Tsrc, face) if Tsrc else pg.ColdBeamSource(sp, w, 7000.0, 1e10, face)
+        n_inj = src.sample()
+        got = util.sort_rows(sp.getParticles())
+        Ls = xm - x0
+        A = Ls[1] * Ls[2] if axis == 0 else (Ls[0] * Ls[2] if axis == 1 else Ls[0] * Ls[1])
+        num = 1e10 * 7000.0 * A * 1e-7 / 2e2
+        r0 = _philox_stream(orc, seed, 2 + 16 * 0, 0xFFFFFFFFFFFFFFFF, 1)   # RNG_SOURCE = 2; the count draw uses index ~0
+        n_macro = int(num + next(r0))                                       # Source.cpp:41
+        if plus:
+            Ls = Ls.copy(); Ls[axis] -= dxs[axis]                           # :51,69,86
+        want = []
+        for t in range(n_macro):
+            r = _philox_stream(orc, seed, 2 + 16 * 0, t, 1)
+            v = S.sample_v3th(r, Tsrc, 16 * util.AMU) if Tsrc else [0.0, 0.0, 0.0]
+            v[axis] += -7000.0 if plus else 7000.0
+            p = [0.0, 0.0, 0.0]
+            for a in range(3):
+                p[a] = float(x0[a] + Ls[a]) if (a == axis and plus) else (float(x0[a]) if a == axis else float(x0[a] + next(r) * Ls[a]))
+            if all(x0[a] <= p[a] < xm[a] for a in range(3)):
+                want.append(p + v + [2e2])
+        want = util.sort_rows(np.array(want))
+        assert n_inj == len(want) > 500 and got.shape == want.shape, (face, n_inj, len(want))
+        assert np.array_equal(got[:, [0, 1, 2, 6]], want[:, [0, 1, 2, 6]])
+        assert np.allclose(got[:, 3:6], want[:, 3:6], rtol=1e-12, atol=1e-6)
+        src.close(); sp.close(); w.close()

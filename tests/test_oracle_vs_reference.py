@@ -219,3 +219,24 @@ def test_mcc_restatement_pinned_against_reference(ref, tmp_path):
     assert 20 < n_ion < 280                                               # both branches exercised
     for o in (m, sn, si, se, w):
         o.close()
+
+
+def test_sampler_restatement_pinned_against_reference(ref):
+    """tests/sampler_restatement.py against Species::sampleV3th / sampleReflectedVelocity of the compiled reference, with its own draws."""
+    import sampler_restatement as S
+    x0, xm, _ = util.discharge_geometry(7, 7, 9)
+    w = util.build_world(ref.World, 7, 7, 9, x0, xm)
+    mass = 16 * util.AMU
+    sp = ref.Species("O", mass, 0.0, w, 5e11)
+    rng = np.random.default_rng(4)
+    for k in range(100):
+        T = float(rng.uniform(100.0, 5000.0))
+        ref.seed(300 + k); draws = [ref.rnd() for _ in range(16)]; ref.seed(300 + k)
+        assert np.array_equal(sp.sampleV3th(T), np.array(S.sample_v3th(iter(draws), T, mass)))
+        n = rng.normal(size=3); n /= np.linalg.norm(n)
+        if k % 3 == 0:
+            n = np.array([0.0, 0.0, 1.0 if k % 2 else -1.0])             # electrode faces: the n.x == 0 branch
+        ref.seed(300 + k)
+        want = sp.sampleReflectedVelocity((0.0, 0.0, 0.001), 750.0, n)
+        assert np.array_equal(want, np.array(S.sample_reflected(iter(draws), 750.0, [float(x) for x in n], mass)))
+    sp.close(); w.close()
