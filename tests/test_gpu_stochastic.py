@@ -441,3 +441,43 @@ def test_loader_and_sources_replayed_particle_by_particle(picgpu, orc):
         assert np.array_equal(got[:, [0, 1, 2, 6]], want[:, [0, 1, 2, 6]])
         assert np.allclose(got[:, 3:6], want[:, 3:6], rtol=1e-12, atol=1e-6)
         src.close(); sp.close(); w.close()
+
+
+def test_neutral_wall_reflection_replayed_particle_by_particle(picgpu, orc):
+    """Diffuse re-emission of neutrals from the electrodes (Species.cpp:194-249, sampleReflectedVelocity :835-853) with the device's
+    Philox stream (one per particle slot) replayed on the host through tests/heavy_restatement.py, which is pinned bit for bit against
+    the compiled reference on CPU: the same particles survive, bounce (several times where the reference does) and leave."""
+    import heavy_restatement as H
+    from test_gpu_dsmc import _philox_stream
+    from test_oracle_vs_reference import _heavy_case
+    pg = picgpu
+    x0, xm, rects, boxes = _heavy_case()
+    w = util.build_world(pg.World, 11, 9, 13, x0, xm, rects)
+    g = util.build_grid(orc, 11, 9, 13, x0, xm, rects)
+    mass, dt, seed, n = 16 * util.AMU, 4e-7, 1618, 3000
+    rng = np.random.default_rng(9)
+    p = np.zeros((n, 7))
+    p[:, 0:2] = x0[0:2] + rng.random((n, 2)) * (xm[0:2] - x0[0:2])
+    low = np.arange(n) % 2 == 0
+    p[:, 2] = np.where(low, 0.05 * 0.005 + rng.random(n) * 4e-4, 0.95 * 0.005 - rng.random(n) * 4e-4)      # just outside an electrode
+    p[:, 3:6] = rng.normal(0, 700.0, (n, 3))
+    p[:, 5] = np.where(low, -np.abs(p[:, 5]) - 300.0, np.abs(p[:, 5]) + 300.0)                              # heading into it
+    p[:, 6] = 5e11
+    keep = np.array([not g.in_object(r[0:3]) and bool(g.in_bounds(r[0:3])) for r in p])
+    p = p[keep]
+    pg.seed(seed)
+    sp = pg.Species("O", mass, 0.0, w, 5e11)
+    sp.setParticles(p)
+    sp.advanceNonElectron(sp, sp, dt)
+    got = util.sort_rows(sp.getParticles())
+    want, n_bounced = [], 0
+    for slot, r in enumerate(p):
+        res = H.advance_neutral(_philox_stream(orc, seed, 3 + 16 * 0, slot, 1), g, boxes, mass, r[0:3], r[3:6], dt)   # RNG_HEAVY = 3, species 0, first heavy push
+        if res is not None:
+            want.append(list(res[0]) + list(res[1]) + [5e11])
+            n_bounced += int(list(res[1]) != [float(c) for c in r[3:6]])
+    want = util.sort_rows(np.array(want))
+    assert n_bounced > 1000 and len(want) < len(p)                              # most hit an electrode, some left through the sides
+    assert got.shape == want.shape
+    assert np.allclose(got, want, rtol=1e-11, atol=1e-15)
+    sp.close(); w.close()

@@ -240,3 +240,50 @@ def test_sampler_restatement_pinned_against_reference(ref):
         want = sp.sampleReflectedVelocity((0.0, 0.0, 0.001), 750.0, n)
         assert np.array_equal(want, np.array(S.sample_reflected(iter(draws), 750.0, [float(x) for x in n], mass)))
     sp.close(); w.close()
+
+
+def _heavy_case(ni=11, nj=9, nk=13):
+    x0, xm, rects = util.discharge_geometry(ni, nj, nk)
+    boxes = []
+    for c, phi, sides in rects:
+        h = [s * 0.5 for s in sides]
+        boxes.append(([c[a] - h[a] for a in range(3)], [c[a] + h[a] for a in range(3)]))           # Object.cpp:163-171
+    return x0, xm, rects, boxes
+
+
+def test_heavy_restatement_pinned_against_reference(orc, ref):
+    """tests/heavy_restatement.py against Species::advanceNonElectron of the compiled reference for single neutrals that hit an
+    electrode (diffuse re-emission, possibly several bounces), leave the box, or fly free - with the reference's own draws."""
+    import heavy_restatement as H
+    x0, xm, rects, boxes = _heavy_case()
+    w = util.build_world(ref.World, 11, 9, 13, x0, xm, rects)
+    g = util.build_grid(orc, 11, 9, 13, x0, xm, rects)
+    mass, dt = 16 * util.AMU, 4e-7
+    rng = np.random.default_rng(8)
+    n_hit = n_gone = 0
+    for k in range(300):
+        p = np.zeros(7)
+        p[0:2] = x0[0:2] + rng.random(2) * (xm[0:2] - x0[0:2])
+        p[2] = 0.05 * 0.005 + rng.random() * 4e-4 if k % 2 == 0 else 0.95 * 0.005 - rng.random() * 4e-4      # just outside an electrode
+        p[3:6] = rng.normal(0, 700.0, 3); p[5] = -abs(p[5]) - 300.0 if k % 2 == 0 else abs(p[5]) + 300.0      # heading into it
+        p[6] = 5e11
+        if g.in_object(p[0:3]) or not g.in_bounds(p[0:3]):
+            continue
+        sp = ref.Species("O", mass, 0.0, w, 5e11)
+        sp.setParticles(p[None, :])
+        ref.seed(900 + k); draws = [ref.rnd() for _ in range(400)]; ref.seed(900 + k)
+        sp.advanceNonElectron(sp, sp, dt)
+        got = sp.getParticles()
+        it = iter(draws)
+        want = H.advance_neutral(it, g, boxes, mass, p[0:3], p[3:6], dt)
+        if want is None:
+            n_gone += 1
+            assert len(got) == 0, k
+        else:
+            assert len(got) == 1, k
+            assert np.array_equal(got[0, 0:3], np.array(want[0])), k
+            assert np.array_equal(got[0, 3:6], np.array(want[1])), k
+            n_hit += int(not np.array_equal(got[0, 3:6], p[3:6]))
+        sp.close()
+    assert n_hit > 100
+    w.close()
