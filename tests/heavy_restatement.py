@@ -63,3 +63,27 @@ def advance_neutral(r, grid, rects, mass, pos, vel, dt):
             continue
         t_rem = 0
     return x, v
+
+
+def advance_ion(r, grid, rects, mass, mpw, neutral_mpw0, pos, vel, dt):
+    """One ion through Species.cpp:179-249 in a zero field (the kick adds 0): it flies free, leaves the box, or is neutralised on
+    a surface - int(mpw / neutrals.mpw0 + rnd()) neutrals are re-emitted from the hit point through neutrals.addParticle
+    (:225-232; rejected when the rounded hit point tests as inside the object or out of bounds).
+    Returns (particle or None, [emitted neutral rows])."""
+    x, v = [float(c) for c in pos], [float(c) for c in vel]
+    old = list(x)
+    x = [x[a] + v[a] * 1.0 * dt for a in range(3)]
+    obj = grid.in_object(x)
+    if not grid.in_bounds(x):
+        return None, []
+    if not obj:
+        return (x, v), []
+    lo, hi = rects[obj - 1]
+    tp, hit, n = rect_line_intersect(lo, hi, old, x)
+    v_mag = math.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+    emitted = []
+    for _ in range(int(mpw / neutral_mpw0 + next(r))):
+        nv = S.sample_reflected(r, v_mag, n, mass)
+        if grid.in_bounds(hit) and not grid.in_object(hit):
+            emitted.append(list(hit) + nv + [neutral_mpw0])
+    return None, emitted

@@ -481,3 +481,46 @@ def test_neutral_wall_reflection_replayed_particle_by_particle(picgpu, orc):
     assert got.shape == want.shape
     assert np.allclose(got, want, rtol=1e-11, atol=1e-15)
     sp.close(); w.close()
+
+
+def test_ion_neutralisation_replayed_particle_by_particle(picgpu, orc):
+    """Ions neutralised on the electrodes (Species.cpp:225-232): int(mpw / neutrals.mpw0 + rnd()) neutrals re-emitted from the hit point
+    through addParticle.  Device Philox streams replayed through heavy_restatement.advance_ion (pinned on CPU): the same ions are
+    absorbed, the same neutrals appear - including which of them addParticle rejects on the surface."""
+    import heavy_restatement as H
+    from test_gpu_dsmc import _philox_stream
+    from test_oracle_vs_reference import _heavy_case
+    pg = picgpu
+    x0, xm, rects, boxes = _heavy_case()
+    w = util.build_world(pg.World, 11, 9, 13, x0, xm, rects)
+    g = util.build_grid(orc, 11, 9, 13, x0, xm, rects)
+    mass, dt, seed, n = 16 * util.AMU, 4e-7, 577, 3000
+    rng = np.random.default_rng(19)
+    p = np.zeros((n, 7))
+    p[:, 0:2] = x0[0:2] + rng.random((n, 2)) * (xm[0:2] - x0[0:2])
+    low = np.arange(n) % 2 == 0
+    p[:, 2] = np.where(low, 0.05 * 0.005 + rng.random(n) * 4e-4, 0.95 * 0.005 - rng.random(n) * 4e-4)
+    p[:, 3:6] = rng.normal(0, 700.0, (n, 3))
+    p[:, 5] = np.where(low, -np.abs(p[:, 5]) - 300.0, np.abs(p[:, 5]) + 300.0)
+    p[:, 6] = 260.0
+    keep = np.array([not g.in_object(r[0:3]) and bool(g.in_bounds(r[0:3])) for r in p])
+    p = p[keep]
+    pg.seed(seed)
+    neu = pg.Species("O", mass, 0.0, w, 100.0)                                     # species 0
+    ion = pg.Species("O+", mass, util.QE, w, 260.0)                                # species 1: its stream is RNG_HEAVY + 16
+    ion.setParticles(p)
+    ion.advanceNonElectron(neu, neu, dt)                                           # E == 0: no kick, no rewind
+    got_i, got_n = util.sort_rows(ion.getParticles()), util.sort_rows(neu.getParticles())
+    want_i, want_n = [], []
+    for slot, r in enumerate(p):
+        left, emitted = H.advance_ion(_philox_stream(orc, seed, 3 + 16 * 1, slot, 1), g, boxes, mass, 260.0, 100.0, r[0:3], r[3:6], dt)
+        if left is not None:
+            want_i.append(list(left[0]) + list(left[1]) + [260.0])
+        want_n += emitted
+    want_i, want_n = util.sort_rows(np.array(want_i)), util.sort_rows(np.array(want_n))
+    assert len(want_n) > 1000 and len(want_i) < len(p) // 2
+    assert got_i.shape == want_i.shape and got_n.shape == want_n.shape
+    assert np.array_equal(got_i, want_i)                                           # free flight: no transcendental involved
+    assert np.array_equal(got_n[:, [0, 1, 2, 6]], want_n[:, [0, 1, 2, 6]])
+    assert np.allclose(got_n[:, 3:6], want_n[:, 3:6], rtol=1e-11, atol=1e-12)
+    ion.close(); neu.close(); w.close()

@@ -287,3 +287,38 @@ def test_heavy_restatement_pinned_against_reference(orc, ref):
         sp.close()
     assert n_hit > 100
     w.close()
+
+
+def test_ion_neutralisation_restatement_pinned_against_reference(orc, ref):
+    """heavy_restatement.advance_ion against the compiled reference: single ions of 2.6 neutral weights hitting an electrode."""
+    import heavy_restatement as H
+    x0, xm, rects, boxes = _heavy_case()
+    w = util.build_world(ref.World, 11, 9, 13, x0, xm, rects)
+    g = util.build_grid(orc, 11, 9, 13, x0, xm, rects)
+    mass, dt = 16 * util.AMU, 4e-7
+    rng = np.random.default_rng(18)
+    n_emitted = 0
+    for k in range(200):
+        p = np.zeros(7)
+        p[0:2] = x0[0:2] + rng.random(2) * (xm[0:2] - x0[0:2])
+        p[2] = 0.05 * 0.005 + rng.random() * 4e-4 if k % 2 == 0 else 0.95 * 0.005 - rng.random() * 4e-4
+        p[3:6] = rng.normal(0, 700.0, 3); p[5] = -abs(p[5]) - 300.0 if k % 2 == 0 else abs(p[5]) + 300.0
+        p[6] = 260.0
+        if g.in_object(p[0:3]) or not g.in_bounds(p[0:3]):
+            continue
+        neu = ref.Species("O", mass, 0.0, w, 100.0); ion = ref.Species("O+", mass, util.QE, w, 260.0)
+        ion.setParticles(p[None, :])
+        ref.seed(1200 + k); draws = [ref.rnd() for _ in range(100)]; ref.seed(1200 + k)
+        ion.advanceNonElectron(neu, neu, dt)
+        left, emitted = H.advance_ion(iter(draws), g, boxes, mass, 260.0, 100.0, p[0:3], p[3:6], dt)
+        got_i, got_n = ion.getParticles(), neu.getParticles()
+        assert len(got_i) == (0 if left is None else 1), k
+        if left is not None:
+            assert np.array_equal(got_i[0, 0:6], np.array(list(left[0]) + list(left[1]))), k
+        assert len(got_n) == len(emitted), (k, len(got_n), len(emitted))
+        if emitted:
+            assert np.array_equal(got_n, np.array(emitted)), k
+            n_emitted += len(emitted)
+        neu.close(); ion.close()
+    assert n_emitted > 50                    # about half of the re-emitted neutrals are rejected by addParticle: the rounded hit point tests as inside (SURVEY B19)
+    w.close()
