@@ -7,6 +7,8 @@ bounds) -> number density -> charge density -> non-linear Poisson (n0 exp((phi-p
 The source's random positions are drawn once with numpy and handed to both sides through addParticle (filter + half-step
 rewind), so the run is deterministic.  The reference sweeps lexicographically and the device red-black: both are run to a
 tight residual and share the fixed point, hence the north-star bound (1e-6 relative) instead of bit equality.
+Reference values: n0 = 1e10 m^-3, Te0 = 1.5 eV, i.e. the physical reading of ch3/v1/main.cpp:72 (read in the solver's own
+argument order the stock main makes the Boltzmann term a constant; the kernels are the same, this choice exercises the exponential).
 """
 import numpy as np
 import pytest
