@@ -228,3 +228,36 @@ def test_one_cell_pair_by_pair_against_the_restatement(picgpu, orc):
     assert abs(st.sigma_v_max - sv_seen) <= 1e-13 * sv_seen                     # the ceiling of the next call (:219-222)
     for o in (m, sp, w):
         o.close()
+
+
+def test_two_species_one_cell_pair_by_pair(picgpu, orc):
+    """applyTwoSpecies (Interactions.cpp:225-265) replayed draw by draw in one cell, like the one-species case above."""
+    pg = picgpu
+    x0, xm = np.array([0.0, 0.0, 0.0]), np.array([2e-3, 2e-3, 2e-3])
+    na, nb, seed, dt, sv_max = 30, 24, 99, 3e-9, 2e-15
+    ma, mb = 16 * util.AMU, 32 * util.AMU
+    pa = util.random_particles(na, x0, 0.5 * xm, seed=4, vth=1100.0, mpw=(MPW0, MPW0)); pa[:, 6] = MPW0
+    pb = util.random_particles(nb, x0, 0.5 * xm, seed=5, vth=300.0, mpw=(MPW0, MPW0)); pb[:, 6] = MPW0
+    w = util.build_world(pg.World, 3, 3, 3, x0, xm, dt=dt)
+    a = pg.Species("O", ma, 0.0, w, MPW0); b = pg.Species("O2", mb, 0.0, w, MPW0)
+    a.setParticles(pa); b.setParticles(pb)
+    pg.seed(seed)
+    m = pg.DSMC_MEX(a, b, w); m.setSigmaVMax(sv_max)
+    st = m.apply(dt)
+    ga, gb = a.getParticles(), b.getParticles()
+    r = _philox_stream(orc, seed, 6 + 16 * 0, 0, 1)                             # the stream of species1 (index 0 in this world)
+    va, vb = pa[:, 3:6].copy(), pb[:, 3:6].copy()
+    n_groups = int(0.5 * na * nb * MPW0 * sv_max * dt / 1e-9 + 0.5)
+    n_coll = 0
+    for _ in range(n_groups):
+        i = int(next(r) * na); j = int(next(r) * nb)
+        d = va[i] - vb[j]
+        v_rel = float(np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]))
+        if orc.dsmc_sigma(ma, mb, v_rel) * v_rel / sv_max > next(r):
+            n_coll += 1
+            va[i], vb[j] = orc.dsmc_collide(ma, mb, next(r), next(r), va[i], vb[j])
+    assert n_groups > 15 and 0 < n_coll < n_groups
+    assert (st.candidates, st.collisions) == (n_groups, n_coll)
+    assert np.allclose(ga[:, 3:6], va, rtol=1e-12, atol=1e-9) and np.allclose(gb[:, 3:6], vb, rtol=1e-12, atol=1e-9)
+    for o in (m, a, b, w):
+        o.close()
