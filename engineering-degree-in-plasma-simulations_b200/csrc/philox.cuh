@@ -5,7 +5,7 @@
 //   counter = (lo32(index), hi32(index), step, block)     index = particle / cell / new-particle number
 // so results do not depend on the launch geometry.  No bit parity with mt19937 is possible or required;
 // stochastic kernels are compared with the reference through ensemble statistics, and
-// draw by draw with host restatements driven by the same streams (tests/*_restatement.py, oracle/pic_oracle.c: orc_philox4x32),
+// draw by draw with host restatements driven by the same streams (kept with the tests, together with a host copy of this generator),
 // which are themselves pinned bit for bit against the compiled reference with its own draws.
 #pragma once
 #include <stdint.h>
