@@ -347,6 +347,9 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    trace_steps = bool(os.environ.get("PICG_STEP_TRACE"))
+    trace_prev = {}
+
     def timed(n_steps, ts0, e2e=False, inject_bufs=None, rho_host=None):
         """Times n_steps on the device (CUDA events on the library's stream); returns ms, particle-steps, iterations."""
         ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
@@ -358,6 +361,12 @@ def run_ours(args):
             n_now = sum(sp.getNumParticles() for sp in order) if e2e else None
             it = step(ts0 + k, inject_bufs[k % len(inject_bufs)] if e2e else None)
             its += it
+            if trace_steps and rank == 0:                     # diagnosis only (synchronises every step): per-step kernel times and populations
+                cur = pg.timers_read()
+                delta = {kk: round(v[0] - trace_prev.get(kk, (0.0, 0))[0], 3) for kk, v in cur.items() if v[0] - trace_prev.get(kk, (0.0, 0))[0] > 0.02}
+                trace_prev.clear(); trace_prev.update(cur)
+                print("step %d: n=%s part=%s movers(stats)=%s ms=%s" % (ts0 + k, {sp.name: sp.getNumParticles() for sp in order}, {sp.name: sp.partitionSize() for sp in order},
+                      pg.mover_stats(), json.dumps(delta)), file=sys.stderr)
             if e2e:                                           # what the reference loop reads every step: counts + diagnostics + rho
                 t0 = time.perf_counter()
                 for sp in order:

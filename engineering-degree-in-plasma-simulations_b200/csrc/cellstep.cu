@@ -297,7 +297,7 @@ int launch_cell_step(picg_species_s* s, int mode, size_t n_limit, size_t n_est) 
         case 4:  rc = launch_cell_mode<4>(g, A, mode); break;
         default: rc = launch_cell_mode<5>(g, A, mode); break;
     }
-    if (rc == PICG_OK && emit) s->movers_fresh = true;       // stays true until the particles move, die or are appended to
+    if (rc == PICG_OK && emit) { s->movers_fresh = true; s->movers_saved = false; }       // stays true until the particles move, die or are appended to
     return rc;
 }
 }  // namespace picg

@@ -44,6 +44,7 @@ struct SpeciesCounters {    // lives in device memory, one per species
     u64 n_movers;           // device-side mover count (sort.cu, cellstep.cu)
     u64 n_impact;           // heavy push: particles that ended their first sub-move inside an object (handled by k_heavy_impacts)
     u64 n_listed;           // movers of slots [0, n_listed) are listed in mv_trip (written by the deposit pass that listed them)
+    u64 n_movers_dep;       // n_movers as the deposit pass left it (sort.cu: list builds append the tail behind it and restore it)
 };
 
 struct picg_world_s {
@@ -87,6 +88,7 @@ struct picg_species_s {
     // (slot, current cell, home cell) of the particles that left their slot's home cell: three arrays of mv_trip_cap entries
     unsigned* mv_trip = nullptr; size_t mv_trip_cap = 0;
     bool wants_lists = false;          // per-cell lists have been asked for (MC collisions): deposit passes emit the movers on the fly
+    bool movers_saved = false;         // ctr->n_movers_dep holds the mover count of the deposit pass that set movers_fresh
     bool movers_fresh = false;         // mv_trip[0, ctr->n_movers) lists the movers of the partition for the current particle positions
     bool part_valid = false;           // cell_start is a partition of [0, part_n) (possibly stale: particles may have drifted)
     size_t part_n = 0;                 // upper bound of the particle count at the last sort
@@ -123,6 +125,9 @@ struct picg_mcc_s {
     u64* stats = nullptr;              // device: candidates, collisions, ionizations
     u64 step = 0;
     size_t last_appends[3] = {0, 0, 0};   // neutrals, electrons, ions appended by the previous apply (capacity estimate)
+    int fixed_weight = 0;              // 1: the fixed-weight algorithm of ch4/v2 (Interactions.cpp:566-641) instead of v3's variable weights
+    unsigned char* chunk_used[3] = {nullptr, nullptr, nullptr}; size_t chunk_cap[3] = {0, 0, 0};   // per-chunk fill counts of the appended regions (mcc.cu)
+    unsigned* orphans[3] = {nullptr, nullptr, nullptr};
 };
 
 struct picg_dsmc_s {

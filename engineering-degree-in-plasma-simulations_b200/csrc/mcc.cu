@@ -5,10 +5,21 @@
 // [cell_start[c], cell_start[c+1]).  One thread owns one cell and runs the reference's candidate loop
 // sequentially (weights and the neutral list mutate inside the loop, :687-725), cells are independent.
 // RNG: Philox stream (RNG_MCC) addressed by (cell, apply-call number), so results are independent of the
-// launch geometry.  New ions / electrons / split-off neutrals are appended through atomic cursors.
+// launch geometry.
+//   k_mcc<1> : the fixed-weight ancestor of the same interaction, MC_MEX_Ionization::apply of ch4/v2
+//           (ch4/v2/Interactions.cpp:566-641, collide :678-735, evaluateSigmaIon :560-563): Bird's NTC candidate count with
+//           neutrals.mpw0, unweighted acceptance sigma*v_rel / (sigma*v_rel)_max, no ionisation threshold guard, products created
+//           through Species::addParticle (bounds / object filter and half-step rewind, ch4/v2/Species.cpp:226-237), neutrals never
+//           depleted.  BASELINE.json config 3.
+// Appends.  Every product is a new particle at the end of a store.  One atomic per product on the store's counter serialises
+// at the L2 (one address: ~0.45 ns each, 9 ms for the 2e7 split-off neutrals of a late step), so a warp takes CHUNKS of 32 slots
+// from the counter (one atomic per 32 products) and hands them out through a packed (base, used) word in shared memory.
+// The slots of a chunk that stay unused (at most 31 per warp and store at the end of the kernel) are holes in the freshly
+// appended region; they are listed afterwards and closed by the compaction the push already uses (push.cu).
 #include "common.cuh"
 #include "philox.cuh"
 #include "celllists.cuh"
+#include "push.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -23,6 +34,8 @@ struct MccParams {
     double m_n, m_e, sum_mass, E_rel_eV, E_ele_eV, two_qe_me, c0, c1, c2, B_inc, E_ion_eV, inv_dv, rank_scale;
     int world, rank;
     int n_tab; const double* tab_E; const double* tab_s;
+    // fixed-weight variant (ch4/v2): weights of the created particles, Species::addParticle's rewind
+    int fixed_weight; double neu_mpw0, ion_mpw0, ele_mpw0; int ions_to_create; const double* ef; double qm_ion, qm_ele, half_dt;
 };
 // evaluateSigmaColl (:541-558): std::map lower_bound + linear interpolation, clamped to the end values
 __host__ __device__ __forceinline__ double sigma_coll(const MccParams& P, double E) {
@@ -35,7 +48,7 @@ __host__ __device__ __forceinline__ double sigma_coll(const MccParams& P, double
 }
 // evaluateSigmaIon (:559-566)
 __host__ __device__ __forceinline__ double sigma_ion(const MccParams& P, double E) {
-    if (E <= P.E_ion_eV) return 0;
+    if (!P.fixed_weight && E <= P.E_ion_eV) return 0;                                  // the guard is new in v3; ch4/v2 (:560-563) evaluates the fit everywhere
     return P.c0 * log(E / P.c1) / E * exp(-P.c2 / E);
 }
 // newVelocityElecton, IONIZE_1 / LAB frame (:845-862); note i x u is not normalised
@@ -59,7 +72,7 @@ __device__ __forceinline__ bool collide(PhiloxStream& r, const MccParams& P, con
     if (r.next() <= Pion) {
         double ve_mag = sqrt(ve[0] * ve[0] + ve[1] * ve[1] + ve[2] * ve[2]);
         double E_inc = ve_mag * ve_mag * P.E_ele_eV;
-        if (E_inc < P.E_ion_eV) return false;                                          // :900-905
+        if (!P.fixed_weight && E_inc < P.E_ion_eV) return false;                       // :900-905 (v3 only; ch4/v2 goes on and creates a NaN electron)
         double E_ej = 10.0 * tan(r.next() * atan((E_inc - P.E_ion_eV) / (2 * P.B_inc)));
         double E_sc = E_inc - P.E_ion_eV - E_ej;
         if (E_sc < 0) E_sc = 0.000001;
@@ -80,41 +93,81 @@ __device__ __forceinline__ bool collide(PhiloxStream& r, const MccParams& P, con
     return false;
 }
 
-// Slot reservation BEFORE any state is changed: a collision whose products do not fit is skipped as a whole (and
-// counted), so a full store can never leave half-applied collisions behind.
-__device__ __forceinline__ long long reserve_slot(const Store& s) {
-    u64 dst = atomicAdd(&s.ctr->n, 1ull);
-    if (dst >= s.cap) { atomicAdd(&s.ctr->n, ~0ull); return -1; }          // give the slot back
-    return (long long)dst;
+// ---------------------------------------------------------------- appends: chunks of 32 slots per warp and store
+#define MCC_THREADS 128
+#define MCC_WARPS (MCC_THREADS / 32)
+#define MCC_CHUNK 32
+#define MCC_ORPHANS 4096
+struct ChunkPool {
+    u64* cursor;              // the store's live count, used as a bump pointer: advances by MCC_CHUNK during the kernel
+    u64 base0, limit;         // first appended slot; chunks must end at or below limit (= base0 + 32 * floor((cap - base0) / 32))
+    unsigned char* used;      // used[k]: filled slots of chunk k = (slot - base0) / 32; preset to 32 (full), lowered where a chunk stays partly empty
+    unsigned* orphans;        // [0]: count, then slots that were reserved for a collision that could not complete (a partner store was full)
+};
+// Slot reservation BEFORE any state is changed: a collision whose products do not fit is skipped as a whole (and counted), so a
+// full store can never leave half-applied collisions behind.  word = (chunk base << 6) | slots handed out; ~0 = no chunk yet.
+__device__ __forceinline__ long long reserve_slot(u64* word, const ChunkPool& P) {
+    for (;;) {
+        const u64 old = *(volatile u64*)word;
+        const unsigned used = (unsigned)(old & 63);
+        if (used < MCC_CHUNK) {
+            if (atomicCAS((unsigned long long*)word, old, old + 1) == old) return (long long)((old >> 6) + used);
+            continue;
+        }
+        const u64 nb = atomicAdd((unsigned long long*)P.cursor, (u64)MCC_CHUNK);
+        if (nb + MCC_CHUNK > P.limit) return -1;                                   // store full (the counter is clamped after the kernel)
+        if (atomicCAS((unsigned long long*)word, old, (nb << 6) | 1) == old) return (long long)nb;
+        P.used[(nb - P.base0) >> 5] = 0;                                           // another lane of the warp installed a chunk first: this one stays empty
+    }
 }
-__device__ __forceinline__ void release_slot(const Store& s) { atomicAdd(&s.ctr->n, ~0ull); }
+__device__ __forceinline__ void orphan_slot(const ChunkPool& P, long long slot) {
+    unsigned t = atomicAdd(P.orphans, 1u);
+    if (t < MCC_ORPHANS) P.orphans[1 + t] = (unsigned)slot;
+}
 __device__ __forceinline__ void write_slot(const Store& s, long long dst, const double pos[3], const double v[3], double mpw) {
     s.a[0][dst] = pos[0]; s.a[1][dst] = pos[1]; s.a[2][dst] = pos[2]; s.a[3][dst] = v[0]; s.a[4][dst] = v[1]; s.a[5][dst] = v[2]; s.a[6][dst] = mpw;
 }
 __device__ __forceinline__ void atomic_max_pos_double(double* addr, double v) {     // valid for non-negative doubles
     atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
 }
+// Species::addParticle of ch4/v2 (Species.cpp:226-237): bounds / object filter, then vel -= charge/mass * E(pos) * (0.5 * world.dt)
+__device__ __forceinline__ bool add_particle_filter_rewind(const Grid& g, const double* __restrict__ ef, double q_over_m, double half_dt, const double pos[3], double v[3]) {
+    if (!in_bounds(g, pos[0], pos[1], pos[2]) || in_object(g, pos[0], pos[1], pos[2])) return false;
+    double ex, ey, ez;
+    gather_ef(g, ef, x_to_l(pos[0], g.x0[0], g.inv_dx[0]), x_to_l(pos[1], g.x0[1], g.inv_dx[1]), x_to_l(pos[2], g.x0[2], g.inv_dx[2]), ex, ey, ez);
+    v[0] = __dsub_rn(v[0], __dmul_rn(__dmul_rn(ex, q_over_m), half_dt));
+    v[1] = __dsub_rn(v[1], __dmul_rn(__dmul_rn(ey, q_over_m), half_dt));
+    v[2] = __dsub_rn(v[2], __dmul_rn(__dmul_rn(ez, q_over_m), half_dt));
+    return true;
+}
 
 // stats: [0] candidates [1] collisions [2] ionisations [3] skipped (electron heavier than neutral)
 //        [5] dropped because a product store was full (collision skipped untouched)
-__global__ void __launch_bounds__(128, 6) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, CellLists Ln,
-                                             CellLists Le, double* __restrict__ wsv, u64* __restrict__ stats, double dt,
-                                             uint64_t seed, uint32_t stream, uint32_t call) {
+//        [6] split-off neutrals beyond MCC_EXTRA per cell and call (created, but not selectable by later candidates of the same call)
+//        [7] fixed-weight variant: created electrons with a NaN velocity (ionisation below the threshold, ch4/v2 only) that were not appended
+template <int FIXED>
+__global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, CellLists Ln, CellLists Le, ChunkPool Cn, ChunkPool Ce,
+                                                        ChunkPool Ci, double* __restrict__ wsv, u64* __restrict__ stats, double dt, uint64_t seed, uint32_t stream, uint32_t call) {
+    __shared__ u64 s_chunk[3][MCC_WARPS];
+    if (threadIdx.x < 3 * MCC_WARPS) (&s_chunk[0][0])[threadIdx.x] = ~0ull;
+    __syncthreads();
+    const int wib = threadIdx.x >> 5;
+    u64 *wn = &s_chunk[0][wib], *we = &s_chunk[1][wib], *wi = &s_chunk[2][wib];
     const double W_max = wsv[0];
-    u64 n_cand = 0, n_coll = 0, n_ion = 0, n_skip = 0, n_drop = 0; double step_max = 0;
+    u64 n_cand = 0, n_coll = 0, n_ion = 0, n_skip = 0, n_drop = 0, n_capped = 0, n_nan = 0; double step_max = 0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.nc; c += gridDim.x * blockDim.x) {
         CellView ve = cell_view(Le, c); int np_e = ve.np;
         if (np_e <= 0) continue;
         CellView vn = cell_view(Ln, c); int np_n0 = vn.np;
         if (np_n0 <= 0) continue;
         int np_n = np_n0;
-        // :646.  Multi-GPU: the particles of a cell are spread over G ranks, so the cell's candidate count is estimated
+        // v3 :646 / ch4/v2 :591.  Multi-GPU: the particles of a cell are spread over G ranks, so the cell's candidate count is estimated
         // from the local populations (x G^2), rounded ONCE like the reference's and dealt out to the ranks: n/G each, the n%G left
         // over to a rotating subset.  Rounding per rank instead would lose every cell whose share is below one half.
-        double frac = np_n * np_e * W_max * dt * P.inv_dv * P.rank_scale;
+        double frac = FIXED ? 0.5 * np_n * np_e * P.neu_mpw0 * W_max * dt * P.inv_dv * P.rank_scale : np_n * np_e * W_max * dt * P.inv_dv * P.rank_scale;
         int n_groups = (int)(frac + 0.5);
         if (P.world > 1) n_groups = n_groups / P.world + ((unsigned)(c + (int)call + P.rank) % (unsigned)P.world < (unsigned)(n_groups % P.world) ? 1 : 0);
-        if (n_groups > np_n) n_groups = np_n - 1;                                         // :649-653
+        if (n_groups > np_n) n_groups = np_n - 1;                                         // v3 :649-653 / v2 :598-600
         if (n_groups <= 0) continue;
         PhiloxStream r; r.init(seed, stream, (u64)c, call);
         long long extra[MCC_EXTRA]; int n_extra = 0;
@@ -128,19 +181,49 @@ __global__ void __launch_bounds__(128, 6) k_mcc(Grid g, MccParams P, Store neu, 
             double v_rel = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
             double E_rel = P.E_rel_eV * v_rel * v_rel;
             double s_coll = sigma_coll(P, E_rel);
+            n_cand++;
+            if (FIXED) {                                                                   // ch4/v2 :608-632
+                double sv = s_coll * v_rel;
+                if (sv > step_max) step_max = sv;
+                if (sv / W_max > r.next()) {
+                    n_coll++;
+                    double vnew[3] = {0, 0, 0};
+                    bool ionised = collide(r, P, vn_, ve_, vnew, s_coll);
+                    ele.a[3][pe] = ve_[0]; ele.a[4][pe] = ve_[1]; ele.a[5][pe] = ve_[2];   // collide works on a reference to the electron's velocity
+                    if (ionised) {
+                        n_ion++;
+                        double pos[3] = {neu.a[0][pn], neu.a[1][pn], neu.a[2][pn]};
+                        for (int q = 0; q < P.ions_to_create; q++) {                       // ions.addParticle(pos, vel_neutral, ions.mpw0) :624-626
+                            double vi[3] = {vn_[0], vn_[1], vn_[2]};
+                            if (!add_particle_filter_rewind(g, P.ef, P.qm_ion, P.half_dt, pos, vi)) continue;
+                            long long s1 = reserve_slot(wi, Ci);
+                            if (s1 < 0) { n_drop++; continue; }
+                            write_slot(ion, s1, pos, vi, P.ion_mpw0);
+                        }
+                        // electrons.addParticle(pos, vel_new, electrons.mpw0) :628.  Below the ionisation threshold ch4/v2 computes the
+                        // ejected electron from a negative energy: its velocity is NaN and the reference appends it all the same (its next
+                        // push then indexes the field with (int)NaN).  Such products are counted and not appended here.
+                        if (isnan(vnew[0]) || isnan(vnew[1]) || isnan(vnew[2])) n_nan++;
+                        else if (add_particle_filter_rewind(g, P.ef, P.qm_ele, P.half_dt, pos, vnew)) {
+                            long long s2 = reserve_slot(we, Ce);
+                            if (s2 < 0) n_drop++; else write_slot(ele, s2, pos, vnew, P.ele_mpw0);
+                        }
+                    }
+                }
+                continue;
+            }
             double Wn = neu.a[6][pn], We = ele.a[6][pe];
             double Wg = Wn < We ? We : Wn, Wl = Wn < We ? Wn : We;                         // greaterLesser funkc.h:19-25
             double Wsv = Wg * s_coll * v_rel;
             if (Wsv > step_max) step_max = Wsv;
-            n_cand++;
             if (r.next() < Wsv / W_max) {
                 n_coll++;
                 if (Wn > We) {                                                             // split the neutral (:684-703)
                     double vnew[3] = {0, 0, 0};
                     bool ionised = collide(r, P, vn_, ve_, vnew, s_coll);                  // pure: works on local copies
                     long long s1 = -1, s2 = -1;
-                    if (ionised) { s1 = reserve_slot(ion); if (s1 >= 0) { s2 = reserve_slot(ele); if (s2 < 0) { release_slot(ion); s1 = -1; } } }
-                    else s1 = reserve_slot(neu);
+                    if (ionised) { s1 = reserve_slot(wi, Ci); if (s1 >= 0) { s2 = reserve_slot(we, Ce); if (s2 < 0) { orphan_slot(Ci, s1); s1 = -1; } } }
+                    else s1 = reserve_slot(wn, Cn);
                     if (s1 < 0) { n_drop++; n_coll--; continue; }                          // no room for the products: skip the collision untouched
                     neu.a[6][pn] = Wn - We;
                     ele.a[3][pe] = ve_[0]; ele.a[4][pe] = ve_[1]; ele.a[5][pe] = ve_[2];
@@ -151,7 +234,7 @@ __global__ void __launch_bounds__(128, 6) k_mcc(Grid g, MccParams P, Store neu, 
                         write_slot(ele, s2, pos, vnew, Wl);
                     } else {
                         write_slot(neu, s1, pos, vn_, We);                                 // split-off neutral of the electron's weight
-                        if (n_extra < MCC_EXTRA) { extra[n_extra++] = s1; np_n++; }
+                        if (n_extra < MCC_EXTRA) { extra[n_extra++] = s1; np_n++; } else n_capped++;
                     }
                 } else if (Wn < We) {
                     n_skip++;          // the reference's electron-heavier branch is defective; not reproduced, counted
@@ -160,16 +243,43 @@ __global__ void __launch_bounds__(128, 6) k_mcc(Grid g, MccParams P, Store neu, 
         }
     }
     // block-level reduction of the statistics
-    __shared__ u64 sh[5]; __shared__ double sh_max;
-    if (threadIdx.x == 0) { sh[0] = sh[1] = sh[2] = sh[3] = sh[4] = 0; sh_max = 0; }
+    __shared__ u64 sh[7]; __shared__ double sh_max;
+    if (threadIdx.x == 0) { for (int q = 0; q < 7; q++) sh[q] = 0; sh_max = 0; }
     __syncthreads();
-    if (n_cand) { atomicAdd(&sh[0], n_cand); atomicAdd(&sh[1], n_coll); atomicAdd(&sh[2], n_ion); atomicAdd(&sh[3], n_skip); atomicAdd(&sh[4], n_drop); atomic_max_pos_double(&sh_max, step_max); }
+    if (n_cand) {
+        atomicAdd(&sh[0], n_cand); atomicAdd(&sh[1], n_coll); atomicAdd(&sh[2], n_ion); atomicAdd(&sh[3], n_skip); atomicAdd(&sh[4], n_drop);
+        atomicAdd(&sh[5], n_capped); atomicAdd(&sh[6], n_nan); atomic_max_pos_double(&sh_max, step_max);
+    }
     __syncthreads();
     if (threadIdx.x == 0 && sh[0]) {
         atomicAdd(&stats[0], sh[0]); atomicAdd(&stats[1], sh[1]); atomicAdd(&stats[2], sh[2]); atomicAdd(&stats[3], sh[3]); atomicAdd(&stats[5], sh[4]);
+        atomicAdd(&stats[6], sh[5]); atomicAdd(&stats[7], sh[6]);
         atomic_max_pos_double(&wsv[1], sh_max);
     }
+    // the warps' current chunks are only partly used (every lane of the block is past its last reservation: barrier above)
+    if (threadIdx.x < 3 * MCC_WARPS) {
+        const u64 word = (&s_chunk[0][0])[threadIdx.x];
+        const ChunkPool& C = threadIdx.x < MCC_WARPS ? Cn : (threadIdx.x < 2 * MCC_WARPS ? Ce : Ci);
+        if (word != ~0ull && (word & 63) < MCC_CHUNK) C.used[((word >> 6) - C.base0) >> 5] = (unsigned char)(word & 63);
+    }
 }
+// After the kernel: slots [base0, end) were handed out in chunks, end = min(counter, limit).  Lists the unused slots of partly
+// filled chunks and the orphans as "dead" for the compaction (push.cu), which closes the holes and lowers the count.
+__global__ void __launch_bounds__(256) k_mcc_holes(ChunkPool C, SpeciesCounters* ctr, unsigned* __restrict__ dead_list) {
+    const u64 end = min(ctr->n, C.limit);
+    const u64 nchunks = end > C.base0 ? (end - C.base0) >> 5 : 0;
+    for (u64 k = blockIdx.x * (u64)blockDim.x + threadIdx.x; k < nchunks; k += (u64)gridDim.x * blockDim.x) {
+        const unsigned u = C.used[k];
+        if (u >= MCC_CHUNK) continue;
+        u64 dst = atomicAdd(&ctr->n_dead, (u64)(MCC_CHUNK - u));
+        for (unsigned t = u; t < MCC_CHUNK; t++) dead_list[dst++] = (unsigned)(C.base0 + (k << 5) + t);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned no = min(C.orphans[0], (unsigned)MCC_ORPHANS);
+        if (no) { u64 dst = atomicAdd(&ctr->n_dead, (u64)no); for (unsigned t = 0; t < no; t++) dead_list[dst++] = C.orphans[1 + t]; }
+    }
+}
+__global__ void k_mcc_clamp(ChunkPool C, SpeciesCounters* ctr) { if (ctr->n > C.limit) ctr->n = C.limit; if (ctr->n < C.base0) ctr->n = C.base0; }
 // W_sigma_v_rel_max <- max sampled value of this step, only if a collision happened (:751-756)
 __global__ void k_mcc_finish(double* wsv, const u64* stats) { if (stats[1]) wsv[0] = wsv[1]; }
 __global__ void k_sigma_eval(MccParams P, int n, const double* __restrict__ E, double* __restrict__ sc, double* __restrict__ si) {
@@ -189,6 +299,9 @@ static MccParams make_params(const picg_mcc_s* m) {
     P.inv_dv = 1 / (g.dx[0] * g.dx[1] * g.dx[2]);                                         // :500-501
     P.rank_scale = (double)g_world_size * (double)g_world_size; P.world = g_world_size; P.rank = g_rank;
     P.n_tab = m->n_table; P.tab_E = m->tab_E; P.tab_s = m->tab_s;
+    P.fixed_weight = m->fixed_weight; P.neu_mpw0 = m->neu->mpw0; P.ion_mpw0 = m->ion->mpw0; P.ele_mpw0 = m->ele->mpw0;
+    P.ions_to_create = (int)(m->ele->mpw0 / m->ion->mpw0 + 0.5);                          // ch4/v2 :623
+    P.ef = m->w->ef; P.qm_ion = m->ion->charge / m->ion->mass; P.qm_ele = m->ele->charge / m->ele->mass; P.half_dt = 0.5 * m->w->dt;
     return P;
 }
 // per-cell list lengths as the collision kernel sees them (debug / tests): must equal computeMacroParticlesCount
@@ -238,6 +351,7 @@ int picg_mcc_destroy(picg_mcc_t m) {
     if (!m) return PICG_OK;
     if (g_stream) cudaStreamSynchronize(g_stream);
     cudaFree(m->tab_E); cudaFree(m->tab_s); cudaFree(m->wsv); cudaFree(m->stats);
+    for (int k = 0; k < 3; k++) { cudaFree(m->chunk_used[k]); cudaFree(m->orphans[k]); }
     delete m; return PICG_OK;
 }
 
@@ -246,6 +360,14 @@ int picg_mcc_set_wsv_max(picg_mcc_t m, double v) {
     CUDA_TRY(cudaMemcpyAsync(m->wsv, &v, 8, cudaMemcpyHostToDevice, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));
     return PICG_OK;
+}
+
+// variant 0: variable weights (ch4/v3, the default); 1: fixed weights (ch4/v2/Interactions.cpp:566-641).  Resets the acceptance
+// ceiling to the variant's initial value (v3: 1e-14 * max(mpw0), Interactions.cpp:534; v2: 1e-14, ch4/v2/Interactions.h:129).
+int picg_mcc_set_variant(picg_mcc_t m, int variant) {
+    REQUIRE_DEVICE(); REQUIRE_ARG(m && (variant == 0 || variant == 1), "picg_mcc_set_variant: variant must be 0 (ch4/v3, variable weights) or 1 (ch4/v2, fixed weights)");
+    m->fixed_weight = variant;
+    return picg_mcc_set_wsv_max(m, variant ? 1e-14 : 1e-14 * std::max(m->ele->mpw0, m->neu->mpw0));
 }
 
 int picg_mcc_sigma(picg_mcc_t m, int n, const double* E_eV, double* sc, double* si) {
@@ -284,11 +406,43 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     }
     double zero = 0; CUDA_TRY(cudaMemcpyAsync(m->wsv + 1, &zero, 8, cudaMemcpyHostToDevice, g_stream));
     m->step++;
-    int grid = std::max(1, std::min(div_up(g.nc, 128), g_sm_count * 16));
-    LAUNCH(K_MCC, k_mcc, grid, 128, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), m->wsv, m->stats, dt,
-           g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
+    // chunk pools of the three stores (neutrals, electrons, ions): appended region [n_before, limit), per-chunk fill counts preset to "full"
+    ChunkPool pool[3];
+    size_t max_region = 0;
+    for (int k = 0; k < 3; k++) {
+        picg_species_s* sp = sp3[k];
+        const size_t region = sp->cap - n_before[k], nchunks = region / MCC_CHUNK + 1;
+        max_region = std::max(max_region, region);
+        if (m->chunk_cap[k] < nchunks) {
+            cudaStreamSynchronize(g_stream); cudaFree(m->chunk_used[k]); m->chunk_used[k] = nullptr; m->chunk_cap[k] = 0;
+            cudaError_t e = cudaMalloc(&m->chunk_used[k], nchunks + nchunks / 4 + 256);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(mcc chunk table)", __FILE__, __LINE__);
+            m->chunk_cap[k] = nchunks + nchunks / 4 + 256; note_realloc("mcc chunk table", m->chunk_cap[k]);
+        }
+        if (!m->orphans[k]) CUDA_TRY(cudaMalloc(&m->orphans[k], (MCC_ORPHANS + 1) * 4));
+        CUDA_TRY(cudaMemsetAsync(m->chunk_used[k], MCC_CHUNK, nchunks, g_stream));
+        CUDA_TRY(cudaMemsetAsync(m->orphans[k], 0, 4, g_stream));
+        pool[k].cursor = &sp->ctr->n; pool[k].base0 = n_before[k]; pool[k].limit = n_before[k] + (region / MCC_CHUNK) * MCC_CHUNK;
+        pool[k].used = m->chunk_used[k]; pool[k].orphans = m->orphans[k];
+    }
+    rc = ensure_scratch(m->w, compact_scratch_bytes(std::max<size_t>(max_region, 1))); if (rc) return rc;
+    int grid = std::max(1, std::min(div_up(g.nc, MCC_THREADS), g_sm_count * 16));
+    if (m->fixed_weight) LAUNCH(K_MCC, k_mcc<1>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), pool[0], pool[1], pool[2],
+                                m->wsv, m->stats, dt, g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
+    else LAUNCH(K_MCC, k_mcc<0>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), pool[0], pool[1], pool[2],
+                m->wsv, m->stats, dt, g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
     CHECK_LAUNCH();
     LAUNCH(K_MCC, k_mcc_finish, 1, 1, 0, m->wsv, m->stats); CHECK_LAUNCH();
+    // close the holes of the chunked appends (all of them lie in the appended region, beyond every cell partition)
+    for (int k = 0; k < 3; k++) {
+        picg_species_s* sp = sp3[k];
+        const size_t region = std::max<size_t>(sp->cap - n_before[k], 1);
+        LAUNCH(K_MCC, k_mcc_holes, std::max(1, std::min(div_up(region / MCC_CHUNK + 1, 256), g_sm_count * 4)), 256, 0, pool[k], sp->ctr, (unsigned*)m->w->scratch); CHECK_LAUNCH();
+        LAUNCH(K_MCC, k_mcc_clamp, 1, 1, 0, pool[k], sp->ctr); CHECK_LAUNCH();
+        const bool fresh = sp->movers_fresh, saved = sp->movers_saved;
+        rc = compact_dead(sp, region); if (rc) return rc;
+        sp->movers_fresh = fresh; sp->movers_saved = saved;      // only slots appended by this call moved: the mover list of the partition stays valid
+    }
     u64 host_stats[8];
     CUDA_TRY(cudaMemcpyAsync(host_stats, m->stats, 64, cudaMemcpyDeviceToHost, g_stream));
     for (picg_species_s* s : {neu, ele, ion}) { s->n_host_valid = false; s->n_upper = s->cap; }
@@ -303,6 +457,7 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     }
     if (out) {
         out->candidates = host_stats[0]; out->collisions = host_stats[1]; out->ionizations = host_stats[2]; out->dropped = host_stats[5];
+        out->extras_capped = host_stats[6]; out->nan_products = host_stats[7];
         double wmax; CUDA_TRY(cudaMemcpyAsync(&wmax, m->wsv, 8, cudaMemcpyDeviceToHost, g_stream)); CUDA_TRY(cudaStreamSynchronize(g_stream));
         out->w_sigma_v_max = wmax;
     }

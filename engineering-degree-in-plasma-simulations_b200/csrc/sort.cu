@@ -11,6 +11,8 @@
 // k_cell_start.  ceil(log2(num_cells)/8) passes: 3 for the 256^3 mesh.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 using namespace picg;
 
@@ -208,6 +210,10 @@ __global__ void k_gather_u32(const u64* __restrict__ n_ptr, const unsigned* __re
     for (u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x; p < n; p += (u64)gridDim.x * blockDim.x) out[p] = in[idx[p]];
 }
 __global__ void k_clamp_u64(u64* v, u64 cap) { if (*v > cap) *v = cap; }
+// The deposit pass left n_movers = the movers of the partition.  A list build appends the tail and the vacated slots behind them;
+// the next build (no push or deposit in between: neutrals of the subcycled loop, products appended by a collision call) must start
+// again from the deposit's count, not from the inflated one.
+__global__ void k_movers_checkpoint(SpeciesCounters* ctr, int restore) { if (restore) ctr->n_movers = ctr->n_movers_dep; else ctr->n_movers_dep = ctr->n_movers; }
 
 // The same table for a SPARSE sorted key list (movers).  A key at position p owns the cells (previous key, its key]: short gaps are
 // filled by the key's thread, long ones (a few: at most nc/32) are queued and filled by a warp each.  nc + 1 writes in total.
@@ -235,6 +241,7 @@ __global__ void __launch_bounds__(256) k_cell_start_long(const unsigned* __restr
 namespace picg {
 double g_mover_fraction = 0.10;     // above this fraction of movers the store is re-sorted instead of patched
 static uint64_t g_movers_from_deposit = 0, g_mover_scans = 0, g_mover_resorts = 0;
+static bool trace_sort() { static const bool t = getenv("PICG_TRACE_SORT") && atoi(getenv("PICG_TRACE_SORT")) != 0; return t; }
 // Stable LSD radix sort of (keys, vals) pairs; n is read on the device.  Returns the buffers that hold the result.
 static int radix_sort_pairs(const u64* n_ptr, size_t n_upper, int key_bits, unsigned*& keysA, unsigned*& valsA, unsigned*& keysB, unsigned*& valsB,
                             unsigned* counts, int nblocks) {
@@ -265,6 +272,7 @@ int sort_species(picg_species_s* s) {
     const Grid& g = s->w->g;
     int rc0 = species_refresh_count(s); if (rc0) return rc0;               // a sort is rare: the exact count makes part_n exact
     s->n_upper = s->n_host;
+    if (trace_sort()) fprintf(stderr, "[picgpu] full sort of species %u: n = %zu (partition of the last sort: %zu)\n", s->id, s->n_host, s->part_valid ? s->part_n : (size_t)0);
     size_t cap = std::max<size_t>(s->n_upper, 1);
     if (cap >= 0xffffffffull) return set_error(PICG_ERR_ARG, "picg_species_sort: more than 2^32-1 particles per GPU are not supported");
     int nblocks = std::max(1, std::min(std::min(div_up(cap, SORT_TILE), g_sm_count * 4), 1024));
@@ -333,6 +341,7 @@ int species_exact_lists(picg_species_s* s) {
     u64* cnt = &s->ctr->n_movers;                                            // device-side mover count
     const int tail_only = s->movers_fresh ? 1 : 0;                           // the last deposit pass listed the partition's movers: only the appended tail is left
     if (!tail_only) CUDA_TRY(cudaMemsetAsync(cnt, 0, 8, g_stream));
+    else { k_movers_checkpoint<<<1, 1, 0, g_stream>>>(s->ctr, s->movers_saved ? 1 : 0); CHECK_LAUNCH(); s->movers_saved = true; }
     if (tail_only) g_movers_from_deposit++; else g_mover_scans++;
     size_t n_scan = tail_only ? std::max<size_t>(n > s->part_n ? n - s->part_n : 0, (size_t)1 << 18) : n;   // grid size only (grid-stride loop)
     int pgrid = std::max(1, std::min(div_up(std::max<size_t>(n_scan, 1), 256), g_sm_count * 8));
@@ -341,6 +350,7 @@ int species_exact_lists(picg_species_s* s) {
     u64 n_live_movers = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_live_movers, cnt, 8, cudaMemcpyDeviceToHost, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));
+    if (trace_sort()) fprintf(stderr, "[picgpu] lists of species %u: n = %zu, partition %zu, movers + tail = %llu (cap %zu, %s)\n", s->id, n, s->part_n, (unsigned long long)n_live_movers, mcap, tail_only ? "movers from the deposit pass" : "full scan");
     if (n_live_movers > mcap) { g_mover_resorts++; return sort_species(s); }  // too stale: periodic full radix sort
     int mgrid = std::max(1, std::min(div_up(std::max<size_t>((size_t)n_live_movers, 1), 256), g_sm_count * 4));
     int bits = key_bits_of(g);
@@ -362,9 +372,10 @@ int species_exact_lists(picg_species_s* s) {
         size_t vac_upper = s->part_n > n ? s->part_n - n : 0;
         if (n_live_movers + vac_upper > mcap) { g_mover_resorts++; return sort_species(s); }
         if (vac_upper) { LAUNCH(K_SORT_KEYS, k_find_vacated, std::max(1, std::min(div_up(vac_upper, 256), g_sm_count * 4)), 256, 0, s->home, &s->ctr->n, s->cell_start + g.nc, cnt, (u64)mcap, m_slot, m_home); CHECK_LAUNCH(); }
-        unsigned *ka = m_home, *kb = kB, *va = vA, *vb = vB;
+        unsigned *ka = tmp, *kb = kB, *va = vA, *vb = vB;                                           // sort a copy: the triples of the partition's movers stay intact for the next build
         int mgrid2 = std::max(1, std::min(div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), 256), g_sm_count * 4));
         LAUNCH(K_SORT_KEYS, k_iota_u32, mgrid2, 256, 0, cnt, va); CHECK_LAUNCH();
+        LAUNCH(K_SORT_KEYS, k_copy_u32, mgrid2, 256, 0, cnt, m_home, tmp); CHECK_LAUNCH();
         int hbits = 1; while ((1ull << hbits) < (u64)g.nc + 1) hbits++;
         rc = radix_sort_pairs(cnt, mcap, hbits, ka, va, kb, vb, counts, std::min(nblocks, div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), SORT_TILE))); if (rc) return rc;
         CUDA_TRY(cudaMemsetAsync(queue, 0, 4, g_stream));

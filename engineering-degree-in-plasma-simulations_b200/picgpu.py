@@ -412,7 +412,8 @@ class PotentialSolver:
 
 
 class MccStats(C.Structure):
-    _fields_ = [("candidates", C.c_uint64), ("collisions", C.c_uint64), ("ionizations", C.c_uint64), ("w_sigma_v_max", C.c_double), ("dropped", C.c_uint64)]
+    _fields_ = [("candidates", C.c_uint64), ("collisions", C.c_uint64), ("ionizations", C.c_uint64), ("w_sigma_v_max", C.c_double), ("dropped", C.c_uint64),
+                ("extras_capped", C.c_uint64), ("nan_products", C.c_uint64)]
 
 
 class MC_MEX_Ionization:
@@ -436,6 +437,10 @@ class MC_MEX_Ionization:
 
     def setWsvMax(self, v):
         _chk(lib().picg_mcc_set_wsv_max(self.h, C.c_double(v)))
+
+    def setVariant(self, variant):
+        """0: variable weights (ch4/v3, default); 1: the fixed-weight algorithm of ch4/v2 (ch4/v2/Interactions.cpp:566-641)."""
+        _chk(lib().picg_mcc_set_variant(self.h, int(variant)))
 
     def listCounts(self, which, world):
         out = np.empty((world.ni - 1, world.nj - 1, world.nk - 1), dtype=np.float64)

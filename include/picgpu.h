@@ -219,10 +219,18 @@ PICG_API int picg_mcc_create(picg_species_t neutrals, picg_species_t ions, picg_
                              const double* table_E, const double* table_sigma, int n_table, double E_ion_J, picg_mcc_t* out);
 PICG_API int picg_mcc_destroy(picg_mcc_t m);
 typedef struct { uint64_t candidates, collisions, ionizations; double w_sigma_v_max;
-                 uint64_t dropped; /* collisions skipped (untouched) because a product store was full; 0 in a healthy run */ } picg_mcc_stats;
+                 uint64_t dropped; /* collisions skipped (untouched) because a product store was full; 0 in a healthy run */
+                 uint64_t extras_capped; /* split-off neutrals beyond 16 per cell and call: created, but not selectable by later candidates of the same call (Interactions.cpp:699-701 has no bound) */
+                 uint64_t nan_products;  /* fixed-weight variant: ejected electrons with a NaN velocity (ionisation below the threshold in ch4/v2) that were not appended */
+               } picg_mcc_stats;
 /* Interaction::apply(dt) -> MC_MEX_Ionization::apply_vector_indexes  Interactions.cpp:567-762 */
 PICG_API int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* stats /*may be NULL*/);
 PICG_API int picg_mcc_set_wsv_max(picg_mcc_t m, double v);
+/* variant 0 (default): the variable-weight algorithm of ch4/v3.  variant 1: MC_MEX_Ionization::apply of ch4/v2 with fixed weights
+ * (ch4/v2/Interactions.cpp:566-641, collide :678-735, evaluateSigmaIon :560-563; BASELINE config 3): candidate count
+ * 0.5*np_n*np_e*neutrals.mpw0*(sigma v)_max*dt/dV, unweighted acceptance, no ionisation threshold guard, products through
+ * Species::addParticle (ch4/v2/Species.cpp:226-237: bounds / object filter, half-step rewind), neutrals never depleted. */
+PICG_API int picg_mcc_set_variant(picg_mcc_t m, int variant);
 /* debug / tests: lengths of the exact per-cell particle lists the collision kernel uses (0 neutrals, 1 electrons) */
 PICG_API int picg_mcc_list_counts(picg_mcc_t m, int which, double* cells);
 PICG_API int picg_mcc_sigma(picg_mcc_t m, int n, const double* E_eV, double* sigma_coll, double* sigma_ion); /* evaluateSigmaColl/Ion :541-566 */
