@@ -286,6 +286,7 @@ def run_ours(args):
             t0 = stamp("inject", t0)
         if mcc is not None:
             st = mcc.apply(wl["dt"])
+            counts["mcc"] = (st.candidates, st.collisions, st.ionizations, st.dropped)
             if world > 1:                                   # the acceptance ceiling must be the same on every rank
                 mcc.setWsvMax(mg.common_ceiling(st.w_sigma_v_max, reduce_max))
             t0 = stamp("mcc", t0)
@@ -365,8 +366,8 @@ def run_ours(args):
                 cur = pg.timers_read()
                 delta = {kk: round(v[0] - trace_prev.get(kk, (0.0, 0))[0], 3) for kk, v in cur.items() if v[0] - trace_prev.get(kk, (0.0, 0))[0] > 0.02}
                 trace_prev.clear(); trace_prev.update(cur)
-                print("step %d: n=%s part=%s movers(stats)=%s ms=%s" % (ts0 + k, {sp.name: sp.getNumParticles() for sp in order}, {sp.name: sp.partitionSize() for sp in order},
-                      pg.mover_stats(), json.dumps(delta)), file=sys.stderr)
+                print("step %d: n=%s part=%s movers(stats)=%s mcc(cand,coll,ion,drop)=%s ms=%s" % (ts0 + k, {sp.name: sp.getNumParticles() for sp in order}, {sp.name: sp.partitionSize() for sp in order},
+                      pg.mover_stats(), counts.get("mcc"), json.dumps(delta)), file=sys.stderr)
             if e2e:                                           # what the reference loop reads every step: counts + diagnostics + rho
                 t0 = time.perf_counter()
                 for sp in order:

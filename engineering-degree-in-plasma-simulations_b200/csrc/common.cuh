@@ -126,8 +126,7 @@ struct picg_mcc_s {
     u64 step = 0;
     size_t last_appends[3] = {0, 0, 0};   // neutrals, electrons, ions appended by the previous apply (capacity estimate)
     int fixed_weight = 0;              // 1: the fixed-weight algorithm of ch4/v2 (Interactions.cpp:566-641) instead of v3's variable weights
-    unsigned char* chunk_used[3] = {nullptr, nullptr, nullptr}; size_t chunk_cap[3] = {0, 0, 0};   // per-chunk fill counts of the appended regions (mcc.cu)
-    unsigned* orphans[3] = {nullptr, nullptr, nullptr};
+    unsigned* orphans = nullptr;       // device: 3 x (count, slots): product slots reserved by a collision that could not complete (mcc.cu)
 };
 
 struct picg_dsmc_s {
@@ -168,7 +167,7 @@ enum KernelId {
     K_PUSH_ELECTRONS = 0, K_PUSH_DEPOSIT, K_PUSH_REFLECT, K_PUSH_HEAVY, K_COMPACT, K_DEPOSIT, K_FINALIZE_DEN,
     K_CHARGE_DENSITY, K_SOR, K_RESIDUAL, K_COMPUTE_EF, K_SORT_KEYS, K_SORT_HIST, K_SORT_SCAN, K_SORT_SCATTER,
     K_SORT_PERMUTE, K_CELL_START, K_MCC, K_SOURCE, K_ADD_PARTICLES, K_MOMENTS, K_COUNT_CELLS, K_TRANSPOSE,
-    K_DIAG, K_MISC, K_PUSH_HEAVY_DEPOSIT, K_HEAVY_IMPACTS, K_DSMC, K_PUSH_NEUTRAL, K_PCG, K_DEPOSIT_TAIL, K_NUM_KERNELS
+    K_DIAG, K_MISC, K_PUSH_HEAVY_DEPOSIT, K_HEAVY_IMPACTS, K_DSMC, K_PUSH_NEUTRAL, K_PCG, K_DEPOSIT_TAIL, K_MCC_APPEND, K_NUM_KERNELS
 };
 
 #define CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return picg::cuda_fail(_e, #expr, __FILE__, __LINE__); } while (0)

@@ -12,10 +12,10 @@
 //           through Species::addParticle (bounds / object filter and half-step rewind, ch4/v2/Species.cpp:226-237), neutrals never
 //           depleted.  BASELINE.json config 3.
 // Appends.  Every product is a new particle at the end of a store.  One atomic per product on the store's counter serialises
-// at the L2 (one address: ~0.45 ns each, 9 ms for the 2e7 split-off neutrals of a late step), so a warp takes CHUNKS of 32 slots
-// from the counter (one atomic per 32 products) and hands them out through a packed (base, used) word in shared memory.
-// The slots of a chunk that stay unused (at most 31 per warp and store at the end of the kernel) are holes in the freshly
-// appended region; they are listed afterwards and closed by the compaction the push already uses (push.cu).
+// at the L2 (one address: ~0.45 ns each, 9 ms for the 2e7 split-off neutrals of a late step).  The candidate loop is therefore
+// warp-synchronous: a warp owns 32 consecutive cells (lane = cell), iteration t handles the t-th candidate of every cell, and the
+// products of one iteration take consecutive slots of ONE atomicAdd per store (warp_reserve).  Products of neighbouring cells end
+// up next to each other in the appended tail, which the tail deposit likes.
 #include "common.cuh"
 #include "philox.cuh"
 #include "celllists.cuh"
@@ -93,36 +93,28 @@ __device__ __forceinline__ bool collide(PhiloxStream& r, const MccParams& P, con
     return false;
 }
 
-// ---------------------------------------------------------------- appends: chunks of 32 slots per warp and store
+// ---------------------------------------------------------------- appends: one atomic per warp iteration and store
 #define MCC_THREADS 128
-#define MCC_WARPS (MCC_THREADS / 32)
-#define MCC_CHUNK 32
 #define MCC_ORPHANS 4096
-struct ChunkPool {
-    u64* cursor;              // the store's live count, used as a bump pointer: advances by MCC_CHUNK during the kernel
-    u64 base0, limit;         // first appended slot; chunks must end at or below limit (= base0 + 32 * floor((cap - base0) / 32))
-    unsigned char* used;      // used[k]: filled slots of chunk k = (slot - base0) / 32; preset to 32 (full), lowered where a chunk stays partly empty
-    unsigned* orphans;        // [0]: count, then slots that were reserved for a collision that could not complete (a partner store was full)
-};
-// Slot reservation BEFORE any state is changed: a collision whose products do not fit is skipped as a whole (and counted), so a
-// full store can never leave half-applied collisions behind.  word = (chunk base << 6) | slots handed out; ~0 = no chunk yet.
-__device__ __forceinline__ long long reserve_slot(u64* word, const ChunkPool& P) {
-    for (;;) {
-        const u64 old = *(volatile u64*)word;
-        const unsigned used = (unsigned)(old & 63);
-        if (used < MCC_CHUNK) {
-            if (atomicCAS((unsigned long long*)word, old, old + 1) == old) return (long long)((old >> 6) + used);
-            continue;
-        }
-        const u64 nb = atomicAdd((unsigned long long*)P.cursor, (u64)MCC_CHUNK);
-        if (nb + MCC_CHUNK > P.limit) return -1;                                   // store full (the counter is clamped after the kernel)
-        if (atomicCAS((unsigned long long*)word, old, (nb << 6) | 1) == old) return (long long)nb;
-        P.used[(nb - P.base0) >> 5] = 0;                                           // another lane of the warp installed a chunk first: this one stays empty
-    }
+// A warp walks 32 consecutive cells in lockstep (lane = cell); iteration t handles candidate t of every cell that still has
+// one.  The lanes whose candidate creates a product take consecutive slots of ONE atomicAdd on the store's counter.
+// All 32 lanes call.  Returns the slot, or -1 (not wanted, or the store is full: the counter is clamped after the kernel).
+__device__ __forceinline__ long long warp_reserve(bool want, int lane, u64* cursor, u64 cap) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (!mask) return -1;
+    const int leader = __ffs(mask) - 1;
+    u64 base = 0;
+    if (lane == leader) base = atomicAdd((unsigned long long*)cursor, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!want) return -1;
+    const u64 dst = base + __popc(mask & ((1u << lane) - 1));
+    return dst < cap ? (long long)dst : -1;
 }
-__device__ __forceinline__ void orphan_slot(const ChunkPool& P, long long slot) {
-    unsigned t = atomicAdd(P.orphans, 1u);
-    if (t < MCC_ORPHANS) P.orphans[1 + t] = (unsigned)slot;
+// a slot that was reserved for a collision that could not complete (the partner store was full): listed, closed by the
+// compaction after the kernel (orphans[0]: count)
+__device__ __forceinline__ void orphan_slot(unsigned* orphans, long long slot) {
+    unsigned t = atomicAdd(orphans, 1u);
+    if (t < MCC_ORPHANS) orphans[1 + t] = (unsigned)slot;
 }
 __device__ __forceinline__ void write_slot(const Store& s, long long dst, const double pos[3], const double v[3], double mpw) {
     s.a[0][dst] = pos[0]; s.a[1][dst] = pos[1]; s.a[2][dst] = pos[2]; s.a[3][dst] = v[0]; s.a[4][dst] = v[1]; s.a[5][dst] = v[2]; s.a[6][dst] = mpw;
@@ -144,101 +136,126 @@ __device__ __forceinline__ bool add_particle_filter_rewind(const Grid& g, const 
 // stats: [0] candidates [1] collisions [2] ionisations [3] skipped (electron heavier than neutral)
 //        [5] dropped because a product store was full (collision skipped untouched)
 //        [6] split-off neutrals beyond MCC_EXTRA per cell and call (created, but not selectable by later candidates of the same call)
-//        [7] fixed-weight variant: created electrons with a NaN velocity (ionisation below the threshold, ch4/v2 only) that were not appended
+//        [7] fixed-weight variant: created electrons with a NaN velocity (ionisation below the threshold, ch4/v2 only; appended as the reference does)
+// orphans: [0..2] MCC_ORPHANS + 1 words each for neutrals / electrons / ions
 template <int FIXED>
-__global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, CellLists Ln, CellLists Le, ChunkPool Cn, ChunkPool Ce,
-                                                        ChunkPool Ci, double* __restrict__ wsv, u64* __restrict__ stats, double dt, uint64_t seed, uint32_t stream, uint32_t call) {
-    __shared__ u64 s_chunk[3][MCC_WARPS];
-    if (threadIdx.x < 3 * MCC_WARPS) (&s_chunk[0][0])[threadIdx.x] = ~0ull;
-    __syncthreads();
-    const int wib = threadIdx.x >> 5;
-    u64 *wn = &s_chunk[0][wib], *we = &s_chunk[1][wib], *wi = &s_chunk[2][wib];
+__global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, CellLists Ln, CellLists Le, unsigned* __restrict__ orphans,
+                                                        double* __restrict__ wsv, u64* __restrict__ stats, double dt, uint64_t seed, uint32_t stream, uint32_t call) {
+    const int lane = threadIdx.x & 31;
     const double W_max = wsv[0];
     u64 n_cand = 0, n_coll = 0, n_ion = 0, n_skip = 0, n_drop = 0, n_capped = 0, n_nan = 0; double step_max = 0;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.nc; c += gridDim.x * blockDim.x) {
-        CellView ve = cell_view(Le, c); int np_e = ve.np;
-        if (np_e <= 0) continue;
-        CellView vn = cell_view(Ln, c); int np_n0 = vn.np;
-        if (np_n0 <= 0) continue;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int c0 = warp * 32; c0 < g.nc; c0 += nwarps * 32) {
+        const int c = c0 + lane;
+        CellView ve, vn; int np_e = 0, np_n0 = 0, n_groups = 0;
+        if (c < g.nc) {
+            ve = cell_view(Le, c); np_e = ve.np;
+            if (np_e > 0) { vn = cell_view(Ln, c); np_n0 = vn.np; }
+        }
         int np_n = np_n0;
-        // v3 :646 / ch4/v2 :591.  Multi-GPU: the particles of a cell are spread over G ranks, so the cell's candidate count is estimated
-        // from the local populations (x G^2), rounded ONCE like the reference's and dealt out to the ranks: n/G each, the n%G left
-        // over to a rotating subset.  Rounding per rank instead would lose every cell whose share is below one half.
-        double frac = FIXED ? 0.5 * np_n * np_e * P.neu_mpw0 * W_max * dt * P.inv_dv * P.rank_scale : np_n * np_e * W_max * dt * P.inv_dv * P.rank_scale;
-        int n_groups = (int)(frac + 0.5);
-        if (P.world > 1) n_groups = n_groups / P.world + ((unsigned)(c + (int)call + P.rank) % (unsigned)P.world < (unsigned)(n_groups % P.world) ? 1 : 0);
-        if (n_groups > np_n) n_groups = np_n - 1;                                         // v3 :649-653 / v2 :598-600
-        if (n_groups <= 0) continue;
+        if (np_e > 0 && np_n0 > 0) {
+            // v3 :646 / ch4/v2 :591.  Multi-GPU: the particles of a cell are spread over G ranks, so the cell's candidate count is estimated
+            // from the local populations (x G^2), rounded ONCE like the reference's and dealt out to the ranks: n/G each, the n%G left
+            // over to a rotating subset.  Rounding per rank instead would lose every cell whose share is below one half.
+            double frac = FIXED ? 0.5 * np_n * np_e * P.neu_mpw0 * W_max * dt * P.inv_dv * P.rank_scale : np_n * np_e * W_max * dt * P.inv_dv * P.rank_scale;
+            n_groups = (int)(frac + 0.5);
+            if (P.world > 1) n_groups = n_groups / P.world + ((unsigned)(c + (int)call + P.rank) % (unsigned)P.world < (unsigned)(n_groups % P.world) ? 1 : 0);
+            if (n_groups > np_n) n_groups = np_n - 1;                                     // v3 :649-653 / v2 :598-600
+            if (n_groups < 0) n_groups = 0;
+        }
+        const int max_groups = __reduce_max_sync(0xffffffffu, n_groups);
+        if (max_groups == 0) continue;                                                    // warp-uniform
         PhiloxStream r; r.init(seed, stream, (u64)c, call);
         long long extra[MCC_EXTRA]; int n_extra = 0;
-        for (int t = 0; t < n_groups; t++) {
-            int a = (int)(r.next() * np_n);                                                // rnd(0,np) = 0 + rnd()*(np-0)
-            int b = (int)(r.next() * np_e);
-            u64 pn = a < np_n0 ? (u64)cell_pick(Ln, vn, a) : (u64)extra[a - np_n0];
-            u64 pe = (u64)cell_pick(Le, ve, b);
-            double vn_[3] = {neu.a[3][pn], neu.a[4][pn], neu.a[5][pn]}, ve_[3] = {ele.a[3][pe], ele.a[4][pe], ele.a[5][pe]};
-            double d[3] = {vn_[0] - ve_[0], vn_[1] - ve_[1], vn_[2] - ve_[2]};
-            double v_rel = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-            double E_rel = P.E_rel_eV * v_rel * v_rel;
-            double s_coll = sigma_coll(P, E_rel);
-            n_cand++;
-            if (FIXED) {                                                                   // ch4/v2 :608-632
-                double sv = s_coll * v_rel;
-                if (sv > step_max) step_max = sv;
-                if (sv / W_max > r.next()) {
-                    n_coll++;
-                    double vnew[3] = {0, 0, 0};
-                    bool ionised = collide(r, P, vn_, ve_, vnew, s_coll);
-                    ele.a[3][pe] = ve_[0]; ele.a[4][pe] = ve_[1]; ele.a[5][pe] = ve_[2];   // collide works on a reference to the electron's velocity
-                    if (ionised) {
-                        n_ion++;
-                        double pos[3] = {neu.a[0][pn], neu.a[1][pn], neu.a[2][pn]};
-                        for (int q = 0; q < P.ions_to_create; q++) {                       // ions.addParticle(pos, vel_neutral, ions.mpw0) :624-626
-                            double vi[3] = {vn_[0], vn_[1], vn_[2]};
-                            if (!add_particle_filter_rewind(g, P.ef, P.qm_ion, P.half_dt, pos, vi)) continue;
-                            long long s1 = reserve_slot(wi, Ci);
-                            if (s1 < 0) { n_drop++; continue; }
-                            write_slot(ion, s1, pos, vi, P.ion_mpw0);
+        for (int t = 0; t < max_groups; t++) {
+            // kind of product this lane's candidate asks for: 0 none, 1 split-off neutral, 2 ion + electron
+            int kind = 0; u64 pn = 0, pe = 0;
+            double vn_[3] = {0, 0, 0}, ve_[3] = {0, 0, 0}, vnew[3] = {0, 0, 0}, pos[3] = {0, 0, 0}, Wn = 0, We = 0, Wl = 0;
+            bool ion_ok[2] = {false, false};                                               // FIXED: addParticle accepts the ion / the electron
+            double vi[3] = {0, 0, 0};
+            if (t < n_groups) {
+                int a = (int)(r.next() * np_n);                                            // rnd(0,np) = 0 + rnd()*(np-0)
+                int b = (int)(r.next() * np_e);
+                pn = a < np_n0 ? (u64)cell_pick(Ln, vn, a) : (u64)extra[a - np_n0];
+                pe = (u64)cell_pick(Le, ve, b);
+                vn_[0] = neu.a[3][pn]; vn_[1] = neu.a[4][pn]; vn_[2] = neu.a[5][pn]; ve_[0] = ele.a[3][pe]; ve_[1] = ele.a[4][pe]; ve_[2] = ele.a[5][pe];
+                double d[3] = {vn_[0] - ve_[0], vn_[1] - ve_[1], vn_[2] - ve_[2]};
+                double v_rel = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                double E_rel = P.E_rel_eV * v_rel * v_rel;
+                double s_coll = sigma_coll(P, E_rel);
+                n_cand++;
+                if (FIXED) {                                                               // ch4/v2 :608-632
+                    double sv = s_coll * v_rel;
+                    if (sv > step_max) step_max = sv;
+                    if (sv / W_max > r.next()) {
+                        n_coll++;
+                        bool ionised = collide(r, P, vn_, ve_, vnew, s_coll);
+                        ele.a[3][pe] = ve_[0]; ele.a[4][pe] = ve_[1]; ele.a[5][pe] = ve_[2];   // collide works on a reference to the electron's velocity
+                        if (ionised) {
+                            n_ion++; kind = 2;
+                            pos[0] = neu.a[0][pn]; pos[1] = neu.a[1][pn]; pos[2] = neu.a[2][pn];
+                            vi[0] = vn_[0]; vi[1] = vn_[1]; vi[2] = vn_[2];
+                            ion_ok[0] = add_particle_filter_rewind(g, P.ef, P.qm_ion, P.half_dt, pos, vi);      // ions.addParticle(pos, vel_neutral, ions.mpw0) :624-626
+                            // electrons.addParticle(pos, vel_new, electrons.mpw0) :628.  Below the ionisation threshold ch4/v2 computes the
+                            // ejected electron from a negative energy: its velocity is NaN and the reference appends it all the same (addParticle
+                            // only tests the position); between the electrodes it dies at the next electron push, where Rectangle::inObject
+                            // holds for a NaN position (ch4/v2/Species.cpp:193-207) - here as there.  Reproduced, and counted.
+                            if (isnan(vnew[0]) || isnan(vnew[1]) || isnan(vnew[2])) n_nan++;
+                            ion_ok[1] = add_particle_filter_rewind(g, P.ef, P.qm_ele, P.half_dt, pos, vnew);
                         }
-                        // electrons.addParticle(pos, vel_new, electrons.mpw0) :628.  Below the ionisation threshold ch4/v2 computes the
-                        // ejected electron from a negative energy: its velocity is NaN and the reference appends it all the same (its next
-                        // push then indexes the field with (int)NaN).  Such products are counted and not appended here.
-                        if (isnan(vnew[0]) || isnan(vnew[1]) || isnan(vnew[2])) n_nan++;
-                        else if (add_particle_filter_rewind(g, P.ef, P.qm_ele, P.half_dt, pos, vnew)) {
-                            long long s2 = reserve_slot(we, Ce);
-                            if (s2 < 0) n_drop++; else write_slot(ele, s2, pos, vnew, P.ele_mpw0);
-                        }
+                    }
+                } else {
+                    Wn = neu.a[6][pn]; We = ele.a[6][pe];
+                    double Wg = Wn < We ? We : Wn; Wl = Wn < We ? Wn : We;                  // greaterLesser funkc.h:19-25
+                    double Wsv = Wg * s_coll * v_rel;
+                    if (Wsv > step_max) step_max = Wsv;
+                    if (r.next() < Wsv / W_max) {
+                        n_coll++;
+                        if (Wn > We) {                                                     // split the neutral (:684-703)
+                            bool ionised = collide(r, P, vn_, ve_, vnew, s_coll);          // pure: works on local copies
+                            kind = ionised ? 2 : 1;
+                            pos[0] = neu.a[0][pn]; pos[1] = neu.a[1][pn]; pos[2] = neu.a[2][pn];
+                        } else if (Wn < We) {
+                            n_skip++;      // the reference's electron-heavier branch is defective; not reproduced, counted
+                        }                  // equal weights: accepted pair does nothing (:727-734)
                     }
                 }
+            }
+            // ---- the warp's products of this iteration take their slots (every lane is here: the loop bounds are warp-uniform)
+            if (FIXED) {
+                for (int q = 0; q < P.ions_to_create; q++) {                               // :623-626, one ion per round
+                    const bool want = kind == 2 && ion_ok[0];
+                    long long s1 = warp_reserve(want, lane, &ion.ctr->n, ion.cap);
+                    if (want) { if (s1 < 0) n_drop++; else write_slot(ion, s1, pos, vi, P.ion_mpw0); }
+                }
+                const bool want = kind == 2 && ion_ok[1];
+                long long s2 = warp_reserve(want, lane, &ele.ctr->n, ele.cap);
+                if (want) { if (s2 < 0) n_drop++; else write_slot(ele, s2, pos, vnew, P.ele_mpw0); }
                 continue;
             }
-            double Wn = neu.a[6][pn], We = ele.a[6][pe];
-            double Wg = Wn < We ? We : Wn, Wl = Wn < We ? Wn : We;                         // greaterLesser funkc.h:19-25
-            double Wsv = Wg * s_coll * v_rel;
-            if (Wsv > step_max) step_max = Wsv;
-            if (r.next() < Wsv / W_max) {
-                n_coll++;
-                if (Wn > We) {                                                             // split the neutral (:684-703)
-                    double vnew[3] = {0, 0, 0};
-                    bool ionised = collide(r, P, vn_, ve_, vnew, s_coll);                  // pure: works on local copies
-                    long long s1 = -1, s2 = -1;
-                    if (ionised) { s1 = reserve_slot(wi, Ci); if (s1 >= 0) { s2 = reserve_slot(we, Ce); if (s2 < 0) { orphan_slot(Ci, s1); s1 = -1; } } }
-                    else s1 = reserve_slot(wn, Cn);
-                    if (s1 < 0) { n_drop++; n_coll--; continue; }                          // no room for the products: skip the collision untouched
-                    neu.a[6][pn] = Wn - We;
-                    ele.a[3][pe] = ve_[0]; ele.a[4][pe] = ve_[1]; ele.a[5][pe] = ve_[2];
-                    double pos[3] = {neu.a[0][pn], neu.a[1][pn], neu.a[2][pn]};
-                    if (ionised) {
-                        n_ion++;
-                        write_slot(ion, s1, pos, vn_, Wl);                                 // no half-step rewind (:694-695)
-                        write_slot(ele, s2, pos, vnew, Wl);
-                    } else {
-                        write_slot(neu, s1, pos, vn_, We);                                 // split-off neutral of the electron's weight
-                        if (n_extra < MCC_EXTRA) { extra[n_extra++] = s1; np_n++; } else n_capped++;
-                    }
-                } else if (Wn < We) {
-                    n_skip++;          // the reference's electron-heavier branch is defective; not reproduced, counted
-                }                      // equal weights: accepted pair does nothing (:727-734)
+            // Slot reservation BEFORE any state is changed: a collision whose products do not fit is skipped as a whole (and counted), so a
+            // full store can never leave half-applied collisions behind.
+            long long s0 = warp_reserve(kind == 1, lane, &neu.ctr->n, neu.cap);
+            long long s1 = warp_reserve(kind == 2, lane, &ion.ctr->n, ion.cap);
+            long long s2 = warp_reserve(kind == 2, lane, &ele.ctr->n, ele.cap);
+            if (kind == 2 && (s1 < 0 || s2 < 0)) {
+                if (s1 >= 0) orphan_slot(orphans + 2 * (MCC_ORPHANS + 1), s1);
+                if (s2 >= 0) orphan_slot(orphans + 1 * (MCC_ORPHANS + 1), s2);
+                kind = -1;
+            }
+            if (kind == 1 && s0 < 0) kind = -1;
+            if (kind == -1) { n_drop++; n_coll--; }                                        // no room for the products: the collision is skipped untouched
+            if (kind > 0) {
+                neu.a[6][pn] = Wn - We;
+                ele.a[3][pe] = ve_[0]; ele.a[4][pe] = ve_[1]; ele.a[5][pe] = ve_[2];
+                if (kind == 2) {
+                    n_ion++;
+                    write_slot(ion, s1, pos, vn_, Wl);                                     // no half-step rewind (:694-695)
+                    write_slot(ele, s2, pos, vnew, Wl);
+                } else {
+                    write_slot(neu, s0, pos, vn_, We);                                     // split-off neutral of the electron's weight
+                    if (n_extra < MCC_EXTRA) { extra[n_extra++] = s0; np_n++; } else n_capped++;
+                }
             }
         }
     }
@@ -256,32 +273,22 @@ __global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Sto
         atomicAdd(&stats[6], sh[5]); atomicAdd(&stats[7], sh[6]);
         atomic_max_pos_double(&wsv[1], sh_max);
     }
-    // the warps' current chunks are only partly used (every lane of the block is past its last reservation: barrier above)
-    if (threadIdx.x < 3 * MCC_WARPS) {
-        const u64 word = (&s_chunk[0][0])[threadIdx.x];
-        const ChunkPool& C = threadIdx.x < MCC_WARPS ? Cn : (threadIdx.x < 2 * MCC_WARPS ? Ce : Ci);
-        if (word != ~0ull && (word & 63) < MCC_CHUNK) C.used[((word >> 6) - C.base0) >> 5] = (unsigned char)(word & 63);
-    }
 }
-// After the kernel: slots [base0, end) were handed out in chunks, end = min(counter, limit).  Lists the unused slots of partly
-// filled chunks and the orphans as "dead" for the compaction (push.cu), which closes the holes and lowers the count.
-__global__ void __launch_bounds__(256) k_mcc_holes(ChunkPool C, SpeciesCounters* ctr, unsigned* __restrict__ dead_list) {
-    const u64 end = min(ctr->n, C.limit);
-    const u64 nchunks = end > C.base0 ? (end - C.base0) >> 5 : 0;
-    for (u64 k = blockIdx.x * (u64)blockDim.x + threadIdx.x; k < nchunks; k += (u64)gridDim.x * blockDim.x) {
-        const unsigned u = C.used[k];
-        if (u >= MCC_CHUNK) continue;
-        u64 dst = atomicAdd(&ctr->n_dead, (u64)(MCC_CHUNK - u));
-        for (unsigned t = u; t < MCC_CHUNK; t++) dead_list[dst++] = (unsigned)(C.base0 + (k << 5) + t);
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const unsigned no = min(C.orphans[0], (unsigned)MCC_ORPHANS);
-        if (no) { u64 dst = atomicAdd(&ctr->n_dead, (u64)no); for (unsigned t = 0; t < no; t++) dead_list[dst++] = C.orphans[1 + t]; }
-    }
+// After the kernel.  (1) W_sigma_v_rel_max <- max sampled value of this step, only if a collision happened (:751-756).  (2) A counter
+// that ran past the capacity (the reservations beyond it failed) goes back to the capacity.  (3) stats[8 + k]: orphans of store k.
+__global__ void k_mcc_finish(double* wsv, u64* stats, SpeciesCounters* c0, u64 cap0, SpeciesCounters* c1, u64 cap1, SpeciesCounters* c2, u64 cap2, const unsigned* orphans) {
+    if (stats[1]) wsv[0] = wsv[1];
+    if (c0->n > cap0) c0->n = cap0;
+    if (c1->n > cap1) c1->n = cap1;
+    if (c2->n > cap2) c2->n = cap2;
+    for (int k = 0; k < 3; k++) stats[8 + k] = min(orphans[k * (MCC_ORPHANS + 1)], (unsigned)MCC_ORPHANS);
 }
-__global__ void k_mcc_clamp(ChunkPool C, SpeciesCounters* ctr) { if (ctr->n > C.limit) ctr->n = C.limit; if (ctr->n < C.base0) ctr->n = C.base0; }
-// W_sigma_v_rel_max <- max sampled value of this step, only if a collision happened (:751-756)
-__global__ void k_mcc_finish(double* wsv, const u64* stats) { if (stats[1]) wsv[0] = wsv[1]; }
+// rare (a product store ran full in the middle of an ionisation): the orphaned slots become the dead list of the compaction (push.cu)
+__global__ void k_mcc_orphans(const unsigned* __restrict__ orphans, SpeciesCounters* ctr, unsigned* __restrict__ dead_list) {
+    const unsigned no = min(orphans[0], (unsigned)MCC_ORPHANS);
+    for (unsigned t = threadIdx.x; t < no; t += blockDim.x) dead_list[t] = orphans[1 + t];
+    if (threadIdx.x == 0) ctr->n_dead = no;
+}
 __global__ void k_sigma_eval(MccParams P, int n, const double* __restrict__ E, double* __restrict__ sc, double* __restrict__ si) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) { sc[t] = sigma_coll(P, E[t]); si[t] = sigma_ion(P, E[t]); }
 }
@@ -334,14 +341,14 @@ int picg_mcc_create(picg_species_t neutrals, picg_species_t ions, picg_species_t
     for (size_t i = 0; i < tab.size(); i++) { E[i] = tab[i].first; S[i] = tab[i].second; }
     cudaError_t e;
     if ((e = cudaMalloc(&m->tab_E, E.size() * 8)) != cudaSuccess || (e = cudaMalloc(&m->tab_s, S.size() * 8)) != cudaSuccess ||
-        (e = cudaMalloc(&m->wsv, 2 * 8)) != cudaSuccess || (e = cudaMalloc(&m->stats, 8 * 8)) != cudaSuccess) {
+        (e = cudaMalloc(&m->wsv, 2 * 8)) != cudaSuccess || (e = cudaMalloc(&m->stats, 16 * 8)) != cudaSuccess) {
         picg_mcc_destroy(m); return cuda_fail(e, "cudaMalloc(mcc)", __FILE__, __LINE__);
     }
     CUDA_TRY(cudaMemcpyAsync(m->tab_E, E.data(), E.size() * 8, cudaMemcpyHostToDevice, g_stream));
     CUDA_TRY(cudaMemcpyAsync(m->tab_s, S.data(), S.size() * 8, cudaMemcpyHostToDevice, g_stream));
     double wsv[2] = {1e-14 * std::max(electrons->mpw0, neutrals->mpw0), 0.0};             // Interactions.h:129, .cpp:534
     CUDA_TRY(cudaMemcpyAsync(m->wsv, wsv, 16, cudaMemcpyHostToDevice, g_stream));
-    CUDA_TRY(cudaMemsetAsync(m->stats, 0, 64, g_stream));
+    CUDA_TRY(cudaMemsetAsync(m->stats, 0, 128, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));
     *out = m;
     return PICG_OK;
@@ -351,7 +358,7 @@ int picg_mcc_destroy(picg_mcc_t m) {
     if (!m) return PICG_OK;
     if (g_stream) cudaStreamSynchronize(g_stream);
     cudaFree(m->tab_E); cudaFree(m->tab_s); cudaFree(m->wsv); cudaFree(m->stats);
-    for (int k = 0; k < 3; k++) { cudaFree(m->chunk_used[k]); cudaFree(m->orphans[k]); }
+    cudaFree(m->orphans);
     delete m; return PICG_OK;
 }
 
@@ -394,7 +401,7 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     const Grid& g = m->w->g;
     // room for the products: 2x what the last call appended, at least 1 % of the store.  A collision whose products do
     // not fit is skipped untouched on the device and counted (stats.dropped); the store is then grown for the next call.
-    CUDA_TRY(cudaMemsetAsync(m->stats, 0, 64, g_stream));
+    CUDA_TRY(cudaMemsetAsync(m->stats, 0, 128, g_stream));
     rc = species_refresh_count(neu); if (rc) return rc;        // synchronises
     rc = species_refresh_count(ele); if (rc) return rc;
     rc = species_refresh_count(ion); if (rc) return rc;
@@ -406,46 +413,28 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     }
     double zero = 0; CUDA_TRY(cudaMemcpyAsync(m->wsv + 1, &zero, 8, cudaMemcpyHostToDevice, g_stream));
     m->step++;
-    // chunk pools of the three stores (neutrals, electrons, ions): appended region [n_before, limit), per-chunk fill counts preset to "full"
-    ChunkPool pool[3];
-    size_t max_region = 0;
-    for (int k = 0; k < 3; k++) {
-        picg_species_s* sp = sp3[k];
-        const size_t region = sp->cap - n_before[k], nchunks = region / MCC_CHUNK + 1;
-        max_region = std::max(max_region, region);
-        if (m->chunk_cap[k] < nchunks) {
-            cudaStreamSynchronize(g_stream); cudaFree(m->chunk_used[k]); m->chunk_used[k] = nullptr; m->chunk_cap[k] = 0;
-            cudaError_t e = cudaMalloc(&m->chunk_used[k], nchunks + nchunks / 4 + 256);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(mcc chunk table)", __FILE__, __LINE__);
-            m->chunk_cap[k] = nchunks + nchunks / 4 + 256; note_realloc("mcc chunk table", m->chunk_cap[k]);
-        }
-        if (!m->orphans[k]) CUDA_TRY(cudaMalloc(&m->orphans[k], (MCC_ORPHANS + 1) * 4));
-        CUDA_TRY(cudaMemsetAsync(m->chunk_used[k], MCC_CHUNK, nchunks, g_stream));
-        CUDA_TRY(cudaMemsetAsync(m->orphans[k], 0, 4, g_stream));
-        pool[k].cursor = &sp->ctr->n; pool[k].base0 = n_before[k]; pool[k].limit = n_before[k] + (region / MCC_CHUNK) * MCC_CHUNK;
-        pool[k].used = m->chunk_used[k]; pool[k].orphans = m->orphans[k];
-    }
-    rc = ensure_scratch(m->w, compact_scratch_bytes(std::max<size_t>(max_region, 1))); if (rc) return rc;
+    if (!m->orphans) CUDA_TRY(cudaMalloc(&m->orphans, 3 * (MCC_ORPHANS + 1) * 4));
+    for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemsetAsync(m->orphans + k * (MCC_ORPHANS + 1), 0, 4, g_stream));
     int grid = std::max(1, std::min(div_up(g.nc, MCC_THREADS), g_sm_count * 16));
-    if (m->fixed_weight) LAUNCH(K_MCC, k_mcc<1>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), pool[0], pool[1], pool[2],
+    if (m->fixed_weight) LAUNCH(K_MCC, k_mcc<1>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), m->orphans,
                                 m->wsv, m->stats, dt, g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
-    else LAUNCH(K_MCC, k_mcc<0>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), pool[0], pool[1], pool[2],
+    else LAUNCH(K_MCC, k_mcc<0>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), m->orphans,
                 m->wsv, m->stats, dt, g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
     CHECK_LAUNCH();
-    LAUNCH(K_MCC, k_mcc_finish, 1, 1, 0, m->wsv, m->stats); CHECK_LAUNCH();
-    // close the holes of the chunked appends (all of them lie in the appended region, beyond every cell partition)
+    LAUNCH(K_MCC_APPEND, k_mcc_finish, 1, 1, 0, m->wsv, m->stats, neu->ctr, (u64)neu->cap, ele->ctr, (u64)ele->cap, ion->ctr, (u64)ion->cap, m->orphans); CHECK_LAUNCH();
+    u64 host_stats[16];
+    CUDA_TRY(cudaMemcpyAsync(host_stats, m->stats, 128, cudaMemcpyDeviceToHost, g_stream));
+    for (picg_species_s* s : {neu, ele, ion}) { s->n_host_valid = false; s->n_upper = s->cap; }
+    rc = species_refresh_count(neu); if (rc) return rc;          // synchronises: host_stats is valid from here on
     for (int k = 0; k < 3; k++) {
+        if (!host_stats[8 + k]) continue;                       // orphaned slots (a partner store ran full): close the holes
         picg_species_s* sp = sp3[k];
-        const size_t region = std::max<size_t>(sp->cap - n_before[k], 1);
-        LAUNCH(K_MCC, k_mcc_holes, std::max(1, std::min(div_up(region / MCC_CHUNK + 1, 256), g_sm_count * 4)), 256, 0, pool[k], sp->ctr, (unsigned*)m->w->scratch); CHECK_LAUNCH();
-        LAUNCH(K_MCC, k_mcc_clamp, 1, 1, 0, pool[k], sp->ctr); CHECK_LAUNCH();
+        rc = ensure_scratch(m->w, compact_scratch_bytes(MCC_ORPHANS)); if (rc) return rc;
+        LAUNCH(K_MCC_APPEND, k_mcc_orphans, 1, 256, 0, m->orphans + k * (MCC_ORPHANS + 1), sp->ctr, (unsigned*)m->w->scratch); CHECK_LAUNCH();
         const bool fresh = sp->movers_fresh, saved = sp->movers_saved;
-        rc = compact_dead(sp, region); if (rc) return rc;
+        rc = compact_dead(sp, MCC_ORPHANS); if (rc) return rc;
         sp->movers_fresh = fresh; sp->movers_saved = saved;      // only slots appended by this call moved: the mover list of the partition stays valid
     }
-    u64 host_stats[8];
-    CUDA_TRY(cudaMemcpyAsync(host_stats, m->stats, 64, cudaMemcpyDeviceToHost, g_stream));
-    for (picg_species_s* s : {neu, ele, ion}) { s->n_host_valid = false; s->n_upper = s->cap; }
     rc = species_refresh_count(neu); if (rc) return rc;
     rc = species_refresh_count(ele); if (rc) return rc;
     rc = species_refresh_count(ion); if (rc) return rc;

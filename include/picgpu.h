@@ -221,7 +221,7 @@ PICG_API int picg_mcc_destroy(picg_mcc_t m);
 typedef struct { uint64_t candidates, collisions, ionizations; double w_sigma_v_max;
                  uint64_t dropped; /* collisions skipped (untouched) because a product store was full; 0 in a healthy run */
                  uint64_t extras_capped; /* split-off neutrals beyond 16 per cell and call: created, but not selectable by later candidates of the same call (Interactions.cpp:699-701 has no bound) */
-                 uint64_t nan_products;  /* fixed-weight variant: ejected electrons with a NaN velocity (ionisation below the threshold in ch4/v2) that were not appended */
+                 uint64_t nan_products;  /* fixed-weight variant: ejected electrons created with a NaN velocity (ionisation below the threshold; ch4/v2 appends them, they die at the next push between the electrodes) */
                } picg_mcc_stats;
 /* Interaction::apply(dt) -> MC_MEX_Ionization::apply_vector_indexes  Interactions.cpp:567-762 */
 PICG_API int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* stats /*may be NULL*/);

@@ -40,3 +40,13 @@ def ref():
     ref_v3.lib()
     ref_v3.config(subcycling=False, multithreading=False, merging=False, sputtering=False)
     return ref_v3
+
+
+@pytest.fixture(scope="session")
+def ref2():
+    """The compiled ch4/v2 reference (BASELINE config 3: fixed-weight MC_MEX_Ionization)."""
+    from oracle import ref_ch4v2
+    if not ref_ch4v2.available():
+        pytest.skip("oracle/_ref/libref_ch4v2.so not built (reference tree absent)")
+    ref_ch4v2.lib()
+    return ref_ch4v2

@@ -126,3 +126,100 @@ class MccModel:
                         if len(extra) < 16:                            # MCC_EXTRA: split-offs of this call that remain selectable
                             extra.append(q); np_n += 1
         return max(n_groups, 0), n_coll, ions, new_ele, split, step_max
+
+
+def _sqrt(x):
+    return math.sqrt(x) if x >= 0 else float("nan")
+
+
+def _pow(b, e):
+    try:
+        return math.pow(b, e)
+    except ValueError:                                                 # negative base, non-integer exponent: std::pow returns NaN
+        return float("nan")
+
+
+class MccModelV2(MccModel):
+    """The fixed-weight ancestor: MC_MEX_Ionization of ch4/v2 (ch4/v2/Interactions.cpp:476-735).  Differences from v3: Bird's NTC
+    candidate count with neutrals.mpw0 (:591), unweighted acceptance (:608-615), evaluateSigmaIon without the threshold guard
+    (:560-563), collide without the `E_inc < E_ion` early-out (:678-735: the ejected electron of a sub-threshold ionisation gets a
+    NaN velocity), products through Species::addParticle (:624-628), neutrals never depleted (:631)."""
+
+    def __init__(self, m_n, m_e, E_ion_J, tab_E, tab_s, dv, mpw0_n, mpw0_i, mpw0_e):
+        super().__init__(m_n, m_e, E_ion_J, tab_E, tab_s, dv, mpw0_n, mpw0_e)
+        self.w_max0 = 1e-14                                            # ch4/v2/Interactions.h:129
+        self.mpw0_n, self.mpw0_i, self.mpw0_e = mpw0_n, mpw0_i, mpw0_e
+        self.ions_to_create = int(mpw0_e / mpw0_i + 0.5)               # :623
+
+    def sigma_ion(self, E):                                            # :560-563, no guard
+        return self.c0 * math.log(E / self.c1) / E * math.exp(-self.c2 / E) if E > 0 else float("nan")
+
+    def new_velocity_electron(self, r, E, u):                          # :643-662
+        cos_ksi = (2 + E - 2 * _pow(1 + E, next(r))) / E
+        sin_ksi = _sqrt(1 - cos_ksi * cos_ksi)
+        phi = 2 * PI * next(r)
+        v_mag = _sqrt(E * self.two_qe_me)
+        ixu = [0.0 * u[2] - 0.0 * u[1], 0.0 * u[0] - 1.0 * u[2], 1.0 * u[1] - 0.0 * u[0]]
+        uxi = [u[1] * ixu[2] - u[2] * ixu[1], u[2] * ixu[0] - u[0] * ixu[2], u[0] * ixu[1] - u[1] * ixu[0]]
+        sp, cp = math.sin(phi), math.cos(phi)
+        return [(cos_ksi * u[c] + ixu[c] * sin_ksi * sp + uxi[c] * sin_ksi * cp) * v_mag for c in range(3)]
+
+    def collide(self, r, vn, ve, s_coll):                              # :678-735 (IONIZE_1)
+        g = [vn[c] - ve[c] for c in range(3)]
+        g_mag = math.sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2])
+        m_r = self.m_n * self.m_e / self.sum_mass
+        E_rel_J = 0.5 * m_r * g_mag * g_mag
+        p_ion = self.sigma_ion(E_rel_J / QE) / s_coll
+        if next(r) <= p_ion:
+            ve_mag = math.sqrt(ve[0] * ve[0] + ve[1] * ve[1] + ve[2] * ve[2])
+            E_inc = ve_mag * ve_mag * self.E_ele_eV
+            E_ej = 10.0 * math.tan(next(r) * math.atan((E_inc - self.E_ion_eV) / (2 * self.B_inc)))
+            E_sc = E_inc - self.E_ion_eV - E_ej
+            if E_sc < 0:
+                E_sc = 0.000001
+            inv = 1.0 / ve_mag
+            u = [ve[0] * inv, ve[1] * inv, ve[2] * inv]
+            return True, self.new_velocity_electron(r, E_sc, u), self.new_velocity_electron(r, E_ej, u)
+        inv_sum = 1.0 / self.sum_mass
+        cm = [(self.m_n * vn[c] + self.m_e * ve[c]) * inv_sum for c in range(3)]
+        cos_ksi = 2 * next(r) - 1
+        sin_ksi = math.sqrt(1 - cos_ksi * cos_ksi)
+        eps = 2 * PI * next(r)
+        g = [g_mag * cos_ksi, g_mag * sin_ksi * math.cos(eps), g_mag * sin_ksi * math.sin(eps)]
+        f = self.m_n / self.sum_mass
+        return False, [cm[c] - f * g[c] for c in range(3)], [0.0, 0.0, 0.0]
+
+    def apply_cell(self, r, neu, ele, dt, sv_max, add_ion, add_ele):
+        """apply :566-641 for ONE cell holding all of neu / ele.  add_ion / add_ele(pos, vel, mpw) stand for Species::addParticle of the two
+        product species (bounds / object filter + half-step rewind); they return the stored particle or None.
+        Returns (candidates, collisions, ionisations, new ions, new electrons, largest sigma*v_rel sampled)."""
+        np_n, np_e = len(neu), len(ele)
+        frac = 0.5 * np_n * np_e * self.mpw0_n * sv_max * dt * self.inv_dv     # :591
+        n_groups = int(frac + 0.5)
+        if n_groups > np_n:
+            n_groups = np_n - 1                                        # :598-600
+        ions, new_ele = [], []
+        n_coll, n_ion, step_max = 0, 0, 0.0
+        for _ in range(max(n_groups, 0)):
+            pn = neu[int(next(r) * np_n)]
+            pe = ele[int(next(r) * np_e)]
+            vn, ve = pn[3:6], pe[3:6]
+            d = [vn[c] - ve[c] for c in range(3)]
+            v_rel = math.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+            s_coll = self.sigma_coll(self.E_rel_eV * v_rel * v_rel)
+            sv = s_coll * v_rel
+            step_max = max(step_max, sv)
+            if sv / sv_max > next(r):
+                n_coll += 1
+                ionised, ve_new, v_new = self.collide(r, vn, ve, s_coll)
+                pe[3:6] = ve_new
+                if ionised:
+                    n_ion += 1
+                    for _k in range(self.ions_to_create):
+                        q = add_ion(list(pn[0:3]), list(vn), self.mpw0_i)
+                        if q is not None:
+                            ions.append(q)
+                    q = add_ele(list(pn[0:3]), list(v_new), self.mpw0_e)
+                    if q is not None:
+                        new_ele.append(q)
+        return max(n_groups, 0), n_coll, n_ion, ions, new_ele, step_max
