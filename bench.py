@@ -393,11 +393,117 @@ def run_ours(args):
             n = int(t.item())
         return n
 
+    def multi_gpu_self_check(ts):
+        """N > 1 only, outside the timed region: one more step of the multi-GPU path, then rank 0 REDOES its grid work on one GPU from the
+        same inputs and compares bit for bit:
+          * every rank's particles (x, y, z, mpw as they are after the step's push) are gathered onto rank 0 over NCCL and deposited by
+            the single-GPU path into a second World (same scale S): den_fixed and den against the reduce-scattered / all-reduced slabs
+            of the ranks, rho (World::computeChargeDensity of the single path) against the ranks' rho slabs;
+          * the potential: a replicated solve on rank 0 from the potential before the step and the single-path rho, against the slab
+            solve's phi (same iteration count), E against E; and all ranks must hold the same phi and E (checksums)."""
+        def view(ptr_bytes, typestr="<f8"):
+            ptr, nbytes = ptr_bytes
+            return torch.as_tensor(mg.CudaArray(ptr, nbytes // 8, typestr), device="cuda")
+
+        phi_live = view(w.device_ptr(pg.F_PHI)); ef_live = view(w.device_ptr(pg.F_EF)); rho_live = view(w.device_ptr(pg.F_RHO))
+        barrier()
+        phi_before = phi_live.clone()
+        step(ts)
+        barrier()
+        detail = {}
+
+        def assemble(local_full, dtype):
+            """The global array on rank 0: the owned slabs of every rank (slab mode) or rank 0's own full copy."""
+            if slab_range is None:
+                return local_full
+            a, b = slab_range
+            chunk = local_full[a:b].contiguous()
+            if rank == 0:
+                out = torch.empty(nv_total, dtype=dtype, device="cuda")
+                out[a:b] = chunk
+                for r in range(1, world):
+                    dist.recv(out[r * (nv_total // world):(r + 1) * (nv_total // world)], src=r)
+                return out
+            dist.send(chunk, dst=0)
+            return None
+
+        def mismatches(a, b):
+            return int((a.view(torch.int64) != b.view(torch.int64)).sum().item())
+
+        w2 = chk = None
+        if rank == 0:
+            w2 = pg.World(m, m, m, wl["x0"], wl["xm"]); w2.setTime(wl["dt"], 1 << 30)
+            for c, phi, sides in wl["rects"]:
+                w2.addRectangle(c, phi, sides)
+            w2.computeObjectID()
+            chk = []
+        for sp, sdef in zip(order, wl["species"]):
+            n_local = sp.getNumParticles()
+            cnt = torch.tensor([n_local], device="cuda", dtype=torch.int64)
+            allc = [torch.zeros_like(cnt) for _ in range(world)]
+            dist.all_gather(allc, cnt)
+            allc = [int(c.item()) for c in allc]
+            src_ptrs, src_cap = sp.particleArrays(0)
+            src = {k: torch.as_tensor(mg.CudaArray(src_ptrs[k], src_cap, "<f8"), device="cuda") for k in (0, 1, 2, 6)}
+            if rank == 0:
+                c = pg.Species(sdef["name"], sdef["mass"], sdef["charge"], w2, sdef["mpw0"])
+                ptrs, cap = c.particleArrays(sum(allc))
+                dst = {k: torch.as_tensor(mg.CudaArray(ptrs[k], cap, "<f8"), device="cuda") for k in range(7)}
+                for k in (3, 4, 5):
+                    dst[k][:sum(allc)].zero_()                       # velocities are not part of the deposit
+                for k in (0, 1, 2, 6):
+                    dst[k][:allc[0]].copy_(src[k][:allc[0]])
+                    off = allc[0]
+                    for r in range(1, world):
+                        dist.recv(dst[k][off:off + allc[r]], src=r); off += allc[r]
+                torch.cuda.synchronize()
+                c.adopt(sum(allc)); c.setDensityScale(sp.densityScale())
+                c.computeNumberDensity()                                # the single-GPU path: deposit of ALL particles + finalize on the full grid
+                pg.synchronize()
+                chk.append(c)
+            else:
+                for k in (0, 1, 2, 6):
+                    dist.send(src[k][:n_local].contiguous(), dst=0)
+            fixed_all = assemble(view(sp.device_ptr(pg.SF_DEN_FIXED), "<i8"), torch.int64)
+            den_all = assemble(view(sp.device_ptr(pg.SF_DEN)), torch.float64)
+            if rank == 0:
+                detail["den_fixed " + sp.name] = mismatches(fixed_all, view(c.device_ptr(pg.SF_DEN_FIXED), "<i8"))
+                detail["den " + sp.name] = mismatches(den_all, view(c.device_ptr(pg.SF_DEN)))
+                detail["particles " + sp.name] = sum(allc)
+            del fixed_all, den_all
+        rho_all = assemble(rho_live, torch.float64)
+        sums = torch.stack([phi_live.view(torch.int64).sum(), ef_live.view(torch.int64).sum()])       # wrap-around checksums of the bit patterns
+        all_sums = [torch.zeros_like(sums) for _ in range(world)]
+        dist.all_gather(all_sums, sums)
+        if rank == 0:
+            w2.computeChargeDensity(chk)
+            detail["rho"] = mismatches(rho_all, view(w2.device_ptr(pg.F_RHO)))
+            view(w2.device_ptr(pg.F_PHI)).copy_(phi_before); torch.cuda.synchronize()
+            sol2 = pg.PotentialSolver(w2, args.s_max_it, args.s_tol); sol2.setReferenceValues(0.0, 0.0, 1e20)
+            sol2.solveGS(); sol2.computeEF(); pg.synchronize()
+            detail["phi"] = mismatches(phi_live, view(w2.device_ptr(pg.F_PHI)))
+            detail["ef"] = mismatches(ef_live, view(w2.device_ptr(pg.F_EF)))
+            detail["iterations"] = [int(sol.iterations), int(sol2.iterations)]
+            detail["ranks_hold_the_same_phi_and_ef"] = all(bool((t == all_sums[0]).all().item()) for t in all_sums)
+            for o in [sol2] + chk + [w2]:
+                o.close()
+        del phi_before, rho_all
+        torch.cuda.empty_cache()
+        barrier()
+        if rank != 0:
+            return None, None
+        ok = all(detail[k] == 0 for k in detail if k.split(" ")[0] in ("den_fixed", "den", "rho", "phi", "ef")) and \
+            detail["iterations"][0] == detail["iterations"][1] and detail["ranks_hold_the_same_phi_and_ef"]
+        return ("bit_identical" if ok else "MISMATCH"), detail
+
     # ---- warm-up (the clock sampler starts here: nvidia-smi needs ~0.5 s before its first sample)
     clocks = ClockSampler(local); clocks.start()
     ts = 1
     for _ in range(args.warmup):
         step(ts); ts += 1
+    mg_parity, mg_detail = (None, None)
+    if world > 1 and not os.environ.get("PICG_SKIP_SELF_CHECK"):
+        mg_parity, mg_detail = multi_gpu_self_check(ts); ts += 1
     n_start = global_count()
     # ---- timed region: device-resident inputs, per-kernel CUDA-event timers on
     pg.timers_reset(); pg.timers_enable(True); pg.launch_count_reset()
@@ -553,6 +659,10 @@ def run_ours(args):
                           "l2_policy": "inputs larger than L2 (%.1f GB of particle arrays per GPU vs 126 MB L2)" % (sum(per_rank_counts.values()) * 56 / 1e9)},
                "poisson_ms_per_step": poisson_ms, "gpu_launches": int(launches), "device_reallocs_in_timed_region": int(reallocs_timed), "clocks": clk, "roofline": roofline, "kernels": kernels, "e2e": e2e,
                "subcycled": subcycled, "setup_s": round(setup_s, 1)}
+        if world > 1:
+            # rank 0 redid the step's grid work on ONE GPU from all ranks' particles (gathered over NCCL) and compared bit patterns
+            out["multi_gpu_parity"] = mg_parity
+            out["multi_gpu_parity_detail"] = mg_detail
         if not args.skip_cpu_baseline:
             try:
                 out["cpu_baseline"] = cpu_reference_run(args, wl, steps=2, warmup=1)

@@ -240,6 +240,26 @@ int picg_species_upload(picg_species_t s, size_t n, const double* aos7) {
     return PICG_OK;
 }
 
+// Device-resident hand-over of particles (no host staging): the caller gets the seven SoA arrays of the store, writes n particles
+// into them on the library's stream (a peer copy, a collective, its own kernel) and adopts them.  The pointers stay valid until the
+// store grows (reserve first).  Used by bench.py's multi-GPU self-check: every rank's particles gathered onto one GPU over NCCL.
+int picg_species_particle_arrays(picg_species_t s, size_t capacity, void* arrays7[7], size_t* cap_out) {
+    REQUIRE_DEVICE(); REQUIRE_ARG(s && arrays7, "picg_species_particle_arrays: null argument");
+    int rc = species_ensure_capacity(s, std::max<size_t>(capacity, 256)); if (rc) return rc;
+    for (int c = 0; c < 7; c++) arrays7[c] = s->a[c];
+    if (cap_out) *cap_out = s->cap;
+    return PICG_OK;
+}
+int picg_species_adopt(picg_species_t s, size_t n) {
+    REQUIRE_DEVICE(); REQUIRE_ARG(s && n <= s->cap, "picg_species_adopt: more particles than the store holds (picg_species_particle_arrays sizes it)");
+    SpeciesCounters z; memset(&z, 0, sizeof(z)); z.n = n;
+    *s->ctr_host = z;
+    CUDA_TRY(cudaMemcpyAsync(s->ctr, s->ctr_host, sizeof(z), cudaMemcpyHostToDevice, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    s->n_host = n; s->n_host_valid = true; s->n_upper = n; s->sorted_valid = false; s->lists_valid = false; s->movers_fresh = false; s->count_valid = false; s->part_valid = false;
+    return PICG_OK;
+}
+
 int picg_species_download(picg_species_t s, size_t capacity, double* aos7, size_t* n_out) {
     REQUIRE_DEVICE(); REQUIRE_ARG(s && n_out, "picg_species_download: null argument");
     int rc = species_refresh_count(s); if (rc) return rc;

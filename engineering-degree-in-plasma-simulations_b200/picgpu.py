@@ -241,6 +241,17 @@ class Species:
         _chk(lib().picg_species_download(self.h, C.c_size_t(n), _dp(out), C.byref(m)))
         return out[:m.value]
 
+    def particleArrays(self, capacity):
+        """Device pointers of the seven SoA arrays (x y z u v w mpw) sized for `capacity` particles, and the capacity."""
+        arr = (C.c_void_p * 7)()
+        cap = C.c_size_t(0)
+        _chk(lib().picg_species_particle_arrays(self.h, C.c_size_t(int(capacity)), arr, C.byref(cap)))
+        return [arr[c] for c in range(7)], cap.value
+
+    def adopt(self, n):
+        """The first n particles written into particleArrays() become the contents of the store."""
+        _chk(lib().picg_species_adopt(self.h, C.c_size_t(int(n))))
+
     def addParticles(self, aos7):
         a = np.ascontiguousarray(aos7, dtype=np.float64).reshape(-1, 7)
         acc = C.c_size_t(0)

@@ -175,6 +175,11 @@ typedef enum {
 } picg_species_field;
 PICG_API int picg_species_download_field(picg_species_t s, int field, void* host);
 PICG_API int picg_species_device_ptr(picg_species_t s, int field, void** dptr, size_t* bytes);
+/* Device-resident hand-over (no reference counterpart: Species::getPartRef, Species.h:104, hands out the host vector): the seven SoA
+ * arrays x y z u v w mpw of the store, sized for at least `capacity` particles; the caller fills n of them on the library's stream
+ * (picg_stream) and calls picg_species_adopt(s, n), which replaces the contents like picg_species_upload does. */
+PICG_API int picg_species_particle_arrays(picg_species_t s, size_t capacity, void* arrays7[7], size_t* capacity_out /*may be NULL*/);
+PICG_API int picg_species_adopt(picg_species_t s, size_t n);
 /* multi-GPU: after all-reducing DEN_FIXED across ranks, turn it into den (divide by 2^S and node_vol) */
 PICG_API int picg_species_finalize_density(picg_species_t s);
 PICG_API int picg_species_finalize_density_range(picg_species_t s, size_t node_begin, size_t node_end);
