@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--allreduce_density", action="store_true", help="multi-GPU: all-reduce the density accumulators (full grids everywhere) instead of a reduce-scatter onto the slabs")
     ap.add_argument("--poisson", choices=["auto", "replicated", "slab"], default="auto",
                     help="multi-GPU solve: every rank solves the whole grid, or planes split over the ranks with peer-memory halos (auto: slab when N > 1)")
+    ap.add_argument("--poisson_full_max_it", type=int, default=8000, help="iteration budget of the once-per-run solve to the reference's tolerance (main.cpp:82); 0: skip")
     ap.add_argument("--init_max_it", type=int, default=20000, help="iteration cap of the initial vacuum solve (profiling runs use a small value)")
     ap.add_argument("--subcycled_steps", type=int, default=None, help="steps of the reference's subcycled loop timed after the headline (0: skip; default 10 on one GPU, 0 on several)")
     ap.add_argument("--inject", type=int, default=1 << 20, help="e2e: electrons injected from pinned host memory per step")
@@ -226,7 +227,7 @@ def run_ours(args):
         per_rank = s["count"] // world + 1
         # no store may be re-allocated inside a timed region: the neutral store grows by the split-off neutrals of the MC collisions
         # (about 0.5 % per step of this workload), also over the steps of the subcycled loop
-        head = 1.25 + (0.6 if s["name"] == "O" and args.subcycled_steps else 0.0)
+        head = 1.25 + (0.6 if s["name"] == "O" else 0.0)
         sp.reserve(int(per_rank * head) + args.inject * (args.steps + args.warmup + 8))
         sp.loadParticleBoxThermal(wl["box_c"], wl["box_s"], s["den"], s["T"])
         sp.sort()
@@ -287,9 +288,16 @@ def run_ours(args):
         if mcc is not None:
             st = mcc.apply(wl["dt"])
             counts["mcc"] = (st.candidates, st.collisions, st.ionizations, st.dropped)
+            if counts.get("sampling"):
+                # populations the kernels of THIS step work on (the apply call has just refreshed the host-side counts: no extra
+                # synchronisation) and the part of each store the cell partition covers: the per-launch algorithmic bytes follow from these
+                counts["samples"].append({sp.name: (sp.getNumParticles(), sp.partitionSize()) for sp in order})
+                counts["mcc_samples"].append(counts["mcc"])
             if world > 1:                                   # the acceptance ceiling must be the same on every rank
                 mcc.setWsvMax(mg.common_ceiling(st.w_sigma_v_max, reduce_max))
             t0 = stamp("mcc", t0)
+        if mcc is None and counts.get("sampling"):
+            counts["samples"].append({sp.name: (sp.getNumParticles(), sp.partitionSize()) for sp in order})
         pending = []
         for sp in order:
             dt_sp = wl["dt"]
@@ -357,6 +365,7 @@ def run_ours(args):
         barrier()
         psteps = 0
         its = 0
+        step_events = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps)]
         ev0.record(stream)
         for k in range(n_steps):
             n_now = sum(sp.getNumParticles() for sp in order) if e2e else None
@@ -376,9 +385,11 @@ def run_ours(args):
                 pg._chk(pg.lib().picg_world_download(w.h, pg.F_RHO, rho_host.ctypes.data_as(pg.C.POINTER(pg.C.c_double))))
                 stamp("rho download", t0)
                 psteps += n_now
+            step_events[k].record(stream)
         ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
+        counts["step_ms"] = [round(([ev0] + step_events)[k].elapsed_time(step_events[k]), 3) for k in range(n_steps)]
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -509,7 +520,11 @@ def run_ours(args):
     pg.timers_reset(); pg.timers_enable(True); pg.launch_count_reset()
     n_before = len(clocks.rows)
     reallocs0 = pg.realloc_count()
+    counts["sampling"] = True; counts["samples"] = []; counts["mcc_samples"] = []
     ms, _, its = timed(args.steps, ts)
+    counts["sampling"] = False
+    step_ms = counts["step_ms"]
+    samples = counts["samples"]
     reallocs_timed = pg.realloc_count() - reallocs0
     clk = clocks.stop(first=n_before)
     launches = pg.launch_count()
@@ -517,8 +532,12 @@ def run_ours(args):
     kt = pg.timers_read()
     ts += args.steps
     n_end = global_count()
-    n_avg = 0.5 * (n_start + n_end)
-    value = n_avg * args.steps / (ms * 1e-3)
+    # particle-steps = sum over the timed steps of the particles each step advanced (sampled per step), all ranks
+    psteps_timed = float(sum(n for smp in counts["samples"] for (n, _part) in smp.values()))
+    if world > 1:
+        t = torch.tensor([psteps_timed], device="cuda", dtype=torch.float64); dist.all_reduce(t); psteps_timed = float(t.item())
+    n_avg = psteps_timed / args.steps
+    value = psteps_timed / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (largest accumulated device time)
     peaks = {}
@@ -529,37 +548,51 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     per_rank_counts = {sp.name: sp.getNumParticles() for sp in order}
-    part_sizes = {sp.name: sp.partitionSize() for sp in order}
     nv = m ** 3
+    # Algorithmic bytes per launch, from the populations AT each launch (sampled every step, see step()): sum over the steps of
+    # bytes-per-particle x particles of that step, divided by the number of launches.  Node kernels: the nodes THIS rank's launch
+    # touches (the owned slab when Poisson / the density finalisation run on slabs).
+    n_sum = {name: float(sum(smp[name][0] for smp in samples)) for name in per_rank_counts}                         # particle-launches per species
+    cov_sum = float(sum(min(n, part) if part else n for smp in samples for (n, part) in smp.values()))             # covered by a cell partition
+    tail_sum = float(sum(max(n - part, 0) for smp in samples for (n, part) in smp.values() if part))               # appended beyond it
+    slab_nodes = (slab_range[1] - slab_range[0]) if slab_range is not None else nv
+    sor_nodes = slab_nodes if poisson_mode.startswith("slab") else nv
     kernels = {}
     for name, (tot_ms, n_l) in kt.items():
         avg = tot_ms / n_l
         entry = {"ms_total": round(tot_ms, 4), "launches": int(n_l), "ms_avg": round(avg, 5)}
-        alg = None
-        if name == "push_electrons_deposit" or name == "push_electrons":
-            alg = ALG_BYTES_PER_PARTICLE[name] * per_rank_counts["e-"]
+        alg_total = None                                                            # algorithmic bytes of ALL launches in the timed region
+        if name in ("push_electrons_deposit", "push_electrons"):
+            alg_total = ALG_BYTES_PER_PARTICLE[name] * n_sum["e-"]
         elif name == "push_heavy":
-            alg = 96 * per_rank_counts["O+"] if "push_neutral" in kt else 96 * 0.5 * (per_rank_counts["O"] + per_rank_counts["O+"])
+            alg_total = 96 * (n_sum["O+"] if "push_neutral" in kt else n_sum["O"] + n_sum["O+"])
         elif name == "push_neutral":                                               # drift only: pos + vel read, pos written (no kick for charge 0)
-            alg = 72 * per_rank_counts["O"]
-        elif name == "count_per_cell":
-            alg = 24 * float(np.mean(list(per_rank_counts.values())))
-        elif name in ALG_BYTES_PER_NODE:
-            alg = ALG_BYTES_PER_NODE[name] * nv
-        if name == "deposit_density":
+            alg_total = 72 * n_sum["O"]
+        elif name == "deposit_density":
             # the cell-group kernel, one launch per species and step, over the part of the store the cell partition covers; the
             # particles appended since the last sort are deposited by the thread-run kernel ("deposit_tail", timed on its own)
-            covered = {k: min(per_rank_counts[k], part_sizes[k]) if part_sizes[k] else per_rank_counts[k] for k in per_rank_counts}
-            alg_step = 32 * float(sum(covered.values()))
-            entry["alg_GB_per_step"] = round(alg_step / 1e9, 4)
-            alg = alg_step * args.steps / n_l                                      # average per launch, for the common fields below
-        if name == "deposit_tail":
-            alg = 32 * float(sum(max(per_rank_counts[k] - part_sizes[k], 0) for k in per_rank_counts if part_sizes[k])) * args.steps / n_l
-        if alg:
-            entry["alg_GB_per_launch"] = round(alg / 1e9, 4)
-            entry["GBps"] = round(alg / (avg * 1e-3) / 1e9, 1)
+            alg_total = 32 * cov_sum
+        elif name == "deposit_tail":
+            alg_total = 32 * tail_sum
+        elif name == "sor_redblack":
+            alg_total = ALG_BYTES_PER_NODE[name] * sor_nodes * n_l
+        elif name in ("finalize_density", "charge_density"):
+            alg_total = ALG_BYTES_PER_NODE[name] * slab_nodes * n_l
+        elif name in ALG_BYTES_PER_NODE:
+            alg_total = ALG_BYTES_PER_NODE[name] * nv * n_l
+        if alg_total:
+            entry["alg_GB_per_launch"] = round(alg_total / n_l / 1e9, 4)
+            entry["GBps"] = round(alg_total / (tot_ms * 1e-3) / 1e9, 1)
             entry["frac_of_peak"] = round(entry["GBps"] / peak, 4)
         kernels[name] = entry
+    # the deposit stage as a whole: cell-group kernel + tail kernel, all species (north star: ">= 60 % on the push and deposit kernels")
+    if "deposit_density" in kernels:
+        t_dep = kernels["deposit_density"]["ms_total"] + kernels.get("deposit_tail", {"ms_total": 0.0})["ms_total"]
+        deposit_stage = {"alg_GB_per_step": round(32 * (cov_sum + tail_sum) / args.steps / 1e9, 3), "ms_per_step": round(t_dep / args.steps, 3),
+                         "GBps": round(32 * (cov_sum + tail_sum) / (t_dep * 1e-3) / 1e9, 1)}
+        deposit_stage["frac_of_peak"] = round(deposit_stage["GBps"] / peak, 4)
+    else:
+        deposit_stage = None
     dom = max((k for k in kernels if "GBps" in kernels[k]), key=lambda k: kernels[k]["ms_total"])
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this workload (profiles/capture.sh ->
     # profiles/ncu_traffic.py); only quoted when the run IS that workload (same mesh, particle count, one GPU)
@@ -607,6 +640,29 @@ def run_ours(args):
            "kernel_ms_per_step": kt_e2e, "device_reallocs": int(pg.realloc_count() - reallocs1),
            "what": "C-ABI step with host buffers: H2D of injected electrons (pinned), D2H of per-species counters + diagnostics and of rho every step"}
 
+    # ---- Poisson to the reference's tolerance.  The step above runs the solve warm-started with a cap of --s_max_it iterations (both arms);
+    # here the SAME solve is run once with the reference's own budget (main.cpp:82 --s_max_it 8000, tolerance main.cpp:83) from the
+    # current potential and charge density, timed on the device: iterations to tolerance (or the residual left at the cap) and its cost.
+    poisson_full = None
+    if args.poisson_full_max_it > 0:
+        full = pg.PotentialSolver(w, args.poisson_full_max_it, args.s_tol)
+        full.setReferenceValues(0.0, 0.0, 1e20)
+        if poisson_mode.startswith("slab"):
+            full.enableSlabs(rank, world, all_gather_bytes)
+        l2_start = sol.L2
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream); conv = full.solveGS(); e1.record(stream)
+        barrier()
+        ms_full = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_full], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_full = float(t.item())
+        poisson_full = {"max_it": args.poisson_full_max_it, "tol": args.s_tol, "converged": bool(conv), "iterations": int(full.iterations), "ms": round(ms_full, 3),
+                        "ms_per_iteration": round(ms_full / max(1, full.iterations), 5), "l2_before": l2_start, "l2_after": full.L2,
+                        "what": "one warm-started red-black SOR solve with the reference's iteration budget (main.cpp:82) and tolerance on the state the timed steps left; "
+                                "the L2 residual is the reference's (PotentialSolver.cpp:124-159: in V/m^2, i.e. 1/dx^2 = 1e8 times a potential error)"}
+        full.close()
+
     # ---- the reference's subcycled loop (Config::SUBCYCLING + MERGING), reported separately: steps ts = 300, 301, ... so that
     # the window starts with a Species::merge round (main.cpp:179-193: ts > 250 and ts % 50 == 0), an ion push and a neutral push; the default
     # 10 steps hold 10 electron pushes, 1 ion push, 1 neutral push and 1 merge.  (The window cannot be long: in this synthetic discharge the
@@ -650,14 +706,18 @@ def run_ours(args):
     if rank == 0:
         out = {"metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": "synthetic %d^3 mesh, %.3g macro-particles (O/O+/e- = 2:1:1), full PIC-DSMC step, Poisson live" % (m, args.particles),
+               "config": {"workload": "synthetic %d^3 mesh, %.3g macro-particles (O/O+/e- = 2:1:1), full PIC-DSMC step; Poisson: warm-started SOR (omega 1.4) capped at %d iterations per step "
+                                      "(tolerance %g is not reached within the cap, see poisson_to_tolerance)" % (m, args.particles, args.s_max_it, args.s_tol),
                           "mesh": [m, m, m], "particles_global": int(n_avg), "species": {k: int(v) for k, v in per_rank_counts.items()},
                           "steps_per_sort": 1 if mcc else args.sort_every, "mcc": mcc is not None, "moments": bool(args.moments),
                           "poisson": {"max_it": args.s_max_it, "tol": args.s_tol, "mode": poisson_mode, "probe": poisson_probe, "iterations_per_step": its / args.steps,
                                       "initial_solve_iterations": init_iters},
                           "parallelism": "particles split by index over %d GPU(s); int64 density %s; Poisson %s" % (world, density_mode if world > 1 else "on one GPU", poisson_mode.split(" ")[0]),
                           "l2_policy": "inputs larger than L2 (%.1f GB of particle arrays per GPU vs 126 MB L2)" % (sum(per_rank_counts.values()) * 56 / 1e9)},
-               "poisson_ms_per_step": poisson_ms, "gpu_launches": int(launches), "device_reallocs_in_timed_region": int(reallocs_timed), "clocks": clk, "roofline": roofline, "kernels": kernels, "e2e": e2e,
+               "poisson_ms_per_step": poisson_ms, "poisson_to_tolerance": poisson_full, "step_ms": step_ms, "deposit_stage": deposit_stage,
+               "mcc_per_step": {"candidates": [c[0] for c in counts["mcc_samples"]], "collisions": [c[1] for c in counts["mcc_samples"]]} if mcc else None,
+               "populations_per_step": [{k: v[0] for k, v in smp.items()} for smp in samples],
+               "gpu_launches": int(launches), "device_reallocs_in_timed_region": int(reallocs_timed), "clocks": clk, "roofline": roofline, "kernels": kernels, "e2e": e2e,
                "subcycled": subcycled, "setup_s": round(setup_s, 1)}
         if world > 1:
             # rank 0 redid the step's grid work on ONE GPU from all ranks' particles (gathered over NCCL) and compared bit patterns
@@ -761,7 +821,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "particle-steps/s", "value": cb["value"], "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic",
-           "config": {"workload": "synthetic %d^3 mesh, %.3g macro-particles (O/O+/e- = 2:1:1), full PIC-DSMC step, Poisson live" % (args.mesh, args.particles),
+           "config": {"workload": "synthetic %d^3 mesh, %.3g macro-particles (O/O+/e- = 2:1:1), full PIC-DSMC step; Poisson: warm-started SOR (omega 1.4) capped at %d iterations per step "
+                                  "(tolerance %g is not reached within the cap, see poisson_to_tolerance)" % (args.mesh, args.particles, args.s_max_it, args.s_tol),
                       "note": "CPU arm timed on a bounded sample of this workload, see cpu_baseline.sample"},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out))

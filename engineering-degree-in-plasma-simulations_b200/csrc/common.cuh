@@ -83,6 +83,7 @@ struct picg_species_s {
     // exact per-cell lists on top of a stale partition (sort.cu: movers)
     unsigned *home = nullptr, *in_start = nullptr, *out_start = nullptr, *mv_in = nullptr;
     size_t home_cap = 0, lists_cap = 0, mv_cap = 0, mv_stride = 0;
+    unsigned* home_alt = nullptr; size_t home_alt_cap = 0;   // second home array: target of the tail merge (sort.cu), swapped with home
     bool count_valid = false;          // macro_count holds the per-cell counts of the current particle positions (a deposit produces them for free)
     bool lists_valid = false;          // cell_start + in/out mover lists describe the current cell membership exactly
     // (slot, current cell, home cell) of the particles that left their slot's home cell: three arrays of mv_trip_cap entries

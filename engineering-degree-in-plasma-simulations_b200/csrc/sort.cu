@@ -238,8 +238,59 @@ __global__ void __launch_bounds__(256) k_cell_start_long(const unsigned* __restr
     }
 }
 
+// ---------------------------------------------------------------- merge of the appended tail into the cell partition
+// The store is [partition | tail]: slots [0, part_n) ordered by home cell (cell_start of the last sort), the particles appended
+// since then behind them in arrival order.  Sorting only the tail (T << n keys) and opening gaps in the partition puts every tail
+// particle at the end of its current cell's range: slot p of the partition moves to p + tstart[home[p]], the r-th tail particle
+// in cell order (cell c) to cell_start[c+1] + r, with tstart[c] = tail particles in cells below c.  Sources and destinations
+// are two monotone streams, so the pass runs at copy speed - unlike the gather of a full re-sort - and needs no keys of the
+// partition at all.  Home cells of the partition slots do not change (drifted particles stay movers).
+__global__ void __launch_bounds__(256) k_tail_keys(Grid g, const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pz,
+                                                   const u64* __restrict__ n_ptr, const unsigned* __restrict__ part_n_ptr, u64* __restrict__ t_count,
+                                                   unsigned* __restrict__ keys, unsigned* __restrict__ idx) {
+    const u64 n = *n_ptr, first = *part_n_ptr;
+    const u64 T = n > first ? n - first : 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *t_count = T;
+    for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < T; r += (u64)gridDim.x * blockDim.x) {
+        const u64 p = first + r;
+        int i = min(max((int)x_to_l(px[p], g.x0[0], g.inv_dx[0]), 0), g.ci - 1);
+        int j = min(max((int)x_to_l(py[p], g.x0[1], g.inv_dx[1]), 0), g.cj - 1);
+        int k = min(max((int)x_to_l(pz[p], g.x0[2], g.inv_dx[2]), 0), g.ck - 1);
+        keys[r] = (unsigned)cell_of(g, i, j, k);
+        idx[r] = (unsigned)p;
+    }
+}
+template <typename V>
+__global__ void __launch_bounds__(256) k_merge_permute(const unsigned* __restrict__ part_n_ptr, const u64* __restrict__ t_count, const unsigned* __restrict__ home,
+                                                       const unsigned* __restrict__ cs, const unsigned* __restrict__ tstart, const unsigned* __restrict__ tkeys,
+                                                       const unsigned* __restrict__ tidx, const V* __restrict__ in, V* __restrict__ out, int tail_is_key) {
+    const u64 P = *part_n_ptr, T = *t_count;
+    for (u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x; p < P + T; p += (u64)gridDim.x * blockDim.x) {
+        if (p < P) out[p + tstart[home[p]]] = in[p];
+        else {
+            const u64 r = p - P;
+            const unsigned c = tkeys[r];
+            out[(u64)cs[c + 1] + r] = tail_is_key ? (V)c : in[tidx[r]];                // home of a merged tail particle: its current cell
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_merge_cell_start(int nc, unsigned* __restrict__ cs, const unsigned* __restrict__ tstart) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= nc; c += gridDim.x * blockDim.x) cs[c] += tstart[c];
+}
+// the deposit pass listed the partition's movers by slot: the slots moved with the merge
+__global__ void __launch_bounds__(256) k_merge_remap_movers(SpeciesCounters* ctr, int nc, const unsigned* __restrict__ tstart, unsigned* __restrict__ m_slot,
+                                                            const unsigned* __restrict__ m_home, u64 n_new) {
+    const u64 nm = ctr->n_movers;
+    for (u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x; t < nm; t += (u64)gridDim.x * blockDim.x) {
+        const unsigned h = m_home[t];
+        if (h < (unsigned)nc) m_slot[t] += tstart[h];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->n_listed = n_new;                       // merged tail particles sit in their current cell: none is a mover
+}
+
 namespace picg {
-double g_mover_fraction = 0.10;     // above this fraction of movers the store is re-sorted instead of patched
+double g_mover_fraction = 0.10;
+double g_merge_fraction = 0.05;      // a tail above this fraction of the store is merged into the partition (merge_tail)     // above this fraction of movers the store is re-sorted instead of patched
 static uint64_t g_movers_from_deposit = 0, g_mover_scans = 0, g_mover_resorts = 0;
 static bool trace_sort() { static const bool t = getenv("PICG_TRACE_SORT") && atoi(getenv("PICG_TRACE_SORT")) != 0; return t; }
 // Stable LSD radix sort of (keys, vals) pairs; n is read on the device.  Returns the buffers that hold the result.
@@ -302,6 +353,44 @@ int sort_species(picg_species_s* s) {
     return PICG_OK;
 }
 
+// Merges the appended tail [part_n, n) of s into its cell partition (see the kernels above).  n_host must be exact.
+static uint64_t g_tail_merges = 0;
+int merge_tail(picg_species_s* s) {
+    const Grid& g = s->w->g;
+    const size_t n = s->n_host;
+    if (!s->part_valid || n <= s->part_n) return PICG_OK;
+    const size_t T = n - s->part_n;
+    if (trace_sort()) fprintf(stderr, "[picgpu] merge of the tail of species %u: n = %zu, partition %zu, tail %zu\n", s->id, n, s->part_n, T);
+    int nblocks = std::max(1, std::min(std::min(div_up(T, SORT_TILE), g_sm_count * 4), 1024));
+    const size_t Ta = (T + 63) & ~(size_t)63, nca = ((size_t)g.nc + 1 + 63) & ~(size_t)63;
+    size_t bytes = Ta * 16 + nca * 4 + (size_t)256 * nblocks * 4 + 256 * 4 + 256 + 64;
+    int rc = ensure_scratch(s->w, bytes); if (rc) return rc;
+    rc = ensure_u32(s->home_alt, s->home_alt_cap, s->cap); if (rc) return rc;
+    unsigned* keysA = (unsigned*)s->w->scratch; unsigned* keysB = keysA + Ta; unsigned* idxA = keysB + Ta; unsigned* idxB = idxA + Ta;
+    unsigned* tstart = idxB + Ta; unsigned* counts = tstart + nca;
+    u64* t_count = (u64*)(counts + (size_t)256 * nblocks + 256 + 32);
+    const u64* n_ptr = &s->ctr->n; const unsigned* part_n_ptr = s->cell_start + g.nc;
+    int tgrid = std::max(1, std::min(div_up(T, 256), g_sm_count * 8));
+    LAUNCH(K_SORT_KEYS, k_tail_keys, tgrid, 256, 0, g, s->a[0], s->a[1], s->a[2], n_ptr, part_n_ptr, t_count, keysA, idxA); CHECK_LAUNCH();
+    rc = radix_sort_pairs(t_count, T, key_bits_of(g), keysA, idxA, keysB, idxB, counts, nblocks); if (rc) return rc;
+    LAUNCH(K_CELL_START, k_cell_start, tgrid, 256, 0, t_count, keysA, g.nc, tstart); CHECK_LAUNCH();
+    int pgrid = std::max(1, std::min(div_up(n, 256), g_sm_count * 8));
+    for (int c = 0; c < 7; c++) {
+        LAUNCH(K_SORT_PERMUTE, (k_merge_permute<double>), pgrid, 256, 0, part_n_ptr, t_count, s->home, s->cell_start, tstart, keysA, idxA, s->a[c], s->spare, 0); CHECK_LAUNCH();
+        std::swap(s->a[c], s->spare);
+    }
+    LAUNCH(K_SORT_PERMUTE, (k_merge_permute<unsigned>), pgrid, 256, 0, part_n_ptr, t_count, s->home, s->cell_start, tstart, keysA, idxA, s->home, s->home_alt, 1); CHECK_LAUNCH();
+    if (s->movers_fresh) {
+        unsigned* m_slot = s->mv_trip; unsigned* m_home = m_slot + 2 * s->mv_trip_cap;
+        LAUNCH(K_SORT_KEYS, k_merge_remap_movers, g_sm_count * 2, 256, 0, s->ctr, g.nc, tstart, m_slot, m_home, (u64)n); CHECK_LAUNCH();
+    }
+    std::swap(s->home, s->home_alt); std::swap(s->home_cap, s->home_alt_cap);
+    LAUNCH(K_CELL_START, k_merge_cell_start, std::max(1, std::min(div_up((size_t)g.nc + 1, 256), g_sm_count * 8)), 256, 0, g.nc, s->cell_start, tstart); CHECK_LAUNCH();
+    s->part_n = n; s->sorted_valid = false; s->lists_valid = false; s->count_valid = false;
+    g_tail_merges++;
+    return PICG_OK;
+}
+
 // Makes the per-cell lists of s exact for its current particle positions: nothing to do if the store is exactly sorted,
 // a mover pass over a stale partition when few particles changed cell, a full sort otherwise.
 // The species-owned (slot, cell, home) arrays sized by the store capacity (no regrowth while the population grows).
@@ -322,6 +411,10 @@ int species_exact_lists(picg_species_s* s) {
     const double max_frac = g_mover_fraction;
     if (!s->part_valid || n < 4096 || max_frac <= 0) return sort_species(s);
     const Grid& g = s->w->g;
+    // a long tail of appended particles (MC products) is merged into the partition: a streaming pass, no keys of the partition needed
+    if (g_merge_fraction > 0 && n > s->part_n && (double)(n - s->part_n) > g_merge_fraction * (double)n) {
+        rc = merge_tail(s); if (rc) return rc;
+    }
     size_t mcap = (size_t)(max_frac * (double)n) + 1024;
     size_t mcap_alloc = (size_t)(max_frac * (double)s->cap) + 1024;      // sized by the store capacity: no regrowth while the population grows
     // mover triples (slot / current cell / home cell) live in the species (a deposit pass may have listed them already);
@@ -390,6 +483,8 @@ int species_exact_lists(picg_species_s* s) {
 
 extern "C" {
 int picg_set_mover_fraction(double f) { REQUIRE_ARG(f >= 0 && f <= 0.5, "picg_set_mover_fraction: 0 <= f <= 0.5"); g_mover_fraction = f; return PICG_OK; }
+int picg_set_merge_fraction(double f) { REQUIRE_ARG(f >= 0 && f <= 0.5, "picg_set_merge_fraction: 0 <= f <= 0.5 (0: never merge)"); g_merge_fraction = f; return PICG_OK; }
+int picg_tail_merge_count(uint64_t* merges) { if (merges) *merges = g_tail_merges; return PICG_OK; }
 int picg_mover_stats(uint64_t* from_deposit, uint64_t* full_scans, uint64_t* resorts) {
     if (from_deposit) *from_deposit = g_movers_from_deposit;
     if (full_scans) *full_scans = g_mover_scans;

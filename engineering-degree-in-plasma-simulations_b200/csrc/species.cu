@@ -194,7 +194,7 @@ int picg_species_destroy(picg_species_t s) {
     if (!s) return PICG_OK;
     if (g_stream) cudaStreamSynchronize(g_stream);
     for (int c = 0; c < 7; c++) cudaFree(s->a[c]);
-    cudaFree(s->spare); cudaFree(s->home); cudaFree(s->in_start); cudaFree(s->out_start); cudaFree(s->mv_in); cudaFree(s->mv_trip);
+    cudaFree(s->spare); cudaFree(s->home); cudaFree(s->home_alt); cudaFree(s->in_start); cudaFree(s->out_start); cudaFree(s->mv_in); cudaFree(s->mv_trip);
     cudaFree(s->den_fixed); cudaFree(s->den); cudaFree(s->den_avg); cudaFree(s->T); cudaFree(s->vel); cudaFree(s->n_sum);
     cudaFree(s->nv_sum); cudaFree(s->nuu); cudaFree(s->nvv); cudaFree(s->nww); cudaFree(s->macro_count); cudaFree(s->cell_start);
     cudaFree(s->ctr); if (s->ctr_host) cudaFreeHost(s->ctr_host);

@@ -76,6 +76,16 @@ def set_mover_fraction(f):
     _chk(lib().picg_set_mover_fraction(C.c_double(f)))
 
 
+def set_merge_fraction(f):
+    _chk(lib().picg_set_merge_fraction(C.c_double(f)))
+
+
+def tail_merge_count():
+    n = C.c_uint64(0)
+    _chk(lib().picg_tail_merge_count(C.byref(n)))
+    return n.value
+
+
 def mover_stats():
     """(lists re-used from a deposit pass, full mover scans, fall-backs to a full sort) since start."""
     a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -155,6 +155,11 @@ PICG_API int picg_species_count_per_cell(picg_species_t s);
  * changed cell ("movers"); when more than `f` of a species moved, it is re-sorted (periodic radix sort).  f = 0 forces a
  * full sort whenever the order is stale (the reference re-sorts every step). */
 PICG_API int picg_set_mover_fraction(double f);
+/* Particles appended since the last sort (MC products, sources, re-emitted neutrals) form a tail behind the cell partition.  When the
+ * tail exceeds the fraction `f` of the store (default 0.05) it is merged into the partition: only the tail is sorted, the partition is
+ * shifted to open the gaps (a streaming pass; replaces the full re-sort the reference does every step, Species.cpp:905-929).  0: never. */
+PICG_API int picg_set_merge_fraction(double f);
+PICG_API int picg_tail_merge_count(uint64_t* merges);
 /* How the mover lists were obtained since start: passes that re-used the list a deposit pass produced on the fly (only the
  * appended tail is scanned), full scans of the store, and fall-backs to a full radix sort. */
 PICG_API int picg_mover_stats(uint64_t* from_deposit, uint64_t* full_scans, uint64_t* resorts);

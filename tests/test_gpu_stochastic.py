@@ -165,6 +165,52 @@ def test_mover_lists_from_the_deposit_pass(picgpu):
         o.close()
 
 
+def test_tail_merge_keeps_particles_lists_and_deposit_exact(picgpu, orc):
+    """Appended particles form a tail behind the cell partition; above the merge fraction the tail is merged into the partition
+    (sort.cu: merge_tail) instead of re-sorting the store.  After each merge: the same multiset of particles, a partition that covers
+    the whole store, exact per-cell lists (with drifted movers, deaths and a deposit-produced mover list in play) and a bit-exact deposit."""
+    pg = picgpu
+    ni, nj, nk = 9, 9, 13
+    x0, xm, rects = util.discharge_geometry(ni, nj, nk)
+    E, sg = util.momentum_transfer_table()
+    g = util.build_grid(orc, ni, nj, nk, x0, xm, rects)
+    neu0 = util.random_particles(40000, x0, xm, seed=171, vth=600.0, mpw=(5e11, 5e11), lo_frac=(0, 0, 0.15), hi_frac=(1, 1, 0.85))
+    ele0 = util.random_particles(30000, x0, xm, seed=172, vth=2.5e6, mpw=(100.0, 100.0), lo_frac=(0, 0, 0.15), hi_frac=(1, 1, 0.85))
+    pg.set_mover_fraction(0.4); pg.set_merge_fraction(0.03); pg.seed(6)
+    w = util.build_world(pg.World, ni, nj, nk, x0, xm, rects, dt=1e-10)
+    w.upload(pg.F_EF, util.smooth_ef((ni, nj, nk), x0, xm, seed=3, amp=2e6))
+    sn = pg.Species("O", 16 * util.AMU, 0.0, w, 5e11, 1313.9 * 1000 / util.NA); si = pg.Species("O+", 16 * util.AMU, util.QE, w, 100.0); se = pg.Species("e-", util.ME, -util.QE, w, 100.0)
+    sn.setParticles(neu0); se.setParticles(ele0)
+    sn.sort(); se.sort()
+    m = pg.MC_MEX_Ionization(sn, si, se, w, E, sg)
+    m.setWsvMax(5e11 * 8e-20 * 8e6)
+    m.listCounts(1, w)                                    # lists in use: deposit passes list the movers from now on
+    merges0 = pg.tail_merge_count()
+    for it in range(4):
+        se.advanceElectrons(2e-12)                        # some electrons change cell, some are absorbed (holes filled from the end of the store)
+        se.computeNumberDensity()                         # cell-group deposit over the partition: lists the movers on the fly
+        add = util.random_particles(2500 + 500 * it, x0, xm, seed=190 + it, vth=2.5e6, mpw=(100.0, 100.0), lo_frac=(0, 0, 0.2), hi_frac=(1, 1, 0.8))
+        se.addParticles(add)                              # > 3 % of the store appended behind the partition
+        before = util.sort_rows(se.getParticles())
+        assert se.partitionSize() < se.getNumParticles()
+        se.computeMacroParticlesCount()
+        assert np.array_equal(m.listCounts(1, w), se.macro_part_count)       # builds the lists: merges the tail first
+        assert pg.tail_merge_count() >= merges0 + it + 1                      # (the collision call below may also merge the split-off neutrals)
+        assert se.partitionSize() == se.getNumParticles()
+        after = se.getParticles()
+        assert np.array_equal(util.sort_rows(after), before)                  # nothing lost, nothing duplicated, nothing altered
+        se.computeNumberDensity()                                             # cell-group deposit over the merged partition
+        assert np.array_equal(se.den_fixed, g.deposit_fixed(after, se.densityScale()))
+        se.computeMacroParticlesCount()
+        assert np.array_equal(se.macro_part_count.ravel(), g.count_per_cell(after).ravel())
+        assert np.array_equal(m.listCounts(1, w), se.macro_part_count)
+        st = m.apply(1e-10)                               # the collision kernel on the merged partition
+        assert st.collisions > 0
+    pg.set_mover_fraction(0.10); pg.set_merge_fraction(0.05)
+    for o in (m, sn, si, se, w):
+        o.close()
+
+
 def test_cross_sections_match_reference(picgpu, ref):
     x0, xm, rects = util.discharge_geometry(7, 7, 9)
     E, s = util.momentum_transfer_table()
