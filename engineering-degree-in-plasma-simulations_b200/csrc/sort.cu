@@ -238,6 +238,101 @@ __global__ void __launch_bounds__(256) k_cell_start_long(const unsigned* __restr
     }
 }
 
+// ---------------------------------------------------------------- counting sort by cell (short lists: movers, appended tails)
+// The lists that patch the stale partition hold a few entries per cell.  Their keys are cells, and a table of one counter per cell
+// (66 MB at 256^3) lives in the L2: count the keys with atomics, scan the table, hand out positions with a second round of atomics,
+// then order each cell's (tiny) segment by value so that the result does not depend on the order of the atomics.  Keys >= nc are
+// dropped.  The scanned table IS the per-cell offset table the list users need (nc + 1 entries, last = total).
+#define SCAN_T 1024
+#define SCAN_I 4
+__global__ void __launch_bounds__(256) k_count_keys(const u64* __restrict__ n_ptr, const unsigned* __restrict__ keys, unsigned nc, unsigned* __restrict__ cnt) {
+    const u64 n = *n_ptr;
+    for (u64 e = blockIdx.x * (u64)blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) { const unsigned k = keys[e]; if (k < nc) atomicAdd(&cnt[k], 1u); }
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_reduce(const unsigned* __restrict__ in, size_t n, unsigned* __restrict__ sums) {
+    __shared__ unsigned ws[32];
+    const size_t base = ((size_t)blockIdx.x * SCAN_T + threadIdx.x) * SCAN_I;
+    unsigned v = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_I; q++) if (base + q < n) v += in[base + q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned t = ws[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) sums[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(unsigned* __restrict__ sums, int nb) {      // exclusive scan in place, one block
+    __shared__ unsigned ws[32]; __shared__ unsigned carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned v = i < nb ? sums[i] : 0;
+        unsigned x = v;
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) ws[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned wv = ws[lane], wx = wv;
+            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, wx, o); if (lane >= o) wx += y; }
+            ws[lane] = wx - wv;
+        }
+        __syncthreads();
+        const unsigned excl = carry + ws[warp] + x - v;
+        if (i < nb) sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_apply(unsigned* __restrict__ data, size_t n, const unsigned* __restrict__ sums, unsigned* __restrict__ copy) {
+    __shared__ unsigned ws[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t base = ((size_t)blockIdx.x * SCAN_T + threadIdx.x) * SCAN_I;
+    unsigned v[SCAN_I], tot = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_I; q++) { v[q] = base + q < n ? data[base + q] : 0; tot += v[q]; }
+    unsigned x = tot;
+    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) ws[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned wv = ws[lane], wx = wv;
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, wx, o); if (lane >= o) wx += y; }
+        ws[lane] = wx - wv;
+    }
+    __syncthreads();
+    unsigned run = sums[blockIdx.x] + ws[warp] + x - tot;
+#pragma unroll
+    for (int q = 0; q < SCAN_I; q++) { if (base + q < n) { data[base + q] = run; if (copy) copy[base + q] = run; } run += v[q]; }
+}
+__global__ void __launch_bounds__(256) k_fill_by_key(const u64* __restrict__ n_ptr, const unsigned* __restrict__ keys, const unsigned* __restrict__ vals, unsigned nc,
+                                                     unsigned* __restrict__ cursor, unsigned* __restrict__ out_vals, unsigned* __restrict__ out_keys) {
+    const u64 n = *n_ptr;
+    for (u64 e = blockIdx.x * (u64)blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) {
+        const unsigned k = keys[e];
+        if (k >= nc) continue;
+        const unsigned pos = atomicAdd(&cursor[k], 1u);
+        out_vals[pos] = vals[e];
+        if (out_keys) out_keys[pos] = k;
+    }
+}
+// each cell's segment in ascending order of its values (slots): the order no longer depends on the atomics above
+__global__ void __launch_bounds__(256) k_sort_segments(unsigned nc, const unsigned* __restrict__ start, unsigned* __restrict__ vals) {
+    for (unsigned c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+        const unsigned a = start[c], b = start[c + 1];
+        for (unsigned i = a + 1; i < b; i++) {
+            const unsigned v = vals[i]; unsigned j = i;
+            while (j > a && vals[j - 1] > v) { vals[j] = vals[j - 1]; j--; }
+            vals[j] = v;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- merge of the appended tail into the cell partition
 // The store is [partition | tail]: slots [0, part_n) ordered by home cell (cell_start of the last sort), the particles appended
 // since then behind them in arrival order.  Sorting only the tail (T << n keys) and opening gaps in the partition puts every tail
@@ -260,19 +355,22 @@ __global__ void __launch_bounds__(256) k_tail_keys(Grid g, const double* __restr
         idx[r] = (unsigned)p;
     }
 }
-template <typename V>
-__global__ void __launch_bounds__(256) k_merge_permute(const unsigned* __restrict__ part_n_ptr, const u64* __restrict__ t_count, const unsigned* __restrict__ home,
+// source slot of every slot of the merged store (one scattered 4-byte pass; the seven particle arrays and the home array then
+// follow with aligned, coalesced writes through k_sort_permute / k_gather_u32: scattered 8-byte writes with a gap per cell ran at half speed)
+__global__ void __launch_bounds__(256) k_merge_sources(const unsigned* __restrict__ part_n_ptr, const u64* __restrict__ t_count, const unsigned* __restrict__ home,
                                                        const unsigned* __restrict__ cs, const unsigned* __restrict__ tstart, const unsigned* __restrict__ tkeys,
-                                                       const unsigned* __restrict__ tidx, const V* __restrict__ in, V* __restrict__ out, int tail_is_key) {
+                                                       const unsigned* __restrict__ tidx, unsigned* __restrict__ src) {
     const u64 P = *part_n_ptr, T = *t_count;
     for (u64 p = blockIdx.x * (u64)blockDim.x + threadIdx.x; p < P + T; p += (u64)gridDim.x * blockDim.x) {
-        if (p < P) out[p + tstart[home[p]]] = in[p];
-        else {
-            const u64 r = p - P;
-            const unsigned c = tkeys[r];
-            out[(u64)cs[c + 1] + r] = tail_is_key ? (V)c : in[tidx[r]];                // home of a merged tail particle: its current cell
-        }
+        if (p < P) src[p + tstart[home[p]]] = (unsigned)p;
+        else { const u64 r = p - P; src[(u64)cs[tkeys[r] + 1] + r] = tidx[r]; }
     }
+}
+// home cell of the merged slots: unchanged for partition slots, the current cell for the merged tail particles
+__global__ void __launch_bounds__(256) k_merge_home(const u64* __restrict__ n_ptr, const unsigned* __restrict__ part_n_ptr, const unsigned* __restrict__ src,
+                                                    const unsigned* __restrict__ home, const unsigned* __restrict__ tail_cell /* indexed by slot - part_n */, unsigned* __restrict__ out) {
+    const u64 n = *n_ptr, P = *part_n_ptr;
+    for (u64 q = blockIdx.x * (u64)blockDim.x + threadIdx.x; q < n; q += (u64)gridDim.x * blockDim.x) { const unsigned sidx = src[q]; out[q] = sidx < P ? home[sidx] : tail_cell[sidx - P]; }
 }
 __global__ void __launch_bounds__(256) k_merge_cell_start(int nc, unsigned* __restrict__ cs, const unsigned* __restrict__ tstart) {
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= nc; c += gridDim.x * blockDim.x) cs[c] += tstart[c];
@@ -309,6 +407,26 @@ static int radix_sort_pairs(const u64* n_ptr, size_t n_upper, int key_bits, unsi
     return PICG_OK;
 }
 static int key_bits_of(const Grid& g) { int bits = 1; while ((1ull << bits) < (u64)g.nc) bits++; return bits; }
+
+// Counting sort of (keys, vals) by key in [0, nc): start[nc + 1] (zeroed here) becomes the per-cell offset table, out_vals the values in
+// cell order (each cell's segment ascending), out_keys (optional) their keys.  work: (nc + 1) + 8192 words of scratch.
+static size_t counting_sort_words(const Grid& g) { return (((size_t)g.nc + 1 + 63) & ~(size_t)63) + 8192; }
+static int counting_sort_by_cell(const Grid& g, const u64* n_ptr, size_t n_upper, const unsigned* keys, const unsigned* vals, unsigned* start, unsigned* out_vals,
+                                 unsigned* out_keys, unsigned* work, bool ordered) {
+    const size_t nt = (size_t)g.nc + 1;
+    unsigned* cursor = work; unsigned* sums = work + ((nt + 63) & ~(size_t)63);
+    const int nb = div_up(nt, (size_t)SCAN_T * SCAN_I);
+    if (nb > 8192) return set_error(PICG_ERR_ARG, "counting_sort_by_cell: more than 2^25 cells are not supported");
+    const int egrid = std::max(1, std::min(div_up(std::max<size_t>(n_upper, 1), 256), g_sm_count * 8));
+    CUDA_TRY(cudaMemsetAsync(start, 0, nt * 4, g_stream));
+    LAUNCH(K_SORT_HIST, k_count_keys, egrid, 256, 0, n_ptr, keys, (unsigned)g.nc, start); CHECK_LAUNCH();
+    LAUNCH(K_SORT_SCAN, k_scan_reduce, nb, SCAN_T, 0, start, nt, sums); CHECK_LAUNCH();
+    LAUNCH(K_SORT_SCAN, k_scan_sums, 1, 1024, 0, sums, nb); CHECK_LAUNCH();
+    LAUNCH(K_SORT_SCAN, k_scan_apply, nb, SCAN_T, 0, start, nt, sums, cursor); CHECK_LAUNCH();
+    LAUNCH(K_SORT_SCATTER, k_fill_by_key, egrid, 256, 0, n_ptr, keys, vals, (unsigned)g.nc, cursor, out_vals, out_keys); CHECK_LAUNCH();
+    if (ordered) { LAUNCH(K_SORT_SCATTER, k_sort_segments, std::max(1, std::min(div_up((size_t)g.nc, 256), g_sm_count * 8)), 256, 0, (unsigned)g.nc, start, out_vals); CHECK_LAUNCH(); }
+    return PICG_OK;
+}
 
 static int ensure_u32(unsigned*& p, size_t& cap, size_t want) {
     if (cap >= want) return PICG_OK;
@@ -361,25 +479,27 @@ int merge_tail(picg_species_s* s) {
     if (!s->part_valid || n <= s->part_n) return PICG_OK;
     const size_t T = n - s->part_n;
     if (trace_sort()) fprintf(stderr, "[picgpu] merge of the tail of species %u: n = %zu, partition %zu, tail %zu\n", s->id, n, s->part_n, T);
-    int nblocks = std::max(1, std::min(std::min(div_up(T, SORT_TILE), g_sm_count * 4), 1024));
     const size_t Ta = (T + 63) & ~(size_t)63, nca = ((size_t)g.nc + 1 + 63) & ~(size_t)63;
-    size_t bytes = Ta * 16 + nca * 4 + (size_t)256 * nblocks * 4 + 256 * 4 + 256 + 64;
+    const size_t na = (n + 63) & ~(size_t)63;
+    size_t bytes = Ta * 16 + nca * 4 + counting_sort_words(g) * 4 + 256 + 64 + na * 4;
     int rc = ensure_scratch(s->w, bytes); if (rc) return rc;
     rc = ensure_u32(s->home_alt, s->home_alt_cap, s->cap); if (rc) return rc;
-    unsigned* keysA = (unsigned*)s->w->scratch; unsigned* keysB = keysA + Ta; unsigned* idxA = keysB + Ta; unsigned* idxB = idxA + Ta;
-    unsigned* tstart = idxB + Ta; unsigned* counts = tstart + nca;
-    u64* t_count = (u64*)(counts + (size_t)256 * nblocks + 256 + 32);
+    unsigned* keysU = (unsigned*)s->w->scratch; unsigned* idxU = keysU + Ta; unsigned* keysA = idxU + Ta; unsigned* idxA = keysA + Ta;
+    unsigned* tstart = idxA + Ta; unsigned* work = tstart + nca;
+    u64* t_count = (u64*)(work + counting_sort_words(g));
+    unsigned* src = (unsigned*)(t_count + 8);
     const u64* n_ptr = &s->ctr->n; const unsigned* part_n_ptr = s->cell_start + g.nc;
     int tgrid = std::max(1, std::min(div_up(T, 256), g_sm_count * 8));
-    LAUNCH(K_SORT_KEYS, k_tail_keys, tgrid, 256, 0, g, s->a[0], s->a[1], s->a[2], n_ptr, part_n_ptr, t_count, keysA, idxA); CHECK_LAUNCH();
-    rc = radix_sort_pairs(t_count, T, key_bits_of(g), keysA, idxA, keysB, idxB, counts, nblocks); if (rc) return rc;
-    LAUNCH(K_CELL_START, k_cell_start, tgrid, 256, 0, t_count, keysA, g.nc, tstart); CHECK_LAUNCH();
+    LAUNCH(K_SORT_KEYS, k_tail_keys, tgrid, 256, 0, g, s->a[0], s->a[1], s->a[2], n_ptr, part_n_ptr, t_count, keysU, idxU); CHECK_LAUNCH();
+    // tail in cell order: tstart[c] = tail particles in cells below c, (keysA, idxA) = cell and slot of the r-th tail particle
+    rc = counting_sort_by_cell(g, t_count, T, keysU, idxU, tstart, idxA, keysA, work, true); if (rc) return rc;
     int pgrid = std::max(1, std::min(div_up(n, 256), g_sm_count * 8));
+    LAUNCH(K_SORT_PERMUTE, k_merge_sources, pgrid, 256, 0, part_n_ptr, t_count, s->home, s->cell_start, tstart, keysA, idxA, src); CHECK_LAUNCH();
     for (int c = 0; c < 7; c++) {
-        LAUNCH(K_SORT_PERMUTE, (k_merge_permute<double>), pgrid, 256, 0, part_n_ptr, t_count, s->home, s->cell_start, tstart, keysA, idxA, s->a[c], s->spare, 0); CHECK_LAUNCH();
+        LAUNCH(K_SORT_PERMUTE, k_sort_permute, pgrid, 256, 0, s->ctr, src, s->a[c], s->spare); CHECK_LAUNCH();
         std::swap(s->a[c], s->spare);
     }
-    LAUNCH(K_SORT_PERMUTE, (k_merge_permute<unsigned>), pgrid, 256, 0, part_n_ptr, t_count, s->home, s->cell_start, tstart, keysA, idxA, s->home, s->home_alt, 1); CHECK_LAUNCH();
+    LAUNCH(K_SORT_PERMUTE, k_merge_home, pgrid, 256, 0, n_ptr, part_n_ptr, src, s->home, keysU, s->home_alt); CHECK_LAUNCH();       // keysU[slot - part_n]: cell of tail slot
     if (s->movers_fresh) {
         unsigned* m_slot = s->mv_trip; unsigned* m_home = m_slot + 2 * s->mv_trip_cap;
         LAUNCH(K_SORT_KEYS, k_merge_remap_movers, g_sm_count * 2, 256, 0, s->ctr, g.nc, tstart, m_slot, m_home, (u64)n); CHECK_LAUNCH();
@@ -420,17 +540,12 @@ int species_exact_lists(picg_species_s* s) {
     // mover triples (slot / current cell / home cell) live in the species (a deposit pass may have listed them already);
     // radix ping-pong buffers in the scratch arena
     size_t mcapa = (mcap_alloc + 63) & ~(size_t)63;
-    int nblocks = std::max(1, std::min(std::min(div_up(mcap, SORT_TILE), g_sm_count * 4), 1024));
-    const size_t queue_words = 4 + 3 * ((size_t)g.nc / 32 + 64);                 // long-gap queue of k_cell_start_sparse
-    size_t bytes = mcapa * 4 * 4 + (size_t)256 * nblocks * 4 + 256 * 4 + 256 + queue_words * 4;
-    rc = ensure_scratch(s->w, bytes); if (rc) return rc;
+    rc = ensure_scratch(s->w, counting_sort_words(g) * 4 + 256); if (rc) return rc;
     rc = ensure_u32(s->mv_in, s->mv_cap, mcapa * 2); if (rc) return rc;     // [0,mcapa): slots ordered by current cell, [mcapa, 2 mcapa): slots ordered by home cell
     s->mv_stride = mcapa;
     rc = ensure_mover_triples(s); if (rc) return rc;
     unsigned* m_slot = s->mv_trip; unsigned* m_cell = m_slot + s->mv_trip_cap; unsigned* m_home = m_cell + s->mv_trip_cap;
-    unsigned* kB = (unsigned*)s->w->scratch; unsigned* vA = kB + mcapa; unsigned* vB = vA + mcapa; unsigned* tmp = vB + mcapa;
-    unsigned* counts = tmp + mcapa;
-    unsigned* queue = counts + (size_t)256 * nblocks + 256 + 64;
+    unsigned* work = (unsigned*)s->w->scratch;
     u64* cnt = &s->ctr->n_movers;                                            // device-side mover count
     const int tail_only = s->movers_fresh ? 1 : 0;                           // the last deposit pass listed the partition's movers: only the appended tail is left
     if (!tail_only) CUDA_TRY(cudaMemsetAsync(cnt, 0, 8, g_stream));
@@ -445,36 +560,15 @@ int species_exact_lists(picg_species_s* s) {
     CUDA_TRY(cudaStreamSynchronize(g_stream));
     if (trace_sort()) fprintf(stderr, "[picgpu] lists of species %u: n = %zu, partition %zu, movers + tail = %llu (cap %zu, %s)\n", s->id, n, s->part_n, (unsigned long long)n_live_movers, mcap, tail_only ? "movers from the deposit pass" : "full scan");
     if (n_live_movers > mcap) { g_mover_resorts++; return sort_species(s); }  // too stale: periodic full radix sort
-    int mgrid = std::max(1, std::min(div_up(std::max<size_t>((size_t)n_live_movers, 1), 256), g_sm_count * 4));
-    int bits = key_bits_of(g);
-    // (1) in-lists: live movers ordered by their current cell
+    // (1) in-lists: live movers by their current cell (counting sort: the scanned table is in_start, each cell's slots ascending)
+    rc = counting_sort_by_cell(g, cnt, (size_t)n_live_movers, m_cell, m_slot, s->in_start, s->mv_in, nullptr, work, true); if (rc) return rc;
+    // (2) out-lists: every slot whose particle left its home cell (live movers with a home + slots vacated beyond n), by home cell;
+    // movers without a home (appended after the sort) carry home = nc and are dropped
     {
-        unsigned *ka = m_cell, *kb = kB, *va = vA, *vb = vB;
-        LAUNCH(K_SORT_KEYS, k_iota_u32, mgrid, 256, 0, cnt, va); CHECK_LAUNCH();
-        LAUNCH(K_SORT_KEYS, k_copy_u32, mgrid, 256, 0, cnt, m_cell, tmp); CHECK_LAUNCH();          // keep m_cell intact? (not needed later) -> sort a copy
-        ka = tmp;
-        rc = radix_sort_pairs(cnt, mcap, bits, ka, va, kb, vb, counts, std::min(nblocks, div_up(std::max<size_t>((size_t)n_live_movers, 1), SORT_TILE))); if (rc) return rc;
-        CUDA_TRY(cudaMemsetAsync(queue, 0, 4, g_stream));
-        LAUNCH(K_CELL_START, k_cell_start_sparse, mgrid, 256, 0, cnt, ka, g.nc, s->in_start, queue); CHECK_LAUNCH();
-        LAUNCH(K_CELL_START, k_cell_start_long, g_sm_count * 2, 256, 0, queue, s->in_start); CHECK_LAUNCH();
-        LAUNCH(K_SORT_PERMUTE, k_gather_u32, mgrid, 256, 0, cnt, va, m_slot, s->mv_in); CHECK_LAUNCH();
-    }
-    // (2) out-lists: every slot whose particle left its home cell (live movers with a home + slots vacated beyond n), ordered by home
-    {
-        // movers without a home (appended) carry home = nc; they sort to the end and fall outside every cell's range
         size_t vac_upper = s->part_n > n ? s->part_n - n : 0;
         if (n_live_movers + vac_upper > mcap) { g_mover_resorts++; return sort_species(s); }
         if (vac_upper) { LAUNCH(K_SORT_KEYS, k_find_vacated, std::max(1, std::min(div_up(vac_upper, 256), g_sm_count * 4)), 256, 0, s->home, &s->ctr->n, s->cell_start + g.nc, cnt, (u64)mcap, m_slot, m_home); CHECK_LAUNCH(); }
-        unsigned *ka = tmp, *kb = kB, *va = vA, *vb = vB;                                           // sort a copy: the triples of the partition's movers stay intact for the next build
-        int mgrid2 = std::max(1, std::min(div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), 256), g_sm_count * 4));
-        LAUNCH(K_SORT_KEYS, k_iota_u32, mgrid2, 256, 0, cnt, va); CHECK_LAUNCH();
-        LAUNCH(K_SORT_KEYS, k_copy_u32, mgrid2, 256, 0, cnt, m_home, tmp); CHECK_LAUNCH();
-        int hbits = 1; while ((1ull << hbits) < (u64)g.nc + 1) hbits++;
-        rc = radix_sort_pairs(cnt, mcap, hbits, ka, va, kb, vb, counts, std::min(nblocks, div_up(std::max<size_t>((size_t)n_live_movers + vac_upper, 1), SORT_TILE))); if (rc) return rc;
-        CUDA_TRY(cudaMemsetAsync(queue, 0, 4, g_stream));
-        LAUNCH(K_CELL_START, k_cell_start_sparse, mgrid2, 256, 0, cnt, ka, g.nc, s->out_start, queue); CHECK_LAUNCH();
-        LAUNCH(K_CELL_START, k_cell_start_long, g_sm_count * 2, 256, 0, queue, s->out_start); CHECK_LAUNCH();
-        LAUNCH(K_SORT_PERMUTE, k_gather_u32, mgrid2, 256, 0, cnt, va, m_slot, s->mv_in + mcapa); CHECK_LAUNCH();
+        rc = counting_sort_by_cell(g, cnt, (size_t)n_live_movers + vac_upper, m_home, m_slot, s->out_start, s->mv_in + mcapa, nullptr, work, false); if (rc) return rc;
     }
     s->lists_valid = true;
     return PICG_OK;
