@@ -26,7 +26,7 @@
 
 using namespace picg;
 
-namespace picg { int sort_species(picg_species_s* s); int species_exact_lists(picg_species_s* s); }
+namespace picg { int sort_species(picg_species_s* s); int species_exact_lists(picg_species_s* s); int species_prepare_lists(picg_species_s* s); }
 
 #define MCC_EXTRA 16          // split-off neutrals created in this call that remain selectable within the cell (:699-701)
 
@@ -350,6 +350,7 @@ int picg_mcc_create(picg_species_t neutrals, picg_species_t ions, picg_species_t
     CUDA_TRY(cudaMemcpyAsync(m->wsv, wsv, 16, cudaMemcpyHostToDevice, g_stream));
     CUDA_TRY(cudaMemsetAsync(m->stats, 0, 128, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));
+    { int rc = species_prepare_lists(neutrals); if (rc) return rc; rc = species_prepare_lists(electrons); if (rc) return rc; }
     *out = m;
     return PICG_OK;
 }

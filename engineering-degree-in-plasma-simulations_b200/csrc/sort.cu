@@ -377,8 +377,8 @@ __global__ void __launch_bounds__(256) k_merge_cell_start(int nc, unsigned* __re
 }
 // the deposit pass listed the partition's movers by slot: the slots moved with the merge
 __global__ void __launch_bounds__(256) k_merge_remap_movers(SpeciesCounters* ctr, int nc, const unsigned* __restrict__ tstart, unsigned* __restrict__ m_slot,
-                                                            const unsigned* __restrict__ m_home, u64 n_new) {
-    const u64 nm = ctr->n_movers;
+                                                            const unsigned* __restrict__ m_home, u64 n_new, u64 cap) {
+    const u64 nm = min(ctr->n_movers, cap);                                               // (a list that overflowed its buffer leads to a full sort later)
     for (u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x; t < nm; t += (u64)gridDim.x * blockDim.x) {
         const unsigned h = m_home[t];
         if (h < (unsigned)nc) m_slot[t] += tstart[h];
@@ -502,7 +502,7 @@ int merge_tail(picg_species_s* s) {
     LAUNCH(K_SORT_PERMUTE, k_merge_home, pgrid, 256, 0, n_ptr, part_n_ptr, src, s->home, keysU, s->home_alt); CHECK_LAUNCH();       // keysU[slot - part_n]: cell of tail slot
     if (s->movers_fresh) {
         unsigned* m_slot = s->mv_trip; unsigned* m_home = m_slot + 2 * s->mv_trip_cap;
-        LAUNCH(K_SORT_KEYS, k_merge_remap_movers, g_sm_count * 2, 256, 0, s->ctr, g.nc, tstart, m_slot, m_home, (u64)n); CHECK_LAUNCH();
+        LAUNCH(K_SORT_KEYS, k_merge_remap_movers, g_sm_count * 2, 256, 0, s->ctr, g.nc, tstart, m_slot, m_home, (u64)n, (u64)s->mv_trip_cap); CHECK_LAUNCH();
     }
     std::swap(s->home, s->home_alt); std::swap(s->home_cap, s->home_alt_cap);
     LAUNCH(K_CELL_START, k_merge_cell_start, std::max(1, std::min(div_up((size_t)g.nc + 1, 256), g_sm_count * 8)), 256, 0, g.nc, s->cell_start, tstart); CHECK_LAUNCH();
@@ -576,6 +576,11 @@ int species_exact_lists(picg_species_s* s) {
 }  // namespace picg
 
 extern "C" {
+} extern "C++" { namespace picg {
+// Species whose per-cell lists are in use (MC collisions): the second home array of the tail merge is allocated up front, so that no
+// allocation happens inside a time step.
+int species_prepare_lists(picg_species_s* s) { s->wants_lists = true; return ensure_u32(s->home_alt, s->home_alt_cap, s->cap); }
+} } extern "C" {
 int picg_set_mover_fraction(double f) { REQUIRE_ARG(f >= 0 && f <= 0.5, "picg_set_mover_fraction: 0 <= f <= 0.5"); g_mover_fraction = f; return PICG_OK; }
 int picg_set_merge_fraction(double f) { REQUIRE_ARG(f >= 0 && f <= 0.5, "picg_set_merge_fraction: 0 <= f <= 0.5 (0: never merge)"); g_merge_fraction = f; return PICG_OK; }
 int picg_tail_merge_count(uint64_t* merges) { if (merges) *merges = g_tail_merges; return PICG_OK; }

@@ -108,6 +108,11 @@ int species_refresh_count(picg_species_s* s) {
         cudaMemsetAsync(&s->ctr->overflow, 0, 8, g_stream);
         return set_error(PICG_ERR_OOM, "species store full: %llu appended particles were dropped (capacity %zu); call picg_species_reserve", lost, s->cap);
     }
+    if (s->S_pinned && s->ctr_host->den_neg) {        // pinned scale (multi-GPU): nobody re-calibrates, so the wrapped accumulator must not pass silently
+        u64 bad = s->ctr_host->den_neg;
+        cudaMemsetAsync(&s->ctr->den_neg, 0, 8, g_stream);
+        return set_error(PICG_ERR_OVERFLOW, "fixed-point density accumulator overflowed on %llu nodes with the pinned scale S=%d: agree on a smaller S (picg_species_set_density_scale) and deposit again", bad, s->S);
+    }
     return PICG_OK;
 }
 

@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(128) k_heavy_impacts(Grid g, StepArgs A, Heavy
     }
 }
 
+__global__ void k_clamp_count(SpeciesCounters* ctr, u64 cap);       // species.cu
 namespace picg {
 int launch_finalize(picg_species_s* s, size_t u_begin = 0, size_t u_end = (size_t)-1);
 int calibrate_scale(picg_species_s* s, bool count_cells);
@@ -281,6 +282,10 @@ int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals
         else if (mode & 8) LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<false, true>), grid, 128, 0, g, A, H);
         else LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<false, false>), grid, 128, 0, g, A, H);
         CHECK_LAUNCH();
+        if (s->charge != 0) {                         // emit_particle may have run a target store past its capacity: the counter goes back to it
+            LAUNCH(K_HEAVY_IMPACTS, k_clamp_count, 1, 1, 0, neutrals->ctr, (u64)neutrals->cap); CHECK_LAUNCH();
+            if (spherium != neutrals) { LAUNCH(K_HEAVY_IMPACTS, k_clamp_count, 1, 1, 0, spherium->ctr, (u64)spherium->cap); CHECK_LAUNCH(); }
+        }
     }
     return PICG_OK;
 }
@@ -297,7 +302,12 @@ int species_step(picg_species_s* s, bool push, bool heavy, bool deposit, bool fi
         if (s->charge != 0) {                          // room for injected neutrals / sputtered material
             for (picg_species_s* t : {neutrals, sputtering ? spherium : neutrals}) {
                 rc = species_refresh_count(t); if (rc) return rc;
-                if (t->cap < t->n_host + 1024) { rc = species_ensure_capacity(t, t->n_host + t->n_host / 8 + 4096); if (rc) return rc; }
+                // every impacting ion emits int(mpw / mpw0_target + rnd()) particles (Species.cpp:225-232); at most a few per cent of a
+                // species reach an electrode in one (possibly sub-cycled) push.  A store that still runs full is safe: the appends beyond
+                // the capacity are dropped and counted, the counter is clamped (k_clamp_count below), the next refresh reports PICG_ERR_OOM.
+                const double per_ion = std::min(64.0, s->mpw0 / t->mpw0 + 1.0);
+                const size_t room = (size_t)(per_ion * (double)n_snapshot / 16.0) + 65536;
+                if (t->cap < t->n_host + room) { rc = species_ensure_capacity(t, t->n_host + room + t->n_host / 8); if (rc) return rc; }
             }
         }
     }
