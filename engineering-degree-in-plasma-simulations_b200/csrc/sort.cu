@@ -392,8 +392,8 @@ double g_merge_fraction = 0.05;      // a tail above this fraction of the store 
 static uint64_t g_movers_from_deposit = 0, g_mover_scans = 0, g_mover_resorts = 0;
 static bool trace_sort() { static const bool t = getenv("PICG_TRACE_SORT") && atoi(getenv("PICG_TRACE_SORT")) != 0; return t; }
 // Stable LSD radix sort of (keys, vals) pairs; n is read on the device.  Returns the buffers that hold the result.
-static int radix_sort_pairs(const u64* n_ptr, size_t n_upper, int key_bits, unsigned*& keysA, unsigned*& valsA, unsigned*& keysB, unsigned*& valsB,
-                            unsigned* counts, int nblocks) {
+int radix_sort_pairs(const u64* n_ptr, size_t n_upper, int key_bits, unsigned*& keysA, unsigned*& valsA, unsigned*& keysB, unsigned*& valsB,
+                     unsigned* counts, int nblocks) {
     int passes = (key_bits + 7) / 8;
     for (int pass = 0; pass < passes; pass++) {
         int shift = pass * 8;

@@ -368,6 +368,91 @@ class Species:
         return p.value, n.value
 
 
+class Species32:
+    """A species in the fp32 secondary store (csrc/f32.cu): cell index + cell-relative coordinates, 32 bytes per particle.  Same method
+    names as Species for the part of the loop it covers; host arrays are AoS of doubles like Species."""
+
+    def __init__(self, name, mass, charge, world, mpw0):
+        self.name, self.mass, self.charge, self.mpw0, self.world = name, float(mass), float(charge), float(mpw0), world
+        self.h = C.c_void_p()
+        _chk(lib().picg_species32_create(world.h, C.c_double(mass), C.c_double(charge), C.c_double(mpw0), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().picg_species32_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def reserve(self, n):
+        _chk(lib().picg_species32_reserve(self.h, C.c_size_t(int(n))))
+
+    def getNumParticles(self):
+        n = C.c_size_t(0)
+        _chk(lib().picg_species32_count(self.h, C.byref(n)))
+        return n.value
+
+    def setParticles(self, aos7):
+        a = np.ascontiguousarray(aos7, dtype=np.float64).reshape(-1, 7)
+        _chk(lib().picg_species32_upload(self.h, C.c_size_t(a.shape[0]), _dp(a)))
+
+    def fromSpecies(self, species):
+        _chk(lib().picg_species32_from_species(self.h, species.h))
+
+    def getParticles(self):
+        n = self.getNumParticles()
+        out = np.empty((n, 7), dtype=np.float64)
+        got = C.c_size_t(0)
+        _chk(lib().picg_species32_download(self.h, C.c_size_t(n), _dp(out), C.byref(got)))
+        return out[:got.value]
+
+    def advanceElectrons(self, dt):
+        _chk(lib().picg_species32_push_electrons(self.h, C.c_double(dt)))
+
+    def computeNumberDensity(self):
+        _chk(lib().picg_species32_deposit_density(self.h))
+
+    def computeMacroParticlesCount(self):
+        pass                                              # a by-product of the deposit pass
+
+    def setDensityScale(self, S):
+        _chk(lib().picg_species32_set_density_scale(self.h, int(S)))
+
+    def densityScale(self):
+        S = C.c_int(0)
+        _chk(lib().picg_species32_density_scale(self.h, C.byref(S)))
+        return S.value
+
+    def sort(self):
+        _chk(lib().picg_species32_sort(self.h))
+
+    def diagnostics(self):
+        mc = C.c_double(0)
+        ke = C.c_double(0)
+        mom = (C.c_double * 3)()
+        _chk(lib().picg_species32_diagnostics(self.h, C.byref(mc), mom, C.byref(ke)))
+        return mc.value, np.array(list(mom)), ke.value
+
+    def download(self, field):
+        w = self.world
+        if field == SF_MACRO_COUNT:
+            out = np.empty((w.ni - 1, w.nj - 1, w.nk - 1), dtype=np.float64)
+        elif field == SF_DEN_FIXED:
+            out = np.empty((w.ni, w.nj, w.nk), dtype=np.int64)
+        else:
+            out = np.empty((w.ni, w.nj, w.nk), dtype=np.float64)
+        _chk(lib().picg_species32_download_field(self.h, int(field), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    den = property(lambda self: self.download(SF_DEN))
+    den_fixed = property(lambda self: self.download(SF_DEN_FIXED))
+    macro_part_count = property(lambda self: self.download(SF_MACRO_COUNT))
+
+
+def charge_density32(world, species32):
+    """World::computeChargeDensity over fp32 species."""
+    arr = (C.c_void_p * len(species32))(*[s.h for s in species32])
+    _chk(lib().picg_world_charge_density32(world.h, arr, len(species32)))
+
+
 class PotentialSolver:
     """PotentialSolver with SolverType GS (ch4/v3/src/PotentialSolver.h:26-92)."""
 

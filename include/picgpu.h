@@ -52,6 +52,7 @@ typedef struct picg_solver_s*  picg_solver_t;
 typedef struct picg_mcc_s*     picg_mcc_t;
 typedef struct picg_dsmc_s*    picg_dsmc_t;
 typedef struct picg_source_s*  picg_source_t;
+typedef struct picg_species32_s* picg_species32_t;   /* fp32 secondary store, see the end of this file */
 
 /* ------------------------------------------------------------------ runtime */
 PICG_API int         picg_init(int device);                 /* select device, create the stream */
@@ -287,6 +288,31 @@ typedef struct {
 } picg_checkpoint_set;
 PICG_API int picg_checkpoint_save(const char* path, const picg_checkpoint_set* set, uint64_t user_ts /* e.g. World::getTs() */);
 PICG_API int picg_checkpoint_load(const char* path, const picg_checkpoint_set* set, uint64_t* user_ts /*may be NULL*/);
+
+/* ------------------------------------------------------- fp32 secondary path (north star: "1e-4 relative for fp32", float4 loads)
+ * The reference is written against one scalar type (all.h:11 `using type_calc = double`) and rebuilds with float.  Here a species can
+ * live in a single-precision store instead: 32 bytes per particle - the cell index (u32) and the cell-relative coordinates fx, fy, fz
+ * in [0,1), velocities and weight as floats - because an absolute fp32 position cannot carry the motion of the slow species (a neutral
+ * moves 4e-10 m per step, the fp32 spacing at 2.5 cm is 1.9e-9 m).  Node fields stay fp64.  Covered: the electron-type push
+ * (Species::advanceElectrons, Species.cpp:258-399: gather, kick, drift, absorption outside the box / inside an object), number density +
+ * per-cell count (:401-416, :813-819; same int64 fixed-point grid as the fp64 path, deterministic), cell sort, diagnostics (:731-752),
+ * charge density (World.cpp:193-200).  The heavy species' wall interaction and the collision kernels are fp64 only.
+ * Host buffers are the same AoS of doubles (x y z u v w mpw) as for the fp64 store. */
+PICG_API int picg_species32_create(picg_world_t w, double mass, double charge, double mpw0, picg_species32_t* out);
+PICG_API int picg_species32_destroy(picg_species32_t s);
+PICG_API int picg_species32_reserve(picg_species32_t s, size_t capacity);
+PICG_API int picg_species32_count(picg_species32_t s, size_t* n);
+PICG_API int picg_species32_upload(picg_species32_t s, size_t n, const double* aos7);
+PICG_API int picg_species32_from_species(picg_species32_t s, picg_species_t src);      /* device-side conversion of an fp64 store of the same world */
+PICG_API int picg_species32_download(picg_species32_t s, size_t capacity, double* aos7, size_t* n_out);
+PICG_API int picg_species32_push_electrons(picg_species32_t s, double dt);
+PICG_API int picg_species32_deposit_density(picg_species32_t s);                        /* + computeMacroParticlesCount as a by-product */
+PICG_API int picg_species32_set_density_scale(picg_species32_t s, int S);
+PICG_API int picg_species32_density_scale(picg_species32_t s, int* S);
+PICG_API int picg_species32_sort(picg_species32_t s);
+PICG_API int picg_species32_diagnostics(picg_species32_t s, double* micro_count, double momentum[3], double* ke);
+PICG_API int picg_species32_download_field(picg_species32_t s, int field /* PICG_SF_DEN, _DEN_FIXED, _MACRO_COUNT */, void* host);
+PICG_API int picg_world_charge_density32(picg_world_t w, picg_species32_t* species, int n);
 
 #ifdef __cplusplus
 }
