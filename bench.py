@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--poisson_full_max_it", type=int, default=8000, help="iteration budget of the once-per-run solve to the reference's tolerance (main.cpp:82); 0: skip")
     ap.add_argument("--init_max_it", type=int, default=20000, help="iteration cap of the initial vacuum solve (profiling runs use a small value)")
     ap.add_argument("--subcycled_steps", type=int, default=None, help="steps of the reference's subcycled loop timed after the headline (0: skip; default 10 on one GPU, 0 on several)")
+    ap.add_argument("--fp32_steps", type=int, default=5, help="steps of the fp32 secondary path timed after everything else on one GPU (0: skip)")
     ap.add_argument("--inject", type=int, default=1 << 20, help="e2e: electrons injected from pinned host memory per step")
     return ap.parse_args()
 
@@ -227,7 +228,7 @@ def run_ours(args):
         per_rank = s["count"] // world + 1
         # no store may be re-allocated inside a timed region: the neutral store grows by the split-off neutrals of the MC collisions
         # (about 0.5 % per step of this workload), also over the steps of the subcycled loop
-        head = 1.25 + (0.6 if s["name"] == "O" else 0.0)
+        head = 1.25 + (0.85 if s["name"] == "O" else 0.0)     # the neutral store doubles within the run (split-off neutrals of the MC collisions)
         sp.reserve(int(per_rank * head) + args.inject * (args.steps + args.warmup + 8))
         sp.loadParticleBoxThermal(wl["box_c"], wl["box_s"], s["den"], s["T"])
         sp.sort()
@@ -702,6 +703,57 @@ def run_ours(args):
                 raise                                   # (a rank that stops here would leave the others in a collective)
             subcycled = {"error": str(e)[:300]}
 
+    # ---- fp32 secondary path (SURVEY 8d "fp64 headline, fp32 secondary"): the same plasma converted on the device to the cell-relative
+    # single-precision store (csrc/f32.cu) and advanced with the kernels that path has: electron-type push of every species (kick, drift,
+    # absorption), fixed-point deposit + per-cell count, charge density, the same capped Poisson solve and E.  No collisions, no wall
+    # re-emission (fp64 only).  One GPU; last leg of the run (the fp64 stores are released one by one as they are converted).
+    fp32 = None
+    if args.fp32_steps > 0 and world == 1:
+        try:
+            if mcc is not None:
+                mcc.close()
+            sp32 = []
+            for sp in (ele, ion, neu):                      # the small stores first: their fp64 memory is free before the large one is converted
+                c = pg.Species32(sp.name, sp.mass, sp.charge, w, sp.mpw0)
+                c.fromSpecies(sp); sp.close()
+                c.sort()
+                sp32.append(c)
+            for c in sp32:
+                c.computeNumberDensity()                    # fixes the scale S, sizes the scratch arena
+            counts32 = [c.getNumParticles() for c in sp32]
+
+            def step32():
+                for c in sp32:
+                    c.advanceElectrons(wl["dt"]); c.computeNumberDensity()
+                pg.charge_density32(w, sp32)
+                sol.solveGS(); sol.computeEF()
+            step32(); step32()
+            pg.timers_reset(); pg.timers_enable(True)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            barrier(); e0.record(stream)
+            for _ in range(args.fp32_steps):
+                step32()
+            e1.record(stream); barrier()
+            pg.timers_enable(False)
+            ms32 = e0.elapsed_time(e1)
+            k32 = pg.timers_read()
+            n32 = float(sum(c.getNumParticles() for c in sp32))
+            n32_avg = 0.5 * (n32 + float(sum(counts32)))
+            kern32 = {}
+            for name, bpp in (("push_electrons", 56), ("deposit_density", 20)):      # 28 R + 28 W; cell + 3 fractions + weight
+                if name in k32:
+                    tot_ms, n_l = k32[name]
+                    gbps = bpp * n32_avg * args.fp32_steps / (tot_ms * 1e-3) / 1e9
+                    kern32[name] = {"ms_per_step": round(tot_ms / args.fp32_steps, 3), "launches": int(n_l), "alg_bytes_per_particle": bpp, "GBps": round(gbps, 1), "frac_of_peak": round(gbps / peak, 4)}
+            fp32 = {"dtype": "f32", "steps": args.fp32_steps, "ms_per_step": ms32 / args.fp32_steps, "value": n32_avg * args.fp32_steps / (ms32 * 1e-3), "unit": "particle-steps/s",
+                    "particles": int(n32_avg), "kernels": kern32,
+                    "what": "cell-relative fp32 store (32 B per particle): push (electron-type: gather, kick, drift, absorption) + fixed-point deposit + per-cell count of every species, "
+                            "charge density, capped SOR solve and E each step; no collisions, no wall re-emission (fp64 path only)"}
+            for c in sp32:
+                c.close()
+        except Exception as e:                                  # a secondary leg never takes the headline line down
+            fp32 = {"error": str(e)[:300]}
+
     out = None
     if rank == 0:
         out = {"metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -718,7 +770,7 @@ def run_ours(args):
                "mcc_per_step": {"candidates": [c[0] for c in counts["mcc_samples"]], "collisions": [c[1] for c in counts["mcc_samples"]]} if mcc else None,
                "populations_per_step": [{k: v[0] for k, v in smp.items()} for smp in samples],
                "gpu_launches": int(launches), "device_reallocs_in_timed_region": int(reallocs_timed), "clocks": clk, "roofline": roofline, "kernels": kernels, "e2e": e2e,
-               "subcycled": subcycled, "setup_s": round(setup_s, 1)}
+               "subcycled": subcycled, "fp32": fp32, "setup_s": round(setup_s, 1)}
         if world > 1:
             # rank 0 redid the step's grid work on ONE GPU from all ranks' particles (gathered over NCCL) and compared bit patterns
             out["multi_gpu_parity"] = mg_parity

@@ -291,15 +291,19 @@ int ensure_capacity32(picg_species32_s* s, size_t cap) {
     int rc = refresh_count32(s); if (rc) return rc;
     const size_t newcap = (std::max(cap, s->cap + s->cap / 2) + 255) & ~(size_t)255;
     cudaStreamSynchronize(g_stream);
-    for (int c = 0; c < 10; c++) {
-        void** slot = c < 7 ? (void**)&s->f[c] : c == 7 ? (void**)&s->cell : c == 8 ? (void**)&s->fspare : (void**)&s->cspare;
+    cudaFree(s->fspare); cudaFree(s->cspare); s->fspare = nullptr; s->cspare = nullptr;      // the sort's out-of-place targets are allocated when a sort needs them
+    for (int c = 0; c < 8; c++) {
+        void** slot = c < 7 ? (void**)&s->f[c] : (void**)&s->cell;
         void* fresh = nullptr;
         cudaError_t e = cudaMalloc(&fresh, newcap * 4);
-        if (e != cudaSuccess) return set_error(PICG_ERR_OOM, "fp32 species store cannot grow to %zu particles: %s", newcap, cudaGetErrorString(e));
-        if (c < 8 && s->n_host && *slot) { CUDA_TRY(cudaMemcpyAsync(fresh, *slot, s->n_host * 4, cudaMemcpyDeviceToDevice, g_stream)); CUDA_TRY(cudaStreamSynchronize(g_stream)); }
+        if (e != cudaSuccess) {
+            size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
+            return set_error(PICG_ERR_OOM, "fp32 species store cannot grow to %zu particles: %s (%.1f GB free of %.1f)", newcap, cudaGetErrorString(e), fr / 1e9, tot / 1e9);
+        }
+        if (s->n_host && *slot) { CUDA_TRY(cudaMemcpyAsync(fresh, *slot, s->n_host * 4, cudaMemcpyDeviceToDevice, g_stream)); CUDA_TRY(cudaStreamSynchronize(g_stream)); }
         cudaFree(*slot); *slot = fresh;
     }
-    note_realloc("fp32 particle store", newcap * 40);
+    note_realloc("fp32 particle store", newcap * 32);
     s->cap = newcap;
     return ensure_scratch(s->w, std::max(newcap * 16 + (1u << 20), compact_scratch_bytes(newcap) + 64));
 }
@@ -450,6 +454,8 @@ int picg_species32_sort(picg_species32_t s) {
     int nblocks = std::max(1, std::min(std::min(div_up(cap, 2048), g_sm_count * 4), 1024));
     const size_t capa = (cap + 63) & ~(size_t)63;
     rc = ensure_scratch(s->w, capa * 16 + (size_t)256 * nblocks * 4 + 256 * 4 + 256); if (rc) return rc;
+    if (!s->fspare) { cudaError_t e = cudaMalloc(&s->fspare, s->cap * 4); if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(fp32 sort target)", __FILE__, __LINE__); }
+    if (!s->cspare) { cudaError_t e = cudaMalloc(&s->cspare, s->cap * 4); if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(fp32 sort target)", __FILE__, __LINE__); }
     unsigned* keysA = (unsigned*)s->w->scratch; unsigned* keysB = keysA + capa; unsigned* idxA = keysB + capa; unsigned* idxB = idxA + capa; unsigned* counts = idxB + capa;
     const u64* n_ptr = &s->ctr->n;
     const int pgrid = std::max(1, std::min(div_up(cap, 256), g_sm_count * 8));
