@@ -103,6 +103,9 @@ struct picg_solver_s {
     double* partial = nullptr;         // residual partial sums
     unsigned char* cls = nullptr;      // node class per colour-compact node (poisson.cu), rebuilt at the start of every solve
     double* rho_split = nullptr;       // rho per colour-compact node: a colour half-sweep reads its own half with unit stride
+    unsigned char* cls_nat = nullptr;  // node class in node order (the tiled one-pass sweep)
+    double* phi_alt = nullptr;         // second potential buffer of the tiled sweep (phi is double-buffered within a batch of iterations)
+    int sweep_mode = 0;                // 0: k_sor_row (two sweeps per iteration, default: faster), 1: k_sor_tiled (one pass, less DRAM traffic)
     void* pcg_work = nullptr; size_t pcg_bytes = 0;   // NR-PCG work vectors (nrpcg.cu), allocated on first use
     unsigned pcg_gs_fallbacks = 0;     // Newton steps of the last NR-PCG solve whose linear system was finished by the Gauss-Seidel fallback
     // multi-GPU slab decomposition (poisson.cu): planes [i0, i1) of the slowest index belong to this rank; halo planes,
@@ -168,7 +171,7 @@ enum KernelId {
     K_PUSH_ELECTRONS = 0, K_PUSH_DEPOSIT, K_PUSH_REFLECT, K_PUSH_HEAVY, K_COMPACT, K_DEPOSIT, K_FINALIZE_DEN,
     K_CHARGE_DENSITY, K_SOR, K_RESIDUAL, K_COMPUTE_EF, K_SORT_KEYS, K_SORT_HIST, K_SORT_SCAN, K_SORT_SCATTER,
     K_SORT_PERMUTE, K_CELL_START, K_MCC, K_SOURCE, K_ADD_PARTICLES, K_MOMENTS, K_COUNT_CELLS, K_TRANSPOSE,
-    K_DIAG, K_MISC, K_PUSH_HEAVY_DEPOSIT, K_HEAVY_IMPACTS, K_DSMC, K_PUSH_NEUTRAL, K_PCG, K_DEPOSIT_TAIL, K_MCC_APPEND, K_NUM_KERNELS
+    K_DIAG, K_MISC, K_PUSH_HEAVY_DEPOSIT, K_HEAVY_IMPACTS, K_DSMC, K_PUSH_NEUTRAL, K_PCG, K_DEPOSIT_TAIL, K_MCC_APPEND, K_SOR_TILED, K_NUM_KERNELS
 };
 
 #define CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return picg::cuda_fail(_e, #expr, __FILE__, __LINE__); } while (0)

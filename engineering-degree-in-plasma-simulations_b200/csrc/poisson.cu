@@ -41,14 +41,15 @@ __device__ __forceinline__ size_t face_neighbor(const Grid& g, int cls, size_t u
 // row*hk + (k>>1) of colour c's half (hk = ceil(nk/2)).  A half-sweep then reads the node class (1 byte: no index arithmetic or
 // geometry branches in the sweeps) and rho of its own colour with unit stride instead of every other value of whole sectors.
 __global__ void __launch_bounds__(256) k_node_classes(Grid g, int bc_mode, const int* __restrict__ object_id, const double* __restrict__ rho,
-                                                      unsigned char* __restrict__ cls, double* __restrict__ rho_split) {
+                                                      unsigned char* __restrict__ cls, double* __restrict__ rho_split, unsigned char* __restrict__ cls_nat) {
     const int hk = (g.nk + 1) >> 1;
     const size_t half = (size_t)g.ni * g.nj * hk;
     for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < (size_t)g.nv; u += (size_t)gridDim.x * blockDim.x) {
         int k = (int)(u % g.nk); size_t row = u / g.nk; int j = (int)(row % g.nj), i = (int)(row / g.nj);
         const int color = (i + j + k) & 1;                                      // k == (i+j+color)&1 mod 2
         const size_t c = (size_t)color * half + row * hk + (k >> 1);
-        cls[c] = (unsigned char)node_class(g, bc_mode, object_id[u], i, j, k);
+        const unsigned char cl = (unsigned char)node_class(g, bc_mode, object_id[u], i, j, k);
+        cls[c] = cl; cls_nat[u] = cl;                                           // colour-compact for the row sweeps, node order for the tiled sweep
         rho_split[c] = rho[u];
     }
 }
@@ -70,6 +71,75 @@ __global__ void __launch_bounds__(128) k_sor_row(Grid g, SorParams sp, int color
         const double nw = ((rho[crow + (k >> 1)] - sp.qe * ne) * sp.inv_eps0 + (phi[u - si] + phi[u + si]) * sp.inv_d2x + (phi[u - sj] + phi[u + sj]) * sp.inv_d2y +
                            (phi[u - 1] + phi[u + 1]) * sp.inv_d2z) * sp.inv_twos;
         phi[u] = p + sp.w * (nw - p);
+    }
+}
+
+// ---------------------------------------------------------------- one pass per iteration: plane-marching shared-memory tiles
+// A red-black iteration as two row sweeps reads phi twice (279 MB of DRAM traffic per half-sweep at 256^3: 33 B per node and iteration).
+// Here ONE kernel does both colours: a block owns a (j, k) tile and marches along i.  Step p: (A) the RED nodes of plane p are updated
+// from the old BLACK values on the tile extended by one node in j and k (the ring is recomputed by the neighbour tiles: it only
+// reads old values, which never change - phi is double-buffered) and kept in a three-plane ring in shared memory; (B) the BLACK nodes of
+// plane p - 1 are updated from the new red values of planes p - 2, p - 1, p in shared memory, and plane p - 1 leaves for the output
+// buffer as whole rows (new reds from shared memory, new blacks).  Every operand has exactly the value the two-sweep kernels see, and the
+// update expression is the same: the result is bit-identical to k_sor_row.  DRAM traffic: phi read once, rho, class byte, phi
+// written once = 25 B per node and iteration, plus the ring rows shared with the neighbour tiles (served by the L2).
+#define ST_TJ 16
+#define ST_TK 64
+#define ST_ROW (ST_TK + 4)                                   // padded row of the shared-memory planes (ST_TK + 2 used)
+#define ST_THREADS 256
+__device__ __forceinline__ double sor_update(const SorParams& sp, double p, double rho, double im, double ip, double jm, double jp, double km, double kp) {
+    const double ne = (sp.n0 != 0.0) ? sp.n0 * exp((p - sp.phi0) / sp.Te0) : 0.0;
+    const double nw = ((rho - sp.qe * ne) * sp.inv_eps0 + (im + ip) * sp.inv_d2x + (jm + jp) * sp.inv_d2y + (km + kp) * sp.inv_d2z) * sp.inv_twos;
+    return p + sp.w * (nw - p);
+}
+// Within a step a thread requests all operands of a node at once, without looking at the class byte first (neighbour offsets are
+// zeroed on the mesh faces, so every address is valid): one memory round trip per node instead of two.
+#define ST_HALF ((ST_TK + 2) / 2)                            // red (or black) nodes per row of the extended region
+__global__ void __launch_bounds__(ST_THREADS, 4) k_sor_tiled(Grid g, SorParams sp, const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ rho,
+                                                            const unsigned char* __restrict__ cls, int planes_per_block) {
+    __shared__ double R[3][ST_TJ + 2][ST_ROW];
+    const int k0 = blockIdx.x * ST_TK, j0 = blockIdx.y * ST_TJ, ia = blockIdx.z * planes_per_block, ib = min(ia + planes_per_block, g.ni);
+    const long long si = (long long)g.nj * g.nk, sj = g.nk;
+    for (int p = max(ia - 1, 0); p <= ib; p++) {
+        // ---- (A) new red values of plane p on the tile extended by one node in j and k -> R[p % 3]
+        if (p < g.ni) {
+            double (*Rp)[ST_ROW] = R[p % 3];
+            const long long oim = p > 0 ? -si : 0, oip = p < g.ni - 1 ? si : 0;
+            for (int t = threadIdx.x; t < (ST_TJ + 2) * ST_HALF; t += ST_THREADS) {
+                const int jr = t / ST_HALF, j = j0 - 1 + jr;
+                const int kr = 2 * (t - jr * ST_HALF) + ((p + j + k0 + 1) & 1), k = k0 - 1 + kr;      // (p + j + k) even: red
+                if (j < 0 || j >= g.nj || k < 0 || k >= g.nk) continue;
+                const size_t u = ((size_t)p * g.nj + j) * g.nk + k;
+                const long long ojm = j > 0 ? -sj : 0, ojp = j < g.nj - 1 ? sj : 0, okm = k > 0 ? -1 : 0, okp = k < g.nk - 1 ? 1 : 0;
+                const int c = cls[u]; const double v0 = in[u], rh = rho[u];
+                const double a0 = in[u + oim], a1 = in[u + oip], a2 = in[u + ojm], a3 = in[u + ojp], a4 = in[u + okm], a5 = in[u + okp];
+                double v;
+                if (c == 7) v = sor_update(sp, v0, rh, a0, a1, a2, a3, a4, a5);
+                else v = c == 0 ? v0 : c == 1 ? a1 : c == 2 ? a0 : c == 3 ? a3 : c == 4 ? a2 : c == 5 ? a5 : a4;       // face_neighbor: the inward neighbour
+                Rp[jr][kr] = v;
+            }
+        }
+        __syncthreads();
+        // ---- (B) plane q = p - 1 of the tile: new blacks from the new reds in shared memory; the whole plane leaves for `out`
+        const int q = p - 1;
+        if (q >= ia && q < ib) {
+            double (*Rq)[ST_ROW] = R[q % 3]; double (*Rm)[ST_ROW] = R[(q + 2) % 3]; double (*Rn)[ST_ROW] = R[(q + 1) % 3];
+            for (int t = threadIdx.x; t < ST_TJ * ST_TK; t += ST_THREADS) {
+                const int jr = t / ST_TK, kr = t - jr * ST_TK, j = j0 + jr, k = k0 + kr;
+                if (j >= g.nj || k >= g.nk) continue;
+                const int jj = jr + 1, kk = kr + 1;
+                const size_t u = ((size_t)q * g.nj + j) * g.nk + k;
+                double v;
+                if (((q + j + k) & 1) == 0) v = Rq[jj][kk];                                 // red: computed in step q
+                else {
+                    const int c = cls[u]; const double v0 = in[u], rh = rho[u];
+                    if (c == 7) v = sor_update(sp, v0, rh, Rm[jj][kk], Rn[jj][kk], Rq[jj - 1][kk], Rq[jj + 1][kk], Rq[jj][kk - 1], Rq[jj][kk + 1]);
+                    else v = c == 0 ? v0 : c == 1 ? Rn[jj][kk] : c == 2 ? Rm[jj][kk] : c == 3 ? Rq[jj + 1][kk] : c == 4 ? Rq[jj - 1][kk] : c == 5 ? Rq[jj][kk + 1] : Rq[jj][kk - 1];
+                }
+                out[u] = v;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -254,9 +324,11 @@ static int prepare_classes(picg_solver_s* s) {
     if (!s->cls) {
         cudaError_t e = cudaMalloc(&s->cls, 2 * half);
         if (e == cudaSuccess) e = cudaMalloc(&s->rho_split, 2 * half * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&s->cls_nat, (size_t)g.nv);
+        if (e == cudaSuccess) e = cudaMalloc(&s->phi_alt, (size_t)g.nv * 8);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(colour-compact classes / rho)", __FILE__, __LINE__);
     }
-    LAUNCH(K_MISC, k_node_classes, std::min(div_up(g.nv, 256), g_sm_count * 8), 256, 0, g, s->bc_mode, s->w->object_id, s->w->rho, s->cls, s->rho_split); CHECK_LAUNCH();
+    LAUNCH(K_MISC, k_node_classes, std::min(div_up(g.nv, 256), g_sm_count * 8), 256, 0, g, s->bc_mode, s->w->object_id, s->w->rho, s->cls, s->rho_split, s->cls_nat); CHECK_LAUNCH();
     return PICG_OK;
 }
 static SlabArgs slab_args(picg_solver_s* s, unsigned seq_off) {
@@ -267,9 +339,25 @@ static SlabArgs slab_args(picg_solver_s* s, unsigned seq_off) {
     return S;
 }
 // n iterations = 2n colour half-sweeps enqueued back to back (plain launches; `timed` adds the per-kernel bookkeeping)
+static bool use_tiled(const picg_solver_s* s) { return s->slab_world <= 1 && s->sweep_mode == 1; }
 static int enqueue_iterations(picg_solver_s* s, const SorParams& p, unsigned n, bool timed) {
     const Grid& g = s->w->g;
     const bool slab = s->slab_world > 1;
+    if (use_tiled(s)) {                                           // one kernel per iteration, phi double-buffered (see k_sor_tiled)
+        const int tiles = div_up(g.nk, ST_TK) * div_up(g.nj, ST_TJ);
+        int chunks = std::max(1, std::min(g.ni, div_up((size_t)g_sm_count * 4, (size_t)tiles)));       // four blocks per SM: one wave
+        const int ppb = div_up(g.ni, chunks);
+        dim3 tgrid(div_up(g.nk, ST_TK), div_up(g.nj, ST_TJ), div_up(g.ni, ppb));
+        double* src = s->w->phi; double* dst = s->phi_alt;
+        for (unsigned h = 0; h < n; h++) {
+            if (timed) LAUNCH(K_SOR_TILED, k_sor_tiled, tgrid, ST_THREADS, 0, g, p, src, dst, s->w->rho, s->cls_nat, ppb);
+            else k_sor_tiled<<<tgrid, ST_THREADS, 0, g_stream>>>(g, p, src, dst, s->w->rho, s->cls_nat, ppb);
+            CHECK_LAUNCH();
+            std::swap(src, dst);
+        }
+        if (n & 1) CUDA_TRY(cudaMemcpyAsync(s->w->phi, s->phi_alt, (size_t)g.nv * 8, cudaMemcpyDeviceToDevice, g_stream));      // the result lives in the world's phi
+        return PICG_OK;
+    }
     dim3 grid(g.nj, slab ? s->slab_i1 - s->slab_i0 : g.ni);
     for (unsigned h = 0; h < 2 * n; h++) {
         const int color = h & 1;
@@ -310,8 +398,9 @@ static int run_iterations(picg_solver_s* s, const SorParams& p, unsigned n) {
         s->graphs.push_back(entry);
     }
     {
-        TimerScope t(K_SOR);                                      // the whole batch is one timed interval; every half-sweep counts as a launch
-        for (unsigned h = 0; h < 2 * n; h++) count_launch(K_SOR);
+        const bool tiled = use_tiled(s);
+        TimerScope t(tiled ? K_SOR_TILED : K_SOR);               // the whole batch is one timed interval; every sweep kernel counts as a launch
+        for (unsigned h = 0; h < (tiled ? n : 2 * n); h++) count_launch(tiled ? K_SOR_TILED : K_SOR);
         CUDA_TRY(cudaGraphLaunch(exec, g_stream));
     }
     return PICG_OK;
@@ -373,7 +462,7 @@ int picg_solver_destroy(picg_solver_t s) {
     drop_graphs(s);
     for (int r = 0; r < (int)s->peer_phi.size(); r++) if (r != s->slab_rank) { cudaIpcCloseMemHandle(s->peer_phi[r]); cudaIpcCloseMemHandle(s->peer_mbox[r]); }
     cudaFree(s->peer_phi_dev); cudaFree(s->peer_mbox_dev); cudaFree(s->mbox);
-    cudaFree(s->partial); cudaFree(s->cls); cudaFree(s->rho_split); cudaFree(s->pcg_work); delete s; return PICG_OK;
+    cudaFree(s->partial); cudaFree(s->cls); cudaFree(s->rho_split); cudaFree(s->cls_nat); cudaFree(s->phi_alt); cudaFree(s->pcg_work); delete s; return PICG_OK;
 }
 
 // Slab decomposition over `world` ranks on one node.  (1) every rank exports 128 bytes (the CUDA IPC handles of its phi and of
@@ -419,6 +508,15 @@ int picg_solver_slab_enable(picg_solver_t s, int rank, int world, const void* ha
 }
 int picg_solver_set_reference(picg_solver_t s, double phi0, double n0, double Te0) {
     REQUIRE_ARG(s, "picg_solver_set_reference: null solver"); s->phi0 = phi0; s->n0 = n0; s->Te0 = Te0; return PICG_OK;
+}
+// 0 (default): two row sweeps per iteration (k_sor_row); 1: one plane-marching shared-memory pass per iteration (k_sor_tiled).  Same bits.
+// Measured at 256^3 (profiles/r2_sor_tiled.md): the tiled pass moves 26 B per node and iteration instead of 33, but is issue-bound
+// (index arithmetic of two phases + shared-memory traffic: 2.1 x the row sweeps' time), so the row sweeps stay the default.
+// The slab-decomposed multi-GPU solve always uses its own row sweeps (k_sor_slab).
+int picg_solver_set_sweep(picg_solver_t s, int mode) {
+    REQUIRE_ARG(s && (mode == 0 || mode == 1), "picg_solver_set_sweep: mode must be 0 (row sweeps) or 1 (tiled one-pass sweep)");
+    if (mode != s->sweep_mode) drop_graphs(s);
+    s->sweep_mode = mode; return PICG_OK;
 }
 int picg_solver_set_boundary_mode(picg_solver_t s, int mode) {
     REQUIRE_ARG(s && (mode == 0 || mode == 1), "picg_solver_set_boundary_mode: mode must be 0 or 1"); s->bc_mode = mode; return PICG_OK;

@@ -79,7 +79,7 @@ static const char* kKernelNames[K_NUM_KERNELS] = {
     "push_electrons", "push_electrons_deposit", "push_reflect", "push_heavy", "compact", "deposit_density",
     "finalize_density", "charge_density", "sor_redblack", "residual_l2", "compute_ef", "sort_keys", "sort_hist",
     "sort_scan", "sort_scatter", "sort_permute", "cell_start", "mc_ionize", "source_inject", "add_particles",
-    "sample_moments", "count_per_cell", "transpose", "diagnostics", "misc", "push_heavy_deposit", "heavy_impacts", "dsmc_collide", "push_neutral", "nr_pcg", "deposit_tail", "mc_append"};
+    "sample_moments", "count_per_cell", "transpose", "diagnostics", "misc", "push_heavy_deposit", "heavy_impacts", "dsmc_collide", "push_neutral", "nr_pcg", "deposit_tail", "mc_append", "sor_tiled"};
 
 extern "C" {
 

@@ -471,6 +471,10 @@ class PotentialSolver:
     def setReferenceValues(self, phi0, n0, Te0):
         _chk(lib().picg_solver_set_reference(self.h, C.c_double(phi0), C.c_double(n0), C.c_double(Te0)))
 
+    def setSweep(self, mode):
+        """0: row sweeps (two per iteration, default); 1: tiled one-pass sweep.  Same bits."""
+        _chk(lib().picg_solver_set_sweep(self.h, int(mode)))
+
     def setBoundaryMode(self, mode):
         _chk(lib().picg_solver_set_boundary_mode(self.h, int(mode)))
 

@@ -200,6 +200,10 @@ PICG_API int picg_solver_destroy(picg_solver_t s);
 PICG_API int picg_solver_set_reference(picg_solver_t s, double phi0, double n0, double Te0);
 /* boundary mode: 0 = v3/ch3 zero-gradient faces updated in-sweep (PotentialSolver.cpp:96-107),
  *                1 = ch2 interior-only sweep, faces keep their (Dirichlet) values (ch2/v2/PotentialSolver.cpp:39-52) */
+/* How an iteration sweeps the mesh: 0 (default) = two colour sweeps, one block per (i, j) row; 1 = ONE plane-marching pass over
+ * shared-memory tiles that updates both colours (26 B of DRAM traffic per node and iteration instead of 33, but more instructions:
+ * slower on B200, kept as an option).  Bit-identical results. */
+PICG_API int picg_solver_set_sweep(picg_solver_t s, int mode);
 PICG_API int picg_solver_set_boundary_mode(picg_solver_t s, int mode);
 /* solveGS  PotentialSolver.cpp:69-166 as red-black SOR (w=1.4), residual every 25 iterations normalised by nv */
 PICG_API int picg_solver_solve_gs(picg_solver_t s, int* converged, unsigned* iterations, double* L2);

@@ -443,3 +443,31 @@ def test_neutral_push_is_a_pure_drift_and_matches_the_reference(picgpu, ref):
     assert np.array_equal(got, want)
     for o in (nr, wr, ng, wg):
         o.close()
+
+
+@pytest.mark.parametrize("shape,n0,Te0,bc", [((13, 11, 17), 0.0, 1e20, 0), ((13, 11, 17), 1e12, 5000.0, 0), ((37, 21, 133), 0.0, 1e20, 0), ((9, 40, 70), 0.0, 1e20, 1), ((5, 5, 5), 0.0, 1e20, 0)])
+def test_tiled_one_pass_sweep_is_bit_identical_to_the_row_sweeps(picgpu, shape, n0, Te0, bc):
+    """PotentialSolver::solveGS as ONE plane-marching shared-memory pass per iteration (k_sor_tiled, both colours, phi double-buffered)
+    against the two row sweeps per iteration (k_sor_row): the same bits after any number of iterations (odd and even batches, tiles
+    and plane chunks that do not divide the mesh, electrodes, Boltzmann electrons, the ch2 Dirichlet box), the same convergence decision."""
+    pg = picgpu
+    ni, nj, nk = shape
+    x0, xm, rects = util.discharge_geometry(ni, nj, nk)
+    rng = np.random.default_rng(21)
+    rho = rng.normal(0, 1e-7, shape)
+    phis = {}
+    for mode in (0, 1):
+        w = util.build_world(pg.World, ni, nj, nk, x0, xm, rects if bc == 0 else ())
+        w.upload(pg.F_RHO, rho)
+        sol = pg.PotentialSolver(w, 400, 1e-3)
+        sol.setReferenceValues(0.0, n0, Te0); sol.setBoundaryMode(bc); sol.setSweep(mode)
+        out = []
+        for n in (1, 2, 7, 25, 26):                           # plain launches (n < 4) and graph replays, odd and even batch lengths
+            sol.iterate(n); out.append(w.phi)
+        conv = sol.solveGS(); out.append(w.phi)
+        sol.computeEF(); out.append(w.ef)
+        phis[mode] = (out, conv, sol.iterations, sol.L2)
+        sol.close(); w.close()
+    for a, b in zip(phis[0][0], phis[1][0]):
+        assert np.array_equal(a, b)
+    assert phis[0][1:] == phis[1][1:]
