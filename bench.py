@@ -488,8 +488,14 @@ def run_ours(args):
         all_sums = [torch.zeros_like(sums) for _ in range(world)]
         dist.all_gather(all_sums, sums)
         if rank == 0:
-            w2.computeChargeDensity(chk)
+            w2.computeChargeDensity(chk); pg.synchronize()        # (the comparison runs on torch's stream: the library's must have finished)
             detail["rho"] = mismatches(rho_all, view(w2.device_ptr(pg.F_RHO)))
+            if detail["rho"] and os.environ.get("PICG_SELF_CHECK_DEBUG"):
+                r2 = view(w2.device_ptr(pg.F_RHO))
+                bad = (rho_all.view(torch.int64) != r2.view(torch.int64)).nonzero().flatten()
+                for u in bad[:8].tolist() + bad[-3:].tolist():
+                    print("rho mismatch at node %d = (i %d, j %d, k %d): multi-GPU %r, one GPU %r; den(one GPU): %s" % (
+                        u, u // (m * m), (u // m) % m, u % m, float(rho_all[u]), float(r2[u]), [float(view(c.device_ptr(pg.SF_DEN))[u]) for c in chk]), file=sys.stderr)
             view(w2.device_ptr(pg.F_PHI)).copy_(phi_before); torch.cuda.synchronize()
             sol2 = pg.PotentialSolver(w2, args.s_max_it, args.s_tol); sol2.setReferenceValues(0.0, 0.0, 1e20)
             sol2.solveGS(); sol2.computeEF(); pg.synchronize()
@@ -780,6 +786,13 @@ def run_ours(args):
                 out["cpu_baseline"] = cpu_reference_run(args, wl, steps=2, warmup=1)
             except BaseException as e:                     # never lose the device line to the CPU leg
                 out["cpu_baseline"] = {"error": str(e)[:300]}
+            if not args.no_mcc:
+                # the reference's multithreaded configuration (Config.cpp:68-75: hardware_concurrency() - 1 workers; its thread pool serves the
+                # electron push only) is only safe without MC ionisation in the loop: the same step with the interaction off
+                try:
+                    out["cpu_baseline_multithreaded"] = cpu_reference_run(args, wl, steps=2, warmup=1, no_mcc=True)
+                except BaseException as e:
+                    out["cpu_baseline_multithreaded"] = {"error": str(e)[:300]}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -788,12 +801,13 @@ def run_ours(args):
 
 
 # --------------------------------------------------------------------------------------- reference arm (CPU)
-def cpu_reference_run(args, wl_full, steps, warmup):
+def cpu_reference_run(args, wl_full, steps, warmup, no_mcc=None):
     """Times the reference's own CPU implementation of the same step on a bounded sample of the workload: a sub-volume of
     the same plasma (same dx, dt, densities and particles per cell, electrodes kept).  Uses oracle/_ref (the unmodified
     reference compiled here) when present, else the C port of the same loops."""
     from oracle import ref_v3
     import util
+    no_mcc = args.no_mcc if no_mcc is None else no_mcc
     wl, n_total = sub_volume(wl_full, args.cpu_sample_nodes)
     m = wl["mesh"]
     cores = os.cpu_count() or 1
@@ -802,7 +816,7 @@ def cpu_reference_run(args, wl_full, steps, warmup):
         # Config.cpp:68-75 default is hardware_concurrency()-1 threads, used by the electron push only.  With MC ionisation
         # in the loop the thread-pool push leaves stale per-cell index lists behind (the reference then reads
         # particles past the end of its store and crashes), so the reference is run serial in that case.
-        threads = 1 if not args.no_mcc else max(1, cores - 1)
+        threads = 1 if not no_mcc else max(1, cores - 1)
         ref_v3.config(subcycling=False, multithreading=threads > 1, num_threads=threads, merging=False, sputtering=False)
         saved_stdout = os.dup(1)                             # the reference prints progress to stdout: keep the JSON line clean
         sys.stdout.flush()
@@ -825,7 +839,7 @@ def cpu_reference_run(args, wl_full, steps, warmup):
             sp[s["name"]] = o
         order = [sp["O"], sp["O+"], sp["e-"]]
         tmp = tempfile.mkdtemp()
-        mcc = None if args.no_mcc else ref_v3.MC_MEX_Ionization(sp["O"], sp["O+"], sp["e-"], w, util.write_table(os.path.join(tmp, "Oxygen_momentum_transfer.txt")))
+        mcc = None if no_mcc else ref_v3.MC_MEX_Ionization(sp["O"], sp["O+"], sp["e-"], w, util.write_table(os.path.join(tmp, "Oxygen_momentum_transfer.txt")))
 
         def step(ts):
             if mcc:
@@ -861,7 +875,8 @@ def cpu_reference_run(args, wl_full, steps, warmup):
     val = 0.5 * (n0 + n1) * steps / dt
     return {"value": val, "unit": "particle-steps/s", "cores": threads, "host_cores": cores, "kind": kind, "ms_per_step": dt / steps * 1e3,
             "sample": "sub-volume of the same plasma: %d^3 nodes (same dx, dt, densities, %.1f particles/cell), %d macro-particles, %d steps; "
-                      "reference on %d thread(s) (only its electron push can use the thread pool, Species.cpp:258-355; serial when MC ionisation is on, SURVEY B20)" % (m, wl["ppc"], int(n0), steps, threads)}
+                      "reference on %d thread(s)%s (only its electron push can use the thread pool, Species.cpp:258-355; serial when MC ionisation is on, SURVEY B20)"
+                      % (m, wl["ppc"], int(n0), steps, threads, ", MC ionisation off" if no_mcc and not args.no_mcc else "")}
 
 
 def run_reference(args):

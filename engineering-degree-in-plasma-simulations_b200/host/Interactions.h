@@ -4,6 +4,7 @@
 #ifndef INTERACTIONS_H
 #define INTERACTIONS_H
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include "Species.h"
 #include "World.h"
@@ -42,5 +43,8 @@ public:
                       std::string coll_data_path = "data/Oxygen_momentum_transfer.txt", int freq_should_use_map = 10);
     void apply(type_calc dt) noexcept override;
     const picg_mcc_stats& stats() const { return last; }
+    // The same class in ch4/v2 (ch4/v2/Interactions.cpp:476-735) uses FIXED weights: Bird's candidate count with neutrals.mpw0, unweighted
+    // acceptance, products through Species::addParticle, neutrals never depleted.  A ch4/v2 main selects that algorithm here.
+    void useFixedWeights(bool on) { if (picg_mcc_set_variant(handle.get(), on ? 1 : 0) != PICG_OK) throw std::runtime_error(picg_last_error()); }
 };
 #endif

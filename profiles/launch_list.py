@@ -7,7 +7,7 @@ rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))
 h = rows[0]; kn, mv, mu = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
 scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}
 L = [(r[kn].split("(")[0].replace("void ", ""), float(r[mv].replace(",", "")) * scale[r[mu]]) for r in rows[1:] if len(r) > mv]
-pos = [i for i, (n, _) in enumerate(L) if n == "k_mcc"]
+pos = [i for i, (n, _) in enumerate(L) if n == "k_mcc" or n.startswith("k_mcc<")]
 print("# ncu launch list, B200, `%s`" % (sys.argv[2] if len(sys.argv) > 2 else "bench.py"))
 print("# (`ncu --metrics gpu__time_duration.sum --clock-control none`; times are cold-cache and serialised: compare SHARES, not absolutes)")
 print("# %d launches in the whole run; k_mcc launches (one per step) at positions %s" % (len(L), pos))

@@ -144,6 +144,19 @@ def test_reference_main_runs_on_the_device():
     assert len(diag) == 1 + 13                                            # header + num_ts+1 steps
     last = diag[-1].split(",")
     assert int(last[0]) == 12 and np.isfinite([float(x) for x in last[1:]]).all()
+    # the numbers of Output::diagOutput (Outputs.cpp:143-179), checked against what the configuration of main.cpp:89-122 implies
+    cols = diag[0].split(",")
+    rows = [dict(zip(cols, map(float, r.split(","))) ) for r in diag[1:]]
+    kT = util.KB * 300.0
+    for r in rows:
+        assert abs(r["mp_count.O"] - n_neutrals) <= 200 + 30 * r["ts"]                      # neutrals leave through the open faces / split in collisions: a handful per step
+        assert r["real_count.O"] + r["real_count.O+"] == pytest.approx(n_neutrals * 5e11, rel=1e-4)       # weight only moves from O to O+
+        assert r["KE.O"] == pytest.approx(1.5 * kT * r["real_count.O"], rel=0.01)           # 300 K Maxwellian loaded by loadParticleBoxThermal (main.cpp:119)
+        assert r["mp_count.e-"] == 64 + r["mp_count.O+"]                                     # every ionisation adds one ion and one electron (main.cpp:117: 64 at start)
+        assert r["PE"] == pytest.approx(rows[0]["PE"], rel=1e-12) and r["PE"] > 0            # the field is solved once (main.cpp:172) and never again (:260-261)
+        assert r["E_total"] == pytest.approx(r["KE.O"] + r["KE.O+"] + r["KE.e-"] + r["PE"], rel=1e-12)
+    ke_e = [r["KE.e-"] for r in rows]
+    assert ke_e[-1] > 5 * ke_e[0]                                          # the electrons fall through the cathode sheath field: their energy grows every step
 
 
 @pytest.mark.gpu
