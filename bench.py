@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--moments", action="store_true", help="also run Species::sampleMoments every step (SURVEY 8f row 1)")
     ap.add_argument("--cpu_sample_nodes", type=int, default=49, help="nodes per axis of the CPU-baseline sub-volume (same dx, same particles per cell)")
     ap.add_argument("--skip_cpu_baseline", action="store_true")
+    ap.add_argument("--cpu_leg", default=None, help="internal: 'steps,warmup,no_mcc' - run one CPU reference leg and print its JSON (child process of the default run)")
     ap.add_argument("--allreduce_density", action="store_true", help="multi-GPU: all-reduce the density accumulators (full grids everywhere) instead of a reduce-scatter onto the slabs")
     ap.add_argument("--poisson", choices=["auto", "replicated", "slab"], default="auto",
                     help="multi-GPU solve: every rank solves the whole grid, or planes split over the ranks with peer-memory halos (auto: slab when N > 1)")
@@ -782,17 +783,18 @@ def run_ours(args):
             out["multi_gpu_parity"] = mg_parity
             out["multi_gpu_parity_detail"] = mg_detail
         if not args.skip_cpu_baseline:
-            try:
-                out["cpu_baseline"] = cpu_reference_run(args, wl, steps=2, warmup=1)
-            except BaseException as e:                     # never lose the device line to the CPU leg
-                out["cpu_baseline"] = {"error": str(e)[:300]}
+            # Each CPU leg runs in a child process: the reference's thread pool is racy and a crash of the reference must not
+            # take the device line down with it.
+            out["cpu_baseline"] = cpu_leg_in_child(args, steps=2, warmup=1, no_mcc=args.no_mcc)
             if not args.no_mcc:
                 # the reference's multithreaded configuration (Config.cpp:68-75: hardware_concurrency() - 1 workers; its thread pool serves the
                 # electron push only) is only safe without MC ionisation in the loop: the same step with the interaction off
-                try:
-                    out["cpu_baseline_multithreaded"] = cpu_reference_run(args, wl, steps=2, warmup=1, no_mcc=True)
-                except BaseException as e:
-                    out["cpu_baseline_multithreaded"] = {"error": str(e)[:300]}
+                mt = cpu_leg_in_child(args, steps=2, warmup=1, no_mcc=True, tries=1)
+                if "error" in mt:
+                    mt["finding"] = ("the reference's thread-pool electron push cannot run this workload: ThreadPool::AddTask binds its arguments by value (ThreadPool.h:63), so the "
+                                     "per-thread delete buffers of Species.cpp:276-282 stay empty, electrons that leave the domain or hit an electrode are never removed and the next "
+                                     "Field::scatter writes out of range (SIGSEGV in computeNumberDensity); the serial leg above is the reference's only working configuration here")
+                out["cpu_baseline_multithreaded"] = mt
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -801,6 +803,27 @@ def run_ours(args):
 
 
 # --------------------------------------------------------------------------------------- reference arm (CPU)
+
+def cpu_leg_in_child(args, steps, warmup, no_mcc, tries=2):
+    """Runs cpu_reference_run in a child python (same flags) and returns its dict; a crash or a time-out becomes {"error": ...}."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu_leg", "%d,%d,%d" % (steps, warmup, 1 if no_mcc else 0), "--mesh", str(args.mesh), "--particles", repr(args.particles),
+           "--s_max_it", str(args.s_max_it), "--s_tol", repr(args.s_tol), "--cpu_sample_nodes", str(args.cpu_sample_nodes)] + (["--moments"] if args.moments else [])
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    err = "not run"
+    for _ in range(tries):
+        try:
+            p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=600, env=env)
+        except subprocess.TimeoutExpired:
+            err = "CPU leg timed out after 600 s"; continue
+        lines = [l for l in p.stdout.decode(errors="replace").splitlines() if l.startswith("{")]
+        if p.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        err = "CPU leg exited with code %d (the reference crashed)" % p.returncode
+    return {"error": err}
+
+
 def cpu_reference_run(args, wl_full, steps, warmup, no_mcc=None):
     """Times the reference's own CPU implementation of the same step on a bounded sample of the workload: a sub-volume of
     the same plasma (same dx, dt, densities and particles per cell, electrodes kept).  Uses oracle/_ref (the unmodified
@@ -897,7 +920,10 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.cpu_leg:
+        st, wu, nm = (int(v) for v in a.cpu_leg.split(","))
+        print(json.dumps(cpu_reference_run(a, workload(a.mesh, a.particles), steps=st, warmup=wu, no_mcc=bool(nm))))
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
