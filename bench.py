@@ -164,6 +164,10 @@ def run_ours(args):
     pg.init(local)
     pg.set_rank(rank, world)
     pg.seed(0x5EED0000)
+    if os.environ.get("PICG_MERGE_FRACTION"):                  # tuning switches (profiles/r2_list_policy.md)
+        pg.set_merge_fraction(float(os.environ["PICG_MERGE_FRACTION"]))
+    if os.environ.get("PICG_MOVER_FRACTION"):
+        pg.set_mover_fraction(float(os.environ["PICG_MOVER_FRACTION"]))
     stream = torch.cuda.ExternalStream(pg.stream_ptr(), device=local)
 
     if args.subcycled_steps is None:                       # a secondary, single-GPU measurement unless asked for

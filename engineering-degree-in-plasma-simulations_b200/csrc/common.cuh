@@ -130,7 +130,6 @@ struct picg_mcc_s {
     u64 step = 0;
     size_t last_appends[3] = {0, 0, 0};   // neutrals, electrons, ions appended by the previous apply (capacity estimate)
     int fixed_weight = 0;              // 1: the fixed-weight algorithm of ch4/v2 (Interactions.cpp:566-641) instead of v3's variable weights
-    unsigned* orphans = nullptr;       // device: 3 x (count, slots): product slots reserved by a collision that could not complete (mcc.cu)
 };
 
 struct picg_dsmc_s {

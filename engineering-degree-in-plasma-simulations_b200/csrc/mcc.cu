@@ -16,6 +16,12 @@
 // warp-synchronous: a warp owns 32 consecutive cells (lane = cell), iteration t handles the t-th candidate of every cell, and the
 // products of one iteration take consecutive slots of ONE atomicAdd per store (warp_reserve).  Products of neighbouring cells end
 // up next to each other in the appended tail, which the tail deposit likes.
+// Staging.  The products do not go to the stores directly: every product is written as one 64-byte record (x y z u v w mpw) plus its
+// cell into a staging area, indexed by the cursors above.  After the kernel the records of a store are ordered by (cell, order of
+// creation inside the cell) with the counting sort of sort.cu - the key is the cell of the thread that made the product, no position
+// is looked at - and appended to the store in that order (k_stage_commit).  Two things follow: the appended tail of a call is in cell
+// order (its deposit runs on register sums and shared-memory windows instead of eight global reductions per particle), and it no longer
+// depends on the order in which the warps got their turn at the cursors: the same input gives the same stores, bit for bit.
 #include "common.cuh"
 #include "philox.cuh"
 #include "celllists.cuh"
@@ -26,7 +32,11 @@
 
 using namespace picg;
 
-namespace picg { int sort_species(picg_species_s* s); int species_exact_lists(picg_species_s* s); int species_prepare_lists(picg_species_s* s); }
+namespace picg {
+int sort_species(picg_species_s* s); int species_exact_lists(picg_species_s* s); int species_prepare_lists(picg_species_s* s);
+size_t counting_sort_words(const Grid& g);                  // sort.cu
+int scan_cell_table(const Grid& g, unsigned* table, unsigned* work);
+}
 
 #define MCC_EXTRA 16          // split-off neutrals created in this call that remain selectable within the cell (:699-701)
 
@@ -95,7 +105,6 @@ __device__ __forceinline__ bool collide(PhiloxStream& r, const MccParams& P, con
 
 // ---------------------------------------------------------------- appends: one atomic per warp iteration and store
 #define MCC_THREADS 128
-#define MCC_ORPHANS 4096
 // A warp walks 32 consecutive cells in lockstep (lane = cell); iteration t handles candidate t of every cell that still has
 // one.  The lanes whose candidate creates a product take consecutive slots of ONE atomicAdd on the store's counter.
 // All 32 lanes call.  Returns the slot, or -1 (not wanted, or the store is full: the counter is clamped after the kernel).
@@ -110,14 +119,14 @@ __device__ __forceinline__ long long warp_reserve(bool want, int lane, u64* curs
     const u64 dst = base + __popc(mask & ((1u << lane) - 1));
     return dst < cap ? (long long)dst : -1;
 }
-// a slot that was reserved for a collision that could not complete (the partner store was full): listed, closed by the
-// compaction after the kernel (orphans[0]: count)
-__device__ __forceinline__ void orphan_slot(unsigned* orphans, long long slot) {
-    unsigned t = atomicAdd(orphans, 1u);
-    if (t < MCC_ORPHANS) orphans[1 + t] = (unsigned)slot;
-}
-__device__ __forceinline__ void write_slot(const Store& s, long long dst, const double pos[3], const double v[3], double mpw) {
-    s.a[0][dst] = pos[0]; s.a[1][dst] = pos[1]; s.a[2][dst] = pos[2]; s.a[3][dst] = v[0]; s.a[4][dst] = v[1]; s.a[5][dst] = v[2]; s.a[6][dst] = mpw;
+// Staging area of one store: 8 doubles per record (x y z u v w mpw, one spare), the cell of every record, the cursor.
+// kr: (cell, rank of the record among the records of its cell) - a cell's records are made by one thread, one after the other, so the
+// thread numbers them itself; made[c]: how many it made (table zeroed before the launch, written once per cell).
+struct Stage { double* rec; uint2* kr; unsigned* made; u64* cursor; u64 cap; };
+__device__ __forceinline__ void write_stage(const Stage& S, long long e, const double pos[3], const double v[3], double mpw, unsigned cell, int& rank) {
+    double4* r = reinterpret_cast<double4*>(S.rec + 8 * e);
+    r[0] = make_double4(pos[0], pos[1], pos[2], v[0]); r[1] = make_double4(v[1], v[2], mpw, 0.0);
+    S.kr[e] = make_uint2(cell, (unsigned)rank++);
 }
 __device__ __forceinline__ void atomic_max_pos_double(double* addr, double v) {     // valid for non-negative doubles
     atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
@@ -137,9 +146,10 @@ __device__ __forceinline__ bool add_particle_filter_rewind(const Grid& g, const 
 //        [5] dropped because a product store was full (collision skipped untouched)
 //        [6] split-off neutrals beyond MCC_EXTRA per cell and call (created, but not selectable by later candidates of the same call)
 //        [7] fixed-weight variant: created electrons with a NaN velocity (ionisation below the threshold, ch4/v2 only; appended as the reference does)
-// orphans: [0..2] MCC_ORPHANS + 1 words each for neutrals / electrons / ions
+// Sn / Se / Si: staging areas of the neutral / electron / ion products (a record whose collision could not complete, because the partner
+// store was full, gets the key nc and is dropped by the sort)
 template <int FIXED>
-__global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, CellLists Ln, CellLists Le, unsigned* __restrict__ orphans,
+__global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, CellLists Ln, CellLists Le, Stage Sn, Stage Se, Stage Si,
                                                         double* __restrict__ wsv, u64* __restrict__ stats, double dt, uint64_t seed, uint32_t stream, uint32_t call) {
     const int lane = threadIdx.x & 31;
     const double W_max = wsv[0];
@@ -167,18 +177,22 @@ __global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Sto
         if (max_groups == 0) continue;                                                    // warp-uniform
         PhiloxStream r; r.init(seed, stream, (u64)c, call);
         long long extra[MCC_EXTRA]; int n_extra = 0;
+        int made_n = 0, made_e = 0, made_i = 0;                                            // records this cell has staged so far, per store
         for (int t = 0; t < max_groups; t++) {
             // kind of product this lane's candidate asks for: 0 none, 1 split-off neutral, 2 ion + electron
-            int kind = 0; u64 pn = 0, pe = 0;
+            int kind = 0; u64 pn = 0, pe = 0; bool staged = false;
             double vn_[3] = {0, 0, 0}, ve_[3] = {0, 0, 0}, vnew[3] = {0, 0, 0}, pos[3] = {0, 0, 0}, Wn = 0, We = 0, Wl = 0;
             bool ion_ok[2] = {false, false};                                               // FIXED: addParticle accepts the ion / the electron
             double vi[3] = {0, 0, 0};
             if (t < n_groups) {
                 int a = (int)(r.next() * np_n);                                            // rnd(0,np) = 0 + rnd()*(np-0)
                 int b = (int)(r.next() * np_e);
-                pn = a < np_n0 ? (u64)cell_pick(Ln, vn, a) : (u64)extra[a - np_n0];
+                staged = a >= np_n0;                                                       // a neutral split off earlier in this call: still in the staging area
+                pn = staged ? (u64)extra[a - np_n0] : (u64)cell_pick(Ln, vn, a);
                 pe = (u64)cell_pick(Le, ve, b);
-                vn_[0] = neu.a[3][pn]; vn_[1] = neu.a[4][pn]; vn_[2] = neu.a[5][pn]; ve_[0] = ele.a[3][pe]; ve_[1] = ele.a[4][pe]; ve_[2] = ele.a[5][pe];
+                if (staged) { vn_[0] = Sn.rec[8 * pn + 3]; vn_[1] = Sn.rec[8 * pn + 4]; vn_[2] = Sn.rec[8 * pn + 5]; }
+                else { vn_[0] = neu.a[3][pn]; vn_[1] = neu.a[4][pn]; vn_[2] = neu.a[5][pn]; }
+                ve_[0] = ele.a[3][pe]; ve_[1] = ele.a[4][pe]; ve_[2] = ele.a[5][pe];
                 double d[3] = {vn_[0] - ve_[0], vn_[1] - ve_[1], vn_[2] - ve_[2]};
                 double v_rel = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
                 double E_rel = P.E_rel_eV * v_rel * v_rel;
@@ -193,7 +207,7 @@ __global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Sto
                         ele.a[3][pe] = ve_[0]; ele.a[4][pe] = ve_[1]; ele.a[5][pe] = ve_[2];   // collide works on a reference to the electron's velocity
                         if (ionised) {
                             n_ion++; kind = 2;
-                            pos[0] = neu.a[0][pn]; pos[1] = neu.a[1][pn]; pos[2] = neu.a[2][pn];
+                            pos[0] = neu.a[0][pn]; pos[1] = neu.a[1][pn]; pos[2] = neu.a[2][pn];          // (the fixed-weight variant never splits: pn is a store slot)
                             vi[0] = vn_[0]; vi[1] = vn_[1]; vi[2] = vn_[2];
                             ion_ok[0] = add_particle_filter_rewind(g, P.ef, P.qm_ion, P.half_dt, pos, vi);      // ions.addParticle(pos, vel_neutral, ions.mpw0) :624-626
                             // electrons.addParticle(pos, vel_new, electrons.mpw0) :628.  Below the ionisation threshold ch4/v2 computes the
@@ -205,7 +219,7 @@ __global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Sto
                         }
                     }
                 } else {
-                    Wn = neu.a[6][pn]; We = ele.a[6][pe];
+                    Wn = staged ? Sn.rec[8 * pn + 6] : neu.a[6][pn]; We = ele.a[6][pe];
                     double Wg = Wn < We ? We : Wn; Wl = Wn < We ? Wn : We;                  // greaterLesser funkc.h:19-25
                     double Wsv = Wg * s_coll * v_rel;
                     if (Wsv > step_max) step_max = Wsv;
@@ -214,7 +228,8 @@ __global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Sto
                         if (Wn > We) {                                                     // split the neutral (:684-703)
                             bool ionised = collide(r, P, vn_, ve_, vnew, s_coll);          // pure: works on local copies
                             kind = ionised ? 2 : 1;
-                            pos[0] = neu.a[0][pn]; pos[1] = neu.a[1][pn]; pos[2] = neu.a[2][pn];
+                            if (staged) { pos[0] = Sn.rec[8 * pn]; pos[1] = Sn.rec[8 * pn + 1]; pos[2] = Sn.rec[8 * pn + 2]; }
+                            else { pos[0] = neu.a[0][pn]; pos[1] = neu.a[1][pn]; pos[2] = neu.a[2][pn]; }
                         } else if (Wn < We) {
                             n_skip++;      // the reference's electron-heavier branch is defective; not reproduced, counted
                         }                  // equal weights: accepted pair does nothing (:727-734)
@@ -225,39 +240,42 @@ __global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Sto
             if (FIXED) {
                 for (int q = 0; q < P.ions_to_create; q++) {                               // :623-626, one ion per round
                     const bool want = kind == 2 && ion_ok[0];
-                    long long s1 = warp_reserve(want, lane, &ion.ctr->n, ion.cap);
-                    if (want) { if (s1 < 0) n_drop++; else write_slot(ion, s1, pos, vi, P.ion_mpw0); }
+                    long long s1 = warp_reserve(want, lane, Si.cursor, Si.cap);
+                    if (want) { if (s1 < 0) n_drop++; else write_stage(Si, s1, pos, vi, P.ion_mpw0, (unsigned)c, made_i); }
                 }
                 const bool want = kind == 2 && ion_ok[1];
-                long long s2 = warp_reserve(want, lane, &ele.ctr->n, ele.cap);
-                if (want) { if (s2 < 0) n_drop++; else write_slot(ele, s2, pos, vnew, P.ele_mpw0); }
+                long long s2 = warp_reserve(want, lane, Se.cursor, Se.cap);
+                if (want) { if (s2 < 0) n_drop++; else write_stage(Se, s2, pos, vnew, P.ele_mpw0, (unsigned)c, made_e); }
                 continue;
             }
             // Slot reservation BEFORE any state is changed: a collision whose products do not fit is skipped as a whole (and counted), so a
             // full store can never leave half-applied collisions behind.
-            long long s0 = warp_reserve(kind == 1, lane, &neu.ctr->n, neu.cap);
-            long long s1 = warp_reserve(kind == 2, lane, &ion.ctr->n, ion.cap);
-            long long s2 = warp_reserve(kind == 2, lane, &ele.ctr->n, ele.cap);
-            if (kind == 2 && (s1 < 0 || s2 < 0)) {
-                if (s1 >= 0) orphan_slot(orphans + 2 * (MCC_ORPHANS + 1), s1);
-                if (s2 >= 0) orphan_slot(orphans + 1 * (MCC_ORPHANS + 1), s2);
+            long long s0 = warp_reserve(kind == 1, lane, Sn.cursor, Sn.cap);
+            long long s1 = warp_reserve(kind == 2, lane, Si.cursor, Si.cap);
+            long long s2 = warp_reserve(kind == 2, lane, Se.cursor, Se.cap);
+            if (kind == 2 && (s1 < 0 || s2 < 0)) {                                         // the partner's record stays reserved: key nc, dropped by the sort
+                if (s1 >= 0) Si.kr[s1] = make_uint2((unsigned)g.nc, 0u);
+                if (s2 >= 0) Se.kr[s2] = make_uint2((unsigned)g.nc, 0u);
                 kind = -1;
             }
             if (kind == 1 && s0 < 0) kind = -1;
             if (kind == -1) { n_drop++; n_coll--; }                                        // no room for the products: the collision is skipped untouched
             if (kind > 0) {
-                neu.a[6][pn] = Wn - We;
+                if (staged) Sn.rec[8 * pn + 6] = Wn - We; else neu.a[6][pn] = Wn - We;
                 ele.a[3][pe] = ve_[0]; ele.a[4][pe] = ve_[1]; ele.a[5][pe] = ve_[2];
                 if (kind == 2) {
                     n_ion++;
-                    write_slot(ion, s1, pos, vn_, Wl);                                     // no half-step rewind (:694-695)
-                    write_slot(ele, s2, pos, vnew, Wl);
+                    write_stage(Si, s1, pos, vn_, Wl, (unsigned)c, made_i);                      // no half-step rewind (:694-695)
+                    write_stage(Se, s2, pos, vnew, Wl, (unsigned)c, made_e);
                 } else {
-                    write_slot(neu, s0, pos, vn_, We);                                     // split-off neutral of the electron's weight
+                    write_stage(Sn, s0, pos, vn_, We, (unsigned)c, made_n);                      // split-off neutral of the electron's weight
                     if (n_extra < MCC_EXTRA) { extra[n_extra++] = s0; np_n++; } else n_capped++;
                 }
             }
         }
+        if (made_n) Sn.made[c] = (unsigned)made_n;
+        if (made_e) Se.made[c] = (unsigned)made_e;
+        if (made_i) Si.made[c] = (unsigned)made_i;
     }
     // block-level reduction of the statistics
     __shared__ u64 sh[7]; __shared__ double sh_max;
@@ -274,21 +292,33 @@ __global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Sto
         atomic_max_pos_double(&wsv[1], sh_max);
     }
 }
-// After the kernel.  (1) W_sigma_v_rel_max <- max sampled value of this step, only if a collision happened (:751-756).  (2) A counter
-// that ran past the capacity (the reservations beyond it failed) goes back to the capacity.  (3) stats[8 + k]: orphans of store k.
-__global__ void k_mcc_finish(double* wsv, u64* stats, SpeciesCounters* c0, u64 cap0, SpeciesCounters* c1, u64 cap1, SpeciesCounters* c2, u64 cap2, const unsigned* orphans) {
+// After the kernel.  (1) W_sigma_v_rel_max <- max sampled value of this step, only if a collision happened (:751-756).  (2) A cursor
+// that ran past its staging area (the reservations beyond it failed) goes back to the capacity.  stats[8 + k]: records staged for store k.
+__global__ void k_mcc_finish(double* wsv, u64* stats, u64 cap0, u64 cap1, u64 cap2) {
     if (stats[1]) wsv[0] = wsv[1];
-    if (c0->n > cap0) c0->n = cap0;
-    if (c1->n > cap1) c1->n = cap1;
-    if (c2->n > cap2) c2->n = cap2;
-    for (int k = 0; k < 3; k++) stats[8 + k] = min(orphans[k * (MCC_ORPHANS + 1)], (unsigned)MCC_ORPHANS);
+    const u64 cap[3] = {cap0, cap1, cap2};
+    for (int k = 0; k < 3; k++) if (stats[8 + k] > cap[k]) stats[8 + k] = cap[k];
 }
-// rare (a product store ran full in the middle of an ionisation): the orphaned slots become the dead list of the compaction (push.cu)
-__global__ void k_mcc_orphans(const unsigned* __restrict__ orphans, SpeciesCounters* ctr, unsigned* __restrict__ dead_list) {
-    const unsigned no = min(orphans[0], (unsigned)MCC_ORPHANS);
-    for (unsigned t = threadIdx.x; t < no; t += blockDim.x) dead_list[t] = orphans[1 + t];
-    if (threadIdx.x == 0) ctr->n_dead = no;
+// Staging index of the r-th record in (cell, creation) order: start[] = exclusive scan of made[] (records of the cells below).
+__global__ void __launch_bounds__(256) k_stage_index(const u64* __restrict__ n_staged, unsigned nc, const uint2* __restrict__ kr, const unsigned* __restrict__ start, unsigned* __restrict__ sorted) {
+    const u64 n = *n_staged;
+    for (u64 e = blockIdx.x * (u64)blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) {
+        const uint2 v = kr[e];
+        if (v.x < nc) sorted[start[v.x] + v.y] = (unsigned)e;
+    }
 }
+// The staged records of one store in (cell, creation) order -> the end of the store.  sorted[r]: staging index of the r-th record,
+// start[nc]: number of records that are kept.  One thread per record: a 64-byte record in, seven coalesced 8-byte columns out.
+__global__ void __launch_bounds__(256) k_stage_commit(Store st, const double* __restrict__ rec, const unsigned* __restrict__ sorted, const unsigned* __restrict__ n_keep) {
+    const u64 n0 = st.ctr->n, m = *n_keep;
+    for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < m; r += (u64)gridDim.x * blockDim.x) {
+        const double4* src = reinterpret_cast<const double4*>(rec + 8 * (u64)sorted[r]);
+        const double4 lo = src[0], hi = src[1];
+        const u64 d = n0 + r;
+        st.a[0][d] = lo.x; st.a[1][d] = lo.y; st.a[2][d] = lo.z; st.a[3][d] = lo.w; st.a[4][d] = hi.x; st.a[5][d] = hi.y; st.a[6][d] = hi.z;
+    }
+}
+__global__ void k_stage_count(SpeciesCounters* ctr, const unsigned* __restrict__ n_keep) { ctr->n += *n_keep; }
 __global__ void k_sigma_eval(MccParams P, int n, const double* __restrict__ E, double* __restrict__ sc, double* __restrict__ si) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) { sc[t] = sigma_coll(P, E[t]); si[t] = sigma_ion(P, E[t]); }
 }
@@ -359,7 +389,6 @@ int picg_mcc_destroy(picg_mcc_t m) {
     if (!m) return PICG_OK;
     if (g_stream) cudaStreamSynchronize(g_stream);
     cudaFree(m->tab_E); cudaFree(m->tab_s); cudaFree(m->wsv); cudaFree(m->stats);
-    cudaFree(m->orphans);
     delete m; return PICG_OK;
 }
 
@@ -408,38 +437,57 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     rc = species_refresh_count(ion); if (rc) return rc;
     size_t n_before[3] = {neu->n_host, ele->n_host, ion->n_host};
     picg_species_s* sp3[3] = {neu, ele, ion};
+    size_t scap[3], scap_max = 0;                               // room = staging capacity of the store in this call
     for (int k = 0; k < 3; k++) {
-        size_t want = sp3[k]->n_host + std::max<size_t>(std::max<size_t>(2 * m->last_appends[k], sp3[k]->n_host / 100), 65536);
-        if (sp3[k]->cap < want) { rc = species_ensure_capacity(sp3[k], want); if (rc) return rc; }
+        scap[k] = std::max<size_t>(std::max<size_t>(2 * m->last_appends[k], sp3[k]->n_host / 100), 65536);
+        if (sp3[k]->cap < sp3[k]->n_host + scap[k]) { rc = species_ensure_capacity(sp3[k], sp3[k]->n_host + scap[k]); if (rc) return rc; }
+        scap_max = std::max(scap_max, scap[k]);
     }
     double zero = 0; CUDA_TRY(cudaMemcpyAsync(m->wsv + 1, &zero, 8, cudaMemcpyHostToDevice, g_stream));
     m->step++;
-    if (!m->orphans) CUDA_TRY(cudaMalloc(&m->orphans, 3 * (MCC_ORPHANS + 1) * 4));
-    for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemsetAsync(m->orphans + k * (MCC_ORPHANS + 1), 0, 4, g_stream));
+    // staging areas in the scratch arena (free here: the list builds above are done with it): records | (cell, rank) pairs | per-cell
+    // tables of the three stores, then the index list of the commit and the work area of the scan
+    const size_t nt = (size_t)g.nc + 1;
+    size_t rec_off[3], kr_off[3], made_off[3], off = 0;
+    for (int k = 0; k < 3; k++) { rec_off[k] = off; off += ((scap[k] * 64 + 255) & ~(size_t)255); }
+    for (int k = 0; k < 3; k++) { kr_off[k] = off; off += ((scap[k] * 8 + 255) & ~(size_t)255); }
+    for (int k = 0; k < 3; k++) { made_off[k] = off; off += ((nt * 4 + 255) & ~(size_t)255); }
+    const size_t sorted_off = off; off += (scap_max * 4 + 255) & ~(size_t)255;
+    const size_t work_off = off; off += counting_sort_words(g) * 4 + 256;
+    rc = ensure_scratch(m->w, off); if (rc) return rc;
+    char* base = (char*)m->w->scratch;
+    Stage S[3];
+    for (int k = 0; k < 3; k++) {
+        S[k].rec = (double*)(base + rec_off[k]); S[k].kr = (uint2*)(base + kr_off[k]); S[k].made = (unsigned*)(base + made_off[k]); S[k].cursor = m->stats + 8 + k; S[k].cap = scap[k];
+        CUDA_TRY(cudaMemsetAsync(S[k].made, 0, nt * 4, g_stream));
+    }
     int grid = std::max(1, std::min(div_up(g.nc, MCC_THREADS), g_sm_count * 16));
-    if (m->fixed_weight) LAUNCH(K_MCC, k_mcc<1>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), m->orphans,
+    if (m->fixed_weight) LAUNCH(K_MCC, k_mcc<1>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), S[0], S[1], S[2],
                                 m->wsv, m->stats, dt, g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
-    else LAUNCH(K_MCC, k_mcc<0>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), m->orphans,
+    else LAUNCH(K_MCC, k_mcc<0>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), S[0], S[1], S[2],
                 m->wsv, m->stats, dt, g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
     CHECK_LAUNCH();
-    LAUNCH(K_MCC_APPEND, k_mcc_finish, 1, 1, 0, m->wsv, m->stats, neu->ctr, (u64)neu->cap, ele->ctr, (u64)ele->cap, ion->ctr, (u64)ion->cap, m->orphans); CHECK_LAUNCH();
+    LAUNCH(K_MCC_APPEND, k_mcc_finish, 1, 1, 0, m->wsv, m->stats, (u64)scap[0], (u64)scap[1], (u64)scap[2]); CHECK_LAUNCH();
     u64 host_stats[16];
     CUDA_TRY(cudaMemcpyAsync(host_stats, m->stats, 128, cudaMemcpyDeviceToHost, g_stream));
-    for (picg_species_s* s : {neu, ele, ion}) { s->n_host_valid = false; s->n_upper = s->cap; }
-    rc = species_refresh_count(neu); if (rc) return rc;          // synchronises: host_stats is valid from here on
+    CUDA_TRY(cudaStreamSynchronize(g_stream));                  // host_stats is valid from here on
+    // the staged products, store by store, in (cell, creation) order behind the store's particles
     for (int k = 0; k < 3; k++) {
-        if (!host_stats[8 + k]) continue;                       // orphaned slots (a partner store ran full): close the holes
+        const size_t staged = (size_t)host_stats[8 + k];
+        if (!staged) continue;
         picg_species_s* sp = sp3[k];
-        rc = ensure_scratch(m->w, compact_scratch_bytes(MCC_ORPHANS)); if (rc) return rc;
-        LAUNCH(K_MCC_APPEND, k_mcc_orphans, 1, 256, 0, m->orphans + k * (MCC_ORPHANS + 1), sp->ctr, (unsigned*)m->w->scratch); CHECK_LAUNCH();
-        const bool fresh = sp->movers_fresh, saved = sp->movers_saved;
-        rc = compact_dead(sp, MCC_ORPHANS); if (rc) return rc;
-        sp->movers_fresh = fresh; sp->movers_saved = saved;      // only slots appended by this call moved: the mover list of the partition stays valid
+        unsigned* sorted = (unsigned*)(base + sorted_off);
+        rc = scan_cell_table(g, S[k].made, (unsigned*)(base + work_off)); if (rc) return rc;          // made[] -> records in the cells below; made[nc] = records kept
+        const int egrid = std::max(1, std::min(div_up(staged, 256), g_sm_count * 8));
+        LAUNCH(K_MCC_APPEND, k_stage_index, egrid, 256, 0, (const u64*)S[k].cursor, (unsigned)g.nc, (const uint2*)S[k].kr, (const unsigned*)S[k].made, sorted); CHECK_LAUNCH();
+        LAUNCH(K_MCC_APPEND, k_stage_commit, egrid, 256, 0, store_of(sp), (const double*)S[k].rec, (const unsigned*)sorted, (const unsigned*)(S[k].made + g.nc)); CHECK_LAUNCH();
+        LAUNCH(K_MCC_APPEND, k_stage_count, 1, 1, 0, sp->ctr, (const unsigned*)(S[k].made + g.nc)); CHECK_LAUNCH();
+        sp->n_host_valid = false; sp->n_upper = std::min(sp->cap, sp->n_host + staged);
     }
     rc = species_refresh_count(neu); if (rc) return rc;
     rc = species_refresh_count(ele); if (rc) return rc;
     rc = species_refresh_count(ion); if (rc) return rc;
-    for (int k = 0; k < 3; k++) m->last_appends[k] = sp3[k]->n_host - n_before[k];
+    for (int k = 0; k < 3; k++) m->last_appends[k] = host_stats[5] ? std::max(sp3[k]->n_host - n_before[k], scap[k]) : sp3[k]->n_host - n_before[k];   // dropped collisions: twice the room next time
     if (host_stats[1]) { neu->sorted_valid = false; neu->lists_valid = false; neu->count_valid = false; ele->sorted_valid = false; ele->lists_valid = false; ele->count_valid = false; ion->sorted_valid = false; ion->lists_valid = false; ion->count_valid = false; }   // :751-754
     if (host_stats[5]) {                                        // grow so that the next call has room, and tell the caller
         for (int k = 0; k < 3; k++) { rc = species_ensure_capacity(sp3[k], sp3[k]->n_host + std::max<size_t>(4 * (size_t)host_stats[5], sp3[k]->n_host / 10)); if (rc) return rc; }

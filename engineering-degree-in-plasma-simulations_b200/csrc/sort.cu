@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(256) k_merge_remap_movers(SpeciesCounters* ctr
 }
 
 namespace picg {
-double g_mover_fraction = 0.10;
-double g_merge_fraction = 0.05;      // a tail above this fraction of the store is merged into the partition (merge_tail)     // above this fraction of movers the store is re-sorted instead of patched
+double g_mover_fraction = 0.15;
+double g_merge_fraction = 0.12;      // a tail above this fraction of the store is merged into the partition (merge_tail)     // above this fraction of movers the store is re-sorted instead of patched
 static uint64_t g_movers_from_deposit = 0, g_mover_scans = 0, g_mover_resorts = 0;
 static bool trace_sort() { static const bool t = getenv("PICG_TRACE_SORT") && atoi(getenv("PICG_TRACE_SORT")) != 0; return t; }
 // Stable LSD radix sort of (keys, vals) pairs; n is read on the device.  Returns the buffers that hold the result.
@@ -410,8 +410,18 @@ static int key_bits_of(const Grid& g) { int bits = 1; while ((1ull << bits) < (u
 
 // Counting sort of (keys, vals) by key in [0, nc): start[nc + 1] (zeroed here) becomes the per-cell offset table, out_vals the values in
 // cell order (each cell's segment ascending), out_keys (optional) their keys.  work: (nc + 1) + 8192 words of scratch.
-static size_t counting_sort_words(const Grid& g) { return (((size_t)g.nc + 1 + 63) & ~(size_t)63) + 8192; }
-static int counting_sort_by_cell(const Grid& g, const u64* n_ptr, size_t n_upper, const unsigned* keys, const unsigned* vals, unsigned* start, unsigned* out_vals,
+size_t counting_sort_words(const Grid& g) { return (((size_t)g.nc + 1 + 63) & ~(size_t)63) + 8192; }
+// Exclusive scan in place of a per-cell table of nc + 1 entries (the last one, zero on entry, becomes the total).  work: 8192 words.
+int scan_cell_table(const Grid& g, unsigned* table, unsigned* work) {
+    const size_t nt = (size_t)g.nc + 1;
+    const int nb = div_up(nt, (size_t)SCAN_T * SCAN_I);
+    if (nb > 8192) return set_error(PICG_ERR_ARG, "scan_cell_table: more than 2^25 cells are not supported");
+    LAUNCH(K_SORT_SCAN, k_scan_reduce, nb, SCAN_T, 0, table, nt, work); CHECK_LAUNCH();
+    LAUNCH(K_SORT_SCAN, k_scan_sums, 1, 1024, 0, work, nb); CHECK_LAUNCH();
+    LAUNCH(K_SORT_SCAN, k_scan_apply, nb, SCAN_T, 0, table, nt, work, (unsigned*)nullptr); CHECK_LAUNCH();
+    return PICG_OK;
+}
+int counting_sort_by_cell(const Grid& g, const u64* n_ptr, size_t n_upper, const unsigned* keys, const unsigned* vals, unsigned* start, unsigned* out_vals,
                                  unsigned* out_keys, unsigned* work, bool ordered) {
     const size_t nt = (size_t)g.nc + 1;
     unsigned* cursor = work; unsigned* sums = work + ((nt + 63) & ~(size_t)63);

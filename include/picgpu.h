@@ -157,7 +157,7 @@ PICG_API int picg_species_count_per_cell(picg_species_t s);
  * full sort whenever the order is stale (the reference re-sorts every step). */
 PICG_API int picg_set_mover_fraction(double f);
 /* Particles appended since the last sort (MC products, sources, re-emitted neutrals) form a tail behind the cell partition.  When the
- * tail exceeds the fraction `f` of the store (default 0.05) it is merged into the partition: only the tail is sorted, the partition is
+ * tail exceeds the fraction `f` of the store (default 0.12) it is merged into the partition: only the tail is sorted, the partition is
  * shifted to open the gaps (a streaming pass; replaces the full re-sort the reference does every step, Species.cpp:905-929).  0: never. */
 PICG_API int picg_set_merge_fraction(double f);
 PICG_API int picg_tail_merge_count(uint64_t* merges);
