@@ -385,11 +385,12 @@ def run_ours(args):
                       pg.mover_stats(), counts.get("mcc"), json.dumps(delta)), file=sys.stderr)
             if e2e:                                           # what the reference loop reads every step: counts + diagnostics + rho
                 t0 = time.perf_counter()
+                pg._chk(pg.lib().picg_world_download_begin(w.h, pg.F_RHO, rho_host.ctypes.data_as(pg.C.POINTER(pg.C.c_double))))   # rho travels while the diagnostics run
                 for sp in order:
                     sp.diagnostics()
                 t0 = stamp("diagnostics", t0)
-                pg._chk(pg.lib().picg_world_download(w.h, pg.F_RHO, rho_host.ctypes.data_as(pg.C.POINTER(pg.C.c_double))))
-                stamp("rho download", t0)
+                pg._chk(pg.lib().picg_world_download_end(w.h))
+                stamp("rho download (rest)", t0)
                 psteps += n_now
             step_events[k].record(stream)
         ev1.record(stream)

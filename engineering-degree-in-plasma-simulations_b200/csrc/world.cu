@@ -204,6 +204,32 @@ int picg_world_download(picg_world_t w, int field, double* host) {
     return PICG_OK;
 }
 
+// Asynchronous form of the download for callers that have other device work to queue meanwhile (the per-step read-back of rho next
+// to the diagnostics pass): _begin orders the copy after everything queued so far and runs it on a copy stream, _end waits for it.
+// Work that overwrites the field must not be queued before _end.  `host` should be page-locked; one download in flight.
+static cudaStream_t g_copy_stream = nullptr; static cudaEvent_t g_copy_ready = nullptr, g_copy_done = nullptr;
+int picg_world_download_begin(picg_world_t w, int field, double* host) {
+    REQUIRE_DEVICE();
+    REQUIRE_ARG(w && host, "picg_world_download_begin: null argument");
+    void* p; size_t bytes; bool is_int;
+    int rc = world_field(w, field, &p, &bytes, &is_int); if (rc) return rc;
+    REQUIRE_ARG(!is_int, "picg_world_download_begin: integer fields go through picg_world_download");
+    if (!g_copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&g_copy_ready, cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&g_copy_done, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(g_copy_ready, g_stream));
+    CUDA_TRY(cudaStreamWaitEvent(g_copy_stream, g_copy_ready, 0));
+    CUDA_TRY(cudaMemcpyAsync(host, p, bytes, cudaMemcpyDeviceToHost, g_copy_stream));
+    CUDA_TRY(cudaEventRecord(g_copy_done, g_copy_stream));
+    return PICG_OK;
+}
+int picg_world_download_end(picg_world_t w) {
+    REQUIRE_DEVICE(); REQUIRE_ARG(w, "picg_world_download_end: null world");
+    if (g_copy_done) CUDA_TRY(cudaEventSynchronize(g_copy_done));
+    return PICG_OK;
+}
+
 int picg_world_upload(picg_world_t w, int field, const double* host) {
     REQUIRE_DEVICE();
     REQUIRE_ARG(w && host, "picg_world_upload: null argument");

@@ -11,6 +11,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpicgpu.so")
+if os.environ.get("PICGPU_SO"):                 # A/B builds of the same library (profiles/scripts): never a different implementation
+    LIB_PATH = os.path.abspath(os.environ["PICGPU_SO"])
 
 
 class PicgError(RuntimeError):

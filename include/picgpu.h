@@ -94,6 +94,11 @@ typedef enum {
 } picg_world_field;
 /* public Field members World::{phi,rho,node_vol,ef,object_id,node_type}  World.h:51-57 */
 PICG_API int picg_world_download(picg_world_t w, int field, double* host);
+/* the same read-back split in two (replaces nothing in the reference, whose fields live in host memory): _begin queues the copy behind the
+ * work submitted so far on a copy stream, _end waits for it; device work queued in between runs alongside the transfer and must not
+ * overwrite the field.  `host` should be page-locked.  Real-valued fields only; one download in flight. */
+PICG_API int picg_world_download_begin(picg_world_t w, int field, double* host);
+PICG_API int picg_world_download_end(picg_world_t w);
 PICG_API int picg_world_upload(picg_world_t w, int field, const double* host);
 /* World::computeChargeDensity  World.cpp:193-200 : rho = sum_s charge_s * den_s over charged species */
 PICG_API int picg_world_charge_density(picg_world_t w, const picg_species_t* species, int n);
