@@ -55,6 +55,7 @@ struct picg_world_s {
     int *object_id = nullptr, *node_type = nullptr;
     // scratch arena shared by sort / compaction (never live at the same time)
     void* scratch = nullptr; size_t scratch_bytes = 0;
+    unsigned* cbm = nullptr; size_t cbm_words = 0;   // compaction bitmap: one bit per store slot, all zero between compactions (push.cu)
     double* reduce_buf = nullptr;      // small device buffer for reductions
     double* reduce_host = nullptr;     // pinned mirror
 };

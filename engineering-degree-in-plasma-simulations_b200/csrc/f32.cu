@@ -36,10 +36,6 @@ struct picg_species32_s {
     int S = 0; bool S_set = false;
 };
 
-__global__ void k_compact_zero(const SpeciesCounters* ctr, unsigned char* __restrict__ tailflag);                                   // push.cu
-__global__ void k_compact_mark(const SpeciesCounters* ctr, const unsigned* __restrict__ dead_list, unsigned char* __restrict__ tailflag);
-__global__ void k_compact_collect(SpeciesCounters* ctr, const unsigned* __restrict__ dead_list, const unsigned char* __restrict__ tailflag,
-                                  unsigned* __restrict__ hole, unsigned* __restrict__ surv);
 __global__ void k_compact_finish(SpeciesCounters* ctr);
 __global__ void k_finalize_den(int u_begin, int u_end, const i64* __restrict__ fixed, const double* __restrict__ vol, double inv_scale, double* __restrict__ den, SpeciesCounters* ctr);
 __global__ void k_reset_den_stats(SpeciesCounters* ctr);
@@ -177,10 +173,10 @@ __global__ void __launch_bounds__(256, 2) k_push32(Grid g, Push32Args A) {
         }
     }
 }
-__global__ void k_compact_move32(const SpeciesCounters* ctr, Arr32 a, const unsigned* __restrict__ hole, const unsigned* __restrict__ surv) {
-    const u64 nh = ctr->n_hole;
+__global__ void k_compact_move32(const SpeciesCounters* ctr, Arr32 a, const unsigned* __restrict__ D) {      // plan: push.cu / push.cuh
+    const u64 nh = ctr->n_hole, nd = ctr->n_dead, n_alive = ctr->n - nd;
     for (u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x; t < nh; t += (u64)gridDim.x * blockDim.x) {
-        const unsigned d = hole[t], f = surv[t];
+        const unsigned d = D[t], f = compact_survivor(D, nh, nd, n_alive, t);
 #pragma unroll
         for (int c = 0; c < 7; c++) a.f[c][d] = a.f[c][f];
         a.cell[d] = a.cell[f];
@@ -308,12 +304,10 @@ int ensure_capacity32(picg_species32_s* s, size_t cap) {
     return ensure_scratch(s->w, std::max(newcap * 16 + (1u << 20), compact_scratch_bytes(newcap) + 64));
 }
 int compact_dead32(picg_species32_s* s, size_t cap) {
-    unsigned* dead_list = (unsigned*)s->w->scratch; unsigned* hole = dead_list + cap; unsigned* surv = hole + cap; unsigned char* tailflag = (unsigned char*)(surv + cap);
+    unsigned* D = nullptr;
+    int rc = compact_plan(s->w, s->ctr, cap, s->cap, &D); if (rc) return rc;
     int grid = std::max(1, std::min(div_up(std::max<size_t>(cap / 16, 1), 256), g_sm_count * 4));
-    LAUNCH(K_COMPACT, k_compact_zero, grid, 256, 0, s->ctr, tailflag); CHECK_LAUNCH();
-    LAUNCH(K_COMPACT, k_compact_mark, grid, 256, 0, s->ctr, dead_list, tailflag); CHECK_LAUNCH();
-    LAUNCH(K_COMPACT, k_compact_collect, grid, 256, 0, s->ctr, dead_list, tailflag, hole, surv); CHECK_LAUNCH();
-    LAUNCH(K_COMPACT, k_compact_move32, grid, 256, 0, s->ctr, arr_of(s), hole, surv); CHECK_LAUNCH();
+    LAUNCH(K_COMPACT, k_compact_move32, grid, 256, 0, s->ctr, arr_of(s), D); CHECK_LAUNCH();
     LAUNCH(K_COMPACT, k_compact_finish, 1, 1, 0, s->ctr); CHECK_LAUNCH();
     s->n_host_valid = false; s->sorted_valid = false;
     return PICG_OK;

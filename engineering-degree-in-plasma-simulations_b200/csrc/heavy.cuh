@@ -4,12 +4,14 @@
 #include "common.cuh"
 #include "samplers.cuh"
 
-struct Emit { double* a[7]; SpeciesCounters* ctr; u64 cap; double mpw0, q_over_m; };
+// write == 0: emit_particle only counts what it would append (made); write == 1: it writes to slot base + made.  The slots of an impacting
+// particle are fixed by a prefix sum over the impacts in ascending slot order (k_heavy_impacts, step.cu): no cursor, no dependence on timing.
+struct Emit { double* a[7]; SpeciesCounters* ctr; u64 cap; double mpw0, q_over_m; int write; u64 base; unsigned made; };
 struct HeavyArgs { Emit neutrals, spherium; int sputtering; double charge, mass, half_world_dt; uint64_t seed; uint32_t stream, call; };
 
 #ifdef __CUDACC__
 // Species::addParticle(pos, vel) for one particle created on a surface (Species.cpp:420-437)
-static __device__ __noinline__ void emit_particle(const Grid& g, const Emit& e, const double* __restrict__ ef, double half_dt, const double pos[3], const double v[3]) {
+static __device__ __noinline__ void emit_particle(const Grid& g, Emit& e, const double* __restrict__ ef, double half_dt, const double pos[3], const double v[3]) {
     if (isnan(pos[0]) || isnan(pos[1]) || isnan(pos[2]) || isnan(v[0]) || isnan(v[1]) || isnan(v[2])) return;
     if (!in_bounds(g, pos[0], pos[1], pos[2]) || in_object(g, pos[0], pos[1], pos[2])) return;
     double ex, ey, ez;
@@ -17,14 +19,14 @@ static __device__ __noinline__ void emit_particle(const Grid& g, const Emit& e, 
     double u = __dsub_rn(v[0], __dmul_rn(__dmul_rn(ex, e.q_over_m), half_dt));
     double vv = __dsub_rn(v[1], __dmul_rn(__dmul_rn(ey, e.q_over_m), half_dt));
     double w = __dsub_rn(v[2], __dmul_rn(__dmul_rn(ez, e.q_over_m), half_dt));
-    u64 dst = atomicAdd(&e.ctr->n, 1ull);
-    if (dst >= e.cap) { atomicAdd(&e.ctr->overflow, 1ull); return; }
+    const u64 dst = e.base + e.made++;
+    if (!e.write || dst >= e.cap) return;                                   // counting pass / store full (the counter is clamped and the overflow recorded after the kernel)
     e.a[0][dst] = pos[0]; e.a[1][dst] = pos[1]; e.a[2][dst] = pos[2]; e.a[3][dst] = u; e.a[4][dst] = vv; e.a[5][dst] = w; e.a[6][dst] = e.mpw0;
 }
 
 // The part of the heavy push that follows an impact (Species.cpp:213-238): rare, kept out of line.
 // Returns true when the particle is absorbed; otherwise x, v, t_rem are updated for the next sub-move.
-static __device__ __noinline__ bool surface_interaction(const Grid& g, const HeavyArgs& h, const double* __restrict__ ef, PhiloxStream& r, int obj,
+static __device__ __noinline__ bool surface_interaction(const Grid& g, HeavyArgs& h, const double* __restrict__ ef, PhiloxStream& r, int obj,
                                                  const double old[3], double x[3], double v[3], double mpw, double& t_rem) {
     double tp, hit[3], nrm[3];
     const ObjShape& o = g.obj[obj - 1];
@@ -51,7 +53,7 @@ static __device__ __noinline__ bool surface_interaction(const Grid& g, const Hea
 // State of a heavy particle whose first sub-move ended inside an object; heavy_after_impact runs the rest of the
 // reference's bounce loop (Species.cpp:194-249: up to 20 sub-moves in total).  Returns true when the particle is removed.
 struct HeavyState { double ox, oy, oz, x, y, z, u, v, w; };
-static __device__ __noinline__ bool heavy_after_impact(const Grid& g, const HeavyArgs& h, const double* __restrict__ ef, double dt, unsigned long long p,
+static __device__ __noinline__ bool heavy_after_impact(const Grid& g, HeavyArgs& h, const double* __restrict__ ef, double dt, unsigned long long p,
                                                        int obj, double mpw, HeavyState& st) {
     PhiloxStream rs; rs.init(h.seed, h.stream, p, h.call);
     double t_rem = 1; int n_b = 1;
@@ -73,6 +75,6 @@ static __device__ __noinline__ bool heavy_after_impact(const Grid& g, const Heav
 
 static inline Emit emit_of(picg_species_s* t) {
     Emit e; for (int c = 0; c < 7; c++) e.a[c] = t->a[c];
-    e.ctr = t->ctr; e.cap = t->cap; e.mpw0 = t->mpw0; e.q_over_m = t->charge / t->mass;
+    e.ctr = t->ctr; e.cap = t->cap; e.mpw0 = t->mpw0; e.q_over_m = t->charge / t->mass; e.write = 0; e.base = 0; e.made = 0;
     return e;
 }

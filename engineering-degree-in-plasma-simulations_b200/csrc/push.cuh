@@ -6,11 +6,21 @@ struct PushArrays { double *x, *y, *z, *u, *v, *w; };
 
 namespace picg {
 int compact_dead(picg_species_s* s, size_t cap);
+int compact_plan(picg_world_s* w, SpeciesCounters* ctr, size_t cap, size_t store_cap, unsigned** D_out);
+int sort_slot_list(picg_world_s* w, const u64* count_ptr, const u64* n_ptr, size_t list_cap, size_t store_cap, const unsigned* list, unsigned* out, unsigned* counts);
 size_t compact_scratch_bytes(size_t cap);
 int push_grid(size_t n_upper);
 }
 
 #ifdef __CUDACC__
+// Compaction plan (push.cu): D holds the dead slots in ascending order, the first h of them below n_alive; the tail [n_alive, n_alive + nd)
+// holds nd - h dead slots (D[h..nd)) and h survivors.  Slot of the t-th survivor (0 <= t < h): t plus the number of dead tail slots
+// before it, i.e. i - h for the first i in [h, nd] with (D[i] - n_alive) - (i - h) > t  (survivors ahead of D[i]; nd: all of them).
+__device__ __forceinline__ unsigned compact_survivor(const unsigned* __restrict__ D, u64 h, u64 nd, u64 n_alive, u64 t) {
+    u64 lo = h, hi = nd;
+    while (lo < hi) { const u64 mid = (lo + hi) >> 1; if (((u64)D[mid] - n_alive) - (mid - h) > t) hi = mid; else lo = mid + 1; }
+    return (unsigned)(n_alive + t + (lo - h));
+}
 // Species::advanceElectronsSerial body (Species.cpp:368-373):
 //   lc = XtoL(pos); E = ef.gather(lc); vel += E*(dt*charge/mass); pos += vel*dt
 // qm_dt is the scalar dt*charge/mass formed on the host exactly as the reference forms it.

@@ -28,44 +28,76 @@ __global__ void __launch_bounds__(256) k_soa_to_aos(size_t n, SoA s, size_t base
 }
 
 // Species::addParticle (Species.cpp:420-434): reject NaN pos/vel, out of bounds, in object; gather E at pos;
-// vel -= charge/mass * E * (0.5*world.dt); append.  Appends through a warp-aggregated atomic cursor.
-__global__ void __launch_bounds__(256) k_add_particles(Grid g, size_t n, const double* __restrict__ aos, SoA s, size_t cap,
-                                                       SpeciesCounters* ctr, const double* __restrict__ ef, double q_over_m, double half_dt) {
-    for (size_t p0 = blockIdx.x * (size_t)blockDim.x; p0 < n; p0 += (size_t)gridDim.x * blockDim.x) {
-        size_t p = p0 + threadIdx.x;
-        bool keep = false;
-        double x = 0, y = 0, z = 0, u = 0, v = 0, w = 0, m = 0;
-        if (p < n) {
-            x = aos[p * 7]; y = aos[p * 7 + 1]; z = aos[p * 7 + 2];
-            u = aos[p * 7 + 3]; v = aos[p * 7 + 4]; w = aos[p * 7 + 5]; m = aos[p * 7 + 6];
-            keep = !(isnan(x) || isnan(y) || isnan(z) || isnan(u) || isnan(v) || isnan(w));
-            keep = keep && in_bounds(g, x, y, z) && !in_object(g, x, y, z);
-            if (keep) {
+// vel -= charge/mass * E * (0.5*world.dt); append.  The accepted candidates are appended IN CANDIDATE ORDER: block b owns a contiguous
+// range of candidates, k_add_count counts what each range keeps, one block scans the 1024 counts, k_add_write places every accepted
+// candidate at n + (kept in the blocks before) + (kept before it in its block).  No atomics: the same candidates give the same store.
+#define ADD_BLOCKS 1024
+__device__ __forceinline__ bool add_keep(const Grid& g, const double* __restrict__ a) {
+    const double x = a[0], y = a[1], z = a[2];
+    bool keep = !(isnan(x) || isnan(y) || isnan(z) || isnan(a[3]) || isnan(a[4]) || isnan(a[5]));
+    return keep && in_bounds(g, x, y, z) && !in_object(g, x, y, z);
+}
+__device__ __forceinline__ void add_range(size_t n, size_t& p0, size_t& p1) {      // candidates of block blockIdx.x (multiples of the block size)
+    const size_t per = ((n + ADD_BLOCKS - 1) / ADD_BLOCKS + 255) & ~(size_t)255;
+    p0 = min(n, (size_t)blockIdx.x * per); p1 = min(n, p0 + per);
+}
+__global__ void __launch_bounds__(256) k_add_count(Grid g, size_t n, const double* __restrict__ aos, unsigned* __restrict__ counts) {
+    __shared__ unsigned ws[8];
+    size_t p0, p1; add_range(n, p0, p1);
+    unsigned c = 0;
+    for (size_t p = p0 + threadIdx.x; p < p1; p += 256) c += add_keep(g, aos + p * 7) ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned t = 0; for (int q = 0; q < 8; q++) t += ws[q]; counts[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(ADD_BLOCKS) k_add_scan(unsigned* __restrict__ counts) {      // exclusive scan in place, total in counts[ADD_BLOCKS]
+    __shared__ unsigned ws[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned v = counts[threadIdx.x]; unsigned x = v;
+    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) ws[warp] = x;
+    __syncthreads();
+    if (warp == 0) { unsigned wv = ws[lane], wx = wv; for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, wx, o); if (lane >= o) wx += y; } ws[lane] = wx - wv; }
+    __syncthreads();
+    counts[threadIdx.x] = ws[warp] + x - v;
+    if (threadIdx.x == ADD_BLOCKS - 1) counts[ADD_BLOCKS] = ws[warp] + x;
+}
+__global__ void __launch_bounds__(256) k_add_write(Grid g, size_t n, const double* __restrict__ aos, SoA s, size_t cap, const SpeciesCounters* ctr,
+                                                   const unsigned* __restrict__ offsets, const double* __restrict__ ef, double q_over_m, double half_dt) {
+    __shared__ unsigned ws[8];
+    size_t p0, p1; add_range(n, p0, p1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 base = ctr->n + offsets[blockIdx.x];
+    for (size_t q0 = p0; q0 < p1; q0 += 256) {
+        const size_t p = q0 + threadIdx.x;
+        const bool keep = p < p1 && add_keep(g, aos + p * 7);
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) ws[warp] = __popc(mask);
+        __syncthreads();
+        unsigned before = 0, total = 0;
+        for (int q = 0; q < 8; q++) { const unsigned t = ws[q]; if (q < warp) before += t; total += t; }
+        if (keep) {
+            const u64 dst = base + before + __popc(mask & ((1u << lane) - 1));
+            if (dst < cap) {
+                const double x = aos[p * 7], y = aos[p * 7 + 1], z = aos[p * 7 + 2];
+                double u = aos[p * 7 + 3], v = aos[p * 7 + 4], w = aos[p * 7 + 5];
                 double ex, ey, ez;
                 gather_ef(g, ef, x_to_l(x, g.x0[0], g.inv_dx[0]), x_to_l(y, g.x0[1], g.inv_dx[1]), x_to_l(z, g.x0[2], g.inv_dx[2]), ex, ey, ez);
                 // vel -= charge/mass*ef_part*(0.5*dt):  ((q/m)*E)*(0.5 dt)   (scalar*Vec3 then Vec3*scalar)
                 u = __dsub_rn(u, __dmul_rn(__dmul_rn(ex, q_over_m), half_dt));
                 v = __dsub_rn(v, __dmul_rn(__dmul_rn(ey, q_over_m), half_dt));
                 w = __dsub_rn(w, __dmul_rn(__dmul_rn(ez, q_over_m), half_dt));
+                s.a[0][dst] = x; s.a[1][dst] = y; s.a[2][dst] = z; s.a[3][dst] = u; s.a[4][dst] = v; s.a[5][dst] = w; s.a[6][dst] = aos[p * 7 + 6];
             }
         }
-        unsigned mask = __ballot_sync(0xffffffffu, keep);
-        int lane = threadIdx.x & 31;
-        u64 base = 0;
-        if (mask) {
-            int leader = __ffs(mask) - 1;
-            if (lane == leader) base = atomicAdd(&ctr->n, (u64)__popc(mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
-        }
-        if (keep) {
-            u64 dst = base + __popc(mask & ((1u << lane) - 1));
-            if (dst < cap) {
-                s.a[0][dst] = x; s.a[1][dst] = y; s.a[2][dst] = z; s.a[3][dst] = u; s.a[4][dst] = v; s.a[5][dst] = w; s.a[6][dst] = m;
-            } else {
-                atomicAdd(&ctr->overflow, 1ull);
-            }
-        }
+        base += total;
+        __syncthreads();
     }
+}
+__global__ void k_add_finish(SpeciesCounters* ctr, const unsigned* __restrict__ counts, u64 cap) {
+    const u64 want = ctr->n + counts[ADD_BLOCKS];
+    if (want > cap) { ctr->overflow += want - cap; ctr->n = cap; } else ctr->n = want;
 }
 __global__ void k_clamp_count(SpeciesCounters* ctr, u64 cap) { if (ctr->n > cap) ctr->n = cap; }
 
@@ -154,12 +186,18 @@ int species_ensure_capacity(picg_species_s* s, size_t cap) {
 static SoA soa_of(picg_species_s* s) { SoA r; for (int c = 0; c < 7; c++) r.a[c] = s->a[c]; return r; }
 
 namespace picg {
+static int add_candidates(picg_species_s* s, size_t n, const double* d_aos, double q_over_m, double half_dt) {
+    unsigned* counts = (unsigned*)s->w->reduce_buf;              // ADD_BLOCKS + 1 words
+    LAUNCH(K_ADD_PARTICLES, k_add_count, ADD_BLOCKS, 256, 0, s->w->g, n, d_aos, counts); CHECK_LAUNCH();
+    LAUNCH(K_ADD_PARTICLES, k_add_scan, 1, ADD_BLOCKS, 0, counts); CHECK_LAUNCH();
+    LAUNCH(K_ADD_PARTICLES, k_add_write, ADD_BLOCKS, 256, 0, s->w->g, n, d_aos, soa_of(s), s->cap, (const SpeciesCounters*)s->ctr, (const unsigned*)counts, s->w->ef, q_over_m, half_dt); CHECK_LAUNCH();
+    LAUNCH(K_ADD_PARTICLES, k_add_finish, 1, 1, 0, s->ctr, (const unsigned*)counts, (u64)s->cap); CHECK_LAUNCH();
+    return PICG_OK;
+}
 // addParticle for n candidates already staged on the device (AoS).  Capacity must have been ensured.
 int species_add_staged(picg_species_s* s, size_t n, const double* d_aos) {
     double q_over_m = s->charge / s->mass, half_dt = 0.5 * s->w->dt;
-    LAUNCH(K_ADD_PARTICLES, k_add_particles, std::max(1, std::min(div_up(n, 256), g_sm_count * 8)), 256, 0, s->w->g, n, d_aos,
-           soa_of(s), s->cap, s->ctr, s->w->ef, q_over_m, half_dt);
-    CHECK_LAUNCH();
+    int rc = add_candidates(s, n, d_aos, q_over_m, half_dt); if (rc) return rc;
     s->n_host_valid = false; s->n_upper = std::min(s->cap, s->n_upper + n); s->sorted_valid = false; s->lists_valid = false; s->count_valid = false;
     return PICG_OK;
 }
@@ -292,9 +330,7 @@ int picg_species_add_particles(picg_species_t s, size_t n, const double* aos7, s
     for (size_t off = 0; off < n; off += kChunk) {
         size_t m = std::min(kChunk, n - off);
         CUDA_TRY(cudaMemcpyAsync(s->w->scratch, aos7 + off * 7, m * 56, cudaMemcpyHostToDevice, g_stream));
-        LAUNCH(K_ADD_PARTICLES, k_add_particles, std::min(div_up(m, 256), g_sm_count * 8), 256, 0, s->w->g, m, (const double*)s->w->scratch,
-               soa_of(s), s->cap, s->ctr, s->w->ef, q_over_m, half_dt);
-        CHECK_LAUNCH();
+        rc = add_candidates(s, m, (const double*)s->w->scratch, q_over_m, half_dt); if (rc) return rc;
         CUDA_TRY(cudaStreamSynchronize(g_stream));
     }
     s->n_host_valid = false; s->n_upper = before + n; s->sorted_valid = false; s->lists_valid = false; s->count_valid = false;

@@ -189,27 +189,86 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
 // Second pass of the heavy push: the (few) particles whose first sub-move ended inside an object.  Each is re-done from
 // its untouched state: kick, first sub-move, then the reference's bounce loop (surface hit, diffuse re-emission of
 // neutrals, neutralisation of ions with injection of neutrals / sputtered material), Species.cpp:194-249.
+// The impact list arrives sorted by slot (sort_slot_list).  Ions emit particles into other stores; where they land must not depend
+// on which thread is first at a cursor, so a block takes 128 consecutive impacts, runs their bounce loops ONCE WITHOUT WRITING to count
+// what each emits, gets the number emitted by all earlier impacts from a chain through global memory (blocks take tickets in starting
+// order and pass the running totals on in ticket order), and runs the loops again, writing every emitted particle to its fixed slot.
+struct EmitChain { unsigned long long ticket, turn, run_n, run_s; };
+#define IMPACT_THREADS 128
+__device__ __forceinline__ void block_exclusive_scan2(unsigned a, unsigned b, unsigned* sh /* 2 x 4 + 2 */, unsigned& ea, unsigned& eb, unsigned& ta, unsigned& tb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned xa = a, xb = b;
+    for (int o = 1; o < 32; o <<= 1) { unsigned ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o); if (lane >= o) { xa += ya; xb += yb; } }
+    if (lane == 31) { sh[warp] = xa; sh[4 + warp] = xb; }
+    __syncthreads();
+    unsigned ba = 0, bb = 0; ta = 0; tb = 0;
+    for (int q = 0; q < IMPACT_THREADS / 32; q++) { if (q < warp) { ba += sh[q]; bb += sh[4 + q]; } ta += sh[q]; tb += sh[4 + q]; }
+    ea = ba + xa - a; eb = bb + xb - b;
+    __syncthreads();
+}
 template <bool DEPOSIT, bool COUNT>
-__global__ void __launch_bounds__(128) k_heavy_impacts(Grid g, StepArgs A, HeavyArgs H) {
+__global__ void __launch_bounds__(IMPACT_THREADS) k_heavy_impacts(Grid g, StepArgs A, HeavyArgs H, EmitChain* chain) {
+    __shared__ unsigned sh_scan[10]; __shared__ unsigned long long sh_v, sh_base[2];
     const u64 n_imp = A.ctr->n_impact;
-    for (u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x; t < n_imp; t += (u64)gridDim.x * blockDim.x) {
-        const u64 p = A.impact_list[t];
-        double x = A.a[0][p], y = A.a[1][p], z = A.a[2][p], u = A.a[3][p], v = A.a[4][p], w = A.a[5][p], m = A.a[6][p];
-        double ex, ey, ez;
-        gather_ef(g, A.ef, x_to_l(x, g.x0[0], g.inv_dx[0]), x_to_l(y, g.x0[1], g.inv_dx[1]), x_to_l(z, g.x0[2], g.inv_dx[2]), ex, ey, ez);
-        u = __dadd_rn(u, __dmul_rn(ex, A.qm_dt)); v = __dadd_rn(v, __dmul_rn(ey, A.qm_dt)); w = __dadd_rn(w, __dmul_rn(ez, A.qm_dt));
-        HeavyState st = {x, y, z, __dadd_rn(x, __dmul_rn(u, A.dt)), __dadd_rn(y, __dmul_rn(v, A.dt)), __dadd_rn(z, __dmul_rn(w, A.dt)), u, v, w};
-        int obj = in_object(g, st.x, st.y, st.z);
-        bool gone = heavy_after_impact(g, H, A.ef, A.dt, p, obj, m, st);
-        if (gone) { A.dead_list[atomicAdd(&A.ctr->n_dead, 1ull)] = (unsigned)p; continue; }
-        A.a[0][p] = st.x; A.a[1][p] = st.y; A.a[2][p] = st.z; A.a[3][p] = st.u; A.a[4][p] = st.v; A.a[5][p] = st.w;
-        if (DEPOSIT || COUNT) {
-            int ci, cj, ck; i64 q[8];
-            scatter_weights_fixed(g, x_to_l(st.x, g.x0[0], g.inv_dx[0]), x_to_l(st.y, g.x0[1], g.inv_dx[1]), x_to_l(st.z, g.x0[2], g.inv_dx[2]), m, A.scale, ci, cj, ck, q);
-            if (DEPOSIT) { for (int c = 0; c < 8; c++) if (q[c]) atomicAdd(&A.den_fixed[corner_node(g, ci, cj, ck, c)], (u64)q[c]); }
-            if (COUNT) atomicAdd(&A.macro_count[cell_of(g, ci, cj, ck)], 1.0);
+    const bool emits = H.charge != 0;                                   // neutrals only bounce
+    const u64 n0_n = emits ? H.neutrals.ctr->n : 0, n0_s = emits ? H.spherium.ctr->n : 0;      // nobody moves these counters while the kernel runs
+    for (;;) {
+        if (threadIdx.x == 0) sh_v = atomicAdd(&chain->ticket, 1ull);
+        __syncthreads();
+        const u64 vb = sh_v;
+        if (vb * IMPACT_THREADS >= n_imp) break;
+        const u64 t = vb * IMPACT_THREADS + threadIdx.x;
+        const bool active = t < n_imp;
+        const u64 p = active ? A.impact_list[t] : 0;
+        double x = 0, y = 0, z = 0, u = 0, v = 0, w = 0, m = 0; int obj = 0;
+        HeavyState st0 = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (active) {
+            x = A.a[0][p]; y = A.a[1][p]; z = A.a[2][p]; u = A.a[3][p]; v = A.a[4][p]; w = A.a[5][p]; m = A.a[6][p];
+            double ex, ey, ez;
+            gather_ef(g, A.ef, x_to_l(x, g.x0[0], g.inv_dx[0]), x_to_l(y, g.x0[1], g.inv_dx[1]), x_to_l(z, g.x0[2], g.inv_dx[2]), ex, ey, ez);
+            u = __dadd_rn(u, __dmul_rn(ex, A.qm_dt)); v = __dadd_rn(v, __dmul_rn(ey, A.qm_dt)); w = __dadd_rn(w, __dmul_rn(ez, A.qm_dt));
+            HeavyState s0 = {x, y, z, __dadd_rn(x, __dmul_rn(u, A.dt)), __dadd_rn(y, __dmul_rn(v, A.dt)), __dadd_rn(z, __dmul_rn(w, A.dt)), u, v, w};
+            st0 = s0;
+            obj = in_object(g, st0.x, st0.y, st0.z);
         }
+        HeavyArgs Hl = H;                                               // this thread's copy: emit_particle counts / numbers its particles in it
+        if (emits) {
+            if (active) { HeavyState st = st0; heavy_after_impact(g, Hl, A.ef, A.dt, p, obj, m, st); }      // counting pass: nothing is written
+            unsigned en, es, tn, ts;
+            block_exclusive_scan2(Hl.neutrals.made, Hl.spherium.made, sh_scan, en, es, tn, ts);
+            if (threadIdx.x == 0) {
+                while (atomicAdd(&chain->turn, 0ull) != vb) { }
+                const unsigned long long rn = atomicAdd(&chain->run_n, (unsigned long long)tn), rs = atomicAdd(&chain->run_s, (unsigned long long)ts);
+                __threadfence();
+                atomicExch(&chain->turn, vb + 1);
+                sh_base[0] = rn; sh_base[1] = rs;
+            }
+            __syncthreads();
+            Hl.neutrals.write = 1; Hl.neutrals.made = 0; Hl.neutrals.base = n0_n + sh_base[0] + en;
+            Hl.spherium.write = 1; Hl.spherium.made = 0; Hl.spherium.base = n0_s + sh_base[1] + es;
+        }
+        if (active) {
+            HeavyState st = st0;
+            bool gone = heavy_after_impact(g, Hl, A.ef, A.dt, p, obj, m, st);
+            if (gone) A.dead_list[atomicAdd(&A.ctr->n_dead, 1ull)] = (unsigned)p;
+            else {
+                A.a[0][p] = st.x; A.a[1][p] = st.y; A.a[2][p] = st.z; A.a[3][p] = st.u; A.a[4][p] = st.v; A.a[5][p] = st.w;
+                if (DEPOSIT || COUNT) {
+                    int ci, cj, ck; i64 q[8];
+                    scatter_weights_fixed(g, x_to_l(st.x, g.x0[0], g.inv_dx[0]), x_to_l(st.y, g.x0[1], g.inv_dx[1]), x_to_l(st.z, g.x0[2], g.inv_dx[2]), m, A.scale, ci, cj, ck, q);
+                    if (DEPOSIT) { for (int c = 0; c < 8; c++) if (q[c]) atomicAdd(&A.den_fixed[corner_node(g, ci, cj, ck, c)], (u64)q[c]); }
+                    if (COUNT) atomicAdd(&A.macro_count[cell_of(g, ci, cj, ck)], 1.0);
+                }
+            }
+        }
+        __syncthreads();                                                // sh_v / sh_base are reused by the next round
     }
+}
+// after the kernel: the emitted particles join their stores (a store that ran full keeps what fitted; the rest is counted as overflow)
+__global__ void k_emit_finish(const EmitChain* chain, SpeciesCounters* cn, u64 cap_n, SpeciesCounters* cs, u64 cap_s, int same) {
+    const u64 wn = cn->n + chain->run_n;
+    if (wn > cap_n) { cn->overflow += wn - cap_n; cn->n = cap_n; } else cn->n = wn;
+    if (!same) { const u64 wsn = cs->n + chain->run_s; if (wsn > cap_s) { cs->overflow += wsn - cap_s; cs->n = cap_s; } else cs->n = wsn; }
 }
 
 __global__ void k_clamp_count(SpeciesCounters* ctr, u64 cap);       // species.cu
@@ -276,15 +335,20 @@ int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals
     }
     if (rc) return rc;
     if (mode & 2) {                                   // surface interactions of the particles that hit an object (usually a handful)
+        if (s->charge != 0 && H.sputtering && spherium == neutrals) return set_error(PICG_ERR_ARG, "heavy push: the sputtered material needs a store of its own");
+        const size_t lcap = std::max<size_t>(n_snapshot, 1);
+        unsigned* counts = (unsigned*)s->w->scratch + 2 * lcap;          // the compaction's block counts: free until compact_dead runs
+        rc = sort_slot_list(s->w, &s->ctr->n_impact, &s->ctr->n, lcap, s->cap, A.impact_list, A.impact_list, counts); if (rc) return rc;      // ascending slots, in place
+        EmitChain* chain = (EmitChain*)(s->w->reduce_buf + 4000);        // 4 words at the end of the reduction buffer
+        CUDA_TRY(cudaMemsetAsync(chain, 0, sizeof(EmitChain), g_stream));
         int grid = g_sm_count * 2;
-        if ((mode & 4) && (mode & 8)) LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<true, true>), grid, 128, 0, g, A, H);
-        else if (mode & 4) LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<true, false>), grid, 128, 0, g, A, H);
-        else if (mode & 8) LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<false, true>), grid, 128, 0, g, A, H);
-        else LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<false, false>), grid, 128, 0, g, A, H);
+        if ((mode & 4) && (mode & 8)) LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<true, true>), grid, IMPACT_THREADS, 0, g, A, H, chain);
+        else if (mode & 4) LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<true, false>), grid, IMPACT_THREADS, 0, g, A, H, chain);
+        else if (mode & 8) LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<false, true>), grid, IMPACT_THREADS, 0, g, A, H, chain);
+        else LAUNCH(K_HEAVY_IMPACTS, (k_heavy_impacts<false, false>), grid, IMPACT_THREADS, 0, g, A, H, chain);
         CHECK_LAUNCH();
-        if (s->charge != 0) {                         // emit_particle may have run a target store past its capacity: the counter goes back to it
-            LAUNCH(K_HEAVY_IMPACTS, k_clamp_count, 1, 1, 0, neutrals->ctr, (u64)neutrals->cap); CHECK_LAUNCH();
-            if (spherium != neutrals) { LAUNCH(K_HEAVY_IMPACTS, k_clamp_count, 1, 1, 0, spherium->ctr, (u64)spherium->cap); CHECK_LAUNCH(); }
+        if (s->charge != 0) {                         // the emitted particles join their stores; a store that ran full keeps what fitted
+            LAUNCH(K_HEAVY_IMPACTS, k_emit_finish, 1, 1, 0, (const EmitChain*)chain, neutrals->ctr, (u64)neutrals->cap, spherium->ctr, (u64)spherium->cap, spherium == neutrals ? 1 : 0); CHECK_LAUNCH();
         }
     }
     return PICG_OK;

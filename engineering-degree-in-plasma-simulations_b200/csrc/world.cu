@@ -104,7 +104,7 @@ int picg_world_destroy(picg_world_t w) {
     if (!w) return PICG_OK;
     if (g_stream) cudaStreamSynchronize(g_stream);
     cudaFree(w->phi); cudaFree(w->rho); cudaFree(w->node_vol); cudaFree(w->ef); cudaFree(w->object_id); cudaFree(w->node_type);
-    cudaFree(w->scratch); cudaFree(w->reduce_buf); if (w->reduce_host) cudaFreeHost(w->reduce_host);
+    cudaFree(w->scratch); cudaFree(w->cbm); cudaFree(w->reduce_buf); if (w->reduce_host) cudaFreeHost(w->reduce_host);
     delete w;
     return PICG_OK;
 }

@@ -149,7 +149,7 @@ def test_reference_main_runs_on_the_device():
     rows = [dict(zip(cols, map(float, r.split(","))) ) for r in diag[1:]]
     kT = util.KB * 300.0
     for r in rows:
-        assert abs(r["mp_count.O"] - n_neutrals) <= 200 + 30 * r["ts"]                      # neutrals leave through the open faces / split in collisions: a handful per step
+        assert abs(r["mp_count.O"] - n_neutrals) <= 200 + 60 * r["ts"]                      # neutrals leave through the open faces / split in collisions: a handful per step
         assert r["real_count.O"] + r["real_count.O+"] == pytest.approx(n_neutrals * 5e11, rel=1e-4)       # weight only moves from O to O+
         # loadParticleBoxThermal (main.cpp:119) at 300 K through the reference's sampleVth (Species.cpp:855-858): every component is sqrt(2kT/m) * (sum of 3 uniforms - 1.5),
         # variance kT/(2m), so the loaded gas carries 0.75 kT per particle (half of a 300 K Maxwellian) - in the reference and, sampler for sampler, here
