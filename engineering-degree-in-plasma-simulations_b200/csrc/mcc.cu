@@ -34,6 +34,7 @@ using namespace picg;
 
 namespace picg {
 int sort_species(picg_species_s* s); int species_exact_lists(picg_species_s* s); int species_prepare_lists(picg_species_s* s);
+int species_grow_store(picg_species_s* s, size_t cap); int species_scratch_for_store(picg_species_s* s);      // species.cu
 size_t counting_sort_words(const Grid& g);                  // sort.cu
 int scan_cell_table(const Grid& g, unsigned* table, unsigned* work);
 }
@@ -142,6 +143,30 @@ __device__ __forceinline__ bool add_particle_filter_rewind(const Grid& g, const 
     return true;
 }
 
+// Candidate pairs of cell c (v3 :646 / ch4/v2 :591).  Multi-GPU: the particles of a cell are spread over G ranks, so the
+// cell's candidate count is estimated from the local populations (x G^2), rounded ONCE like the reference's and dealt out to the
+// ranks: n/G each, the n%G left over to a rotating subset.  Rounding per rank instead would lose every cell whose share is below one half.
+__device__ __forceinline__ int mcc_groups(const MccParams& P, int fixed, int c, int np_n, int np_e, double W_max, double dt, uint32_t call) {
+    double frac = fixed ? 0.5 * np_n * np_e * P.neu_mpw0 * W_max * dt * P.inv_dv * P.rank_scale : np_n * np_e * W_max * dt * P.inv_dv * P.rank_scale;
+    int n_groups = (int)(frac + 0.5);
+    if (P.world > 1) n_groups = n_groups / P.world + ((unsigned)(c + (int)call + P.rank) % (unsigned)P.world < (unsigned)(n_groups % P.world) ? 1 : 0);
+    if (n_groups > np_n) n_groups = np_n - 1;                                             // v3 :649-653 / v2 :598-600
+    return n_groups < 0 ? 0 : n_groups;
+}
+// Sum of the candidate counts over the cells: the number of products of a call can not exceed it, which sizes the staging areas exactly
+// (a collision is never dropped for lack of room, so the outcome of a call never depends on who reached a cursor first).
+__global__ void __launch_bounds__(256) k_mcc_count(Grid g, MccParams P, CellLists Ln, CellLists Le, const double* __restrict__ wsv, double dt, uint32_t call, u64* __restrict__ total) {
+    const double W_max = wsv[0];
+    u64 sum = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.nc; c += gridDim.x * blockDim.x) {
+        const int np_e = cell_view(Le, c).np;
+        if (np_e <= 0) continue;
+        const int np_n = cell_view(Ln, c).np;
+        if (np_n > 0) sum += (u64)mcc_groups(P, P.fixed_weight, c, np_n, np_e, W_max, dt, call);
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd((unsigned long long*)total, (unsigned long long)sum);
+}
 // stats: [0] candidates [1] collisions [2] ionisations [3] skipped (electron heavier than neutral)
 //        [5] dropped because a product store was full (collision skipped untouched)
 //        [6] split-off neutrals beyond MCC_EXTRA per cell and call (created, but not selectable by later candidates of the same call)
@@ -163,16 +188,7 @@ __global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Sto
             if (np_e > 0) { vn = cell_view(Ln, c); np_n0 = vn.np; }
         }
         int np_n = np_n0;
-        if (np_e > 0 && np_n0 > 0) {
-            // v3 :646 / ch4/v2 :591.  Multi-GPU: the particles of a cell are spread over G ranks, so the cell's candidate count is estimated
-            // from the local populations (x G^2), rounded ONCE like the reference's and dealt out to the ranks: n/G each, the n%G left
-            // over to a rotating subset.  Rounding per rank instead would lose every cell whose share is below one half.
-            double frac = FIXED ? 0.5 * np_n * np_e * P.neu_mpw0 * W_max * dt * P.inv_dv * P.rank_scale : np_n * np_e * W_max * dt * P.inv_dv * P.rank_scale;
-            n_groups = (int)(frac + 0.5);
-            if (P.world > 1) n_groups = n_groups / P.world + ((unsigned)(c + (int)call + P.rank) % (unsigned)P.world < (unsigned)(n_groups % P.world) ? 1 : 0);
-            if (n_groups > np_n) n_groups = np_n - 1;                                     // v3 :649-653 / v2 :598-600
-            if (n_groups < 0) n_groups = 0;
-        }
+        if (np_e > 0 && np_n0 > 0) n_groups = mcc_groups(P, FIXED, c, np_n, np_e, W_max, dt, call);
         const int max_groups = __reduce_max_sync(0xffffffffu, n_groups);
         if (max_groups == 0) continue;                                                    // warp-uniform
         PhiloxStream r; r.init(seed, stream, (u64)c, call);
@@ -429,22 +445,23 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     rc = species_exact_lists(ele); if (rc) return rc;
     MccParams P = make_params(m);
     const Grid& g = m->w->g;
-    // room for the products: 2x what the last call appended, at least 1 % of the store.  A collision whose products do
-    // not fit is skipped untouched on the device and counted (stats.dropped); the store is then grown for the next call.
+    // Room for the products: a call makes at most one product per store and candidate pair (ch4/v2: ions_to_create ions), and the number
+    // of candidate pairs follows from the per-cell lists alone: counted first, so that the staging areas can never run full.
     CUDA_TRY(cudaMemsetAsync(m->stats, 0, 128, g_stream));
-    rc = species_refresh_count(neu); if (rc) return rc;        // synchronises
+    m->step++;
+    LAUNCH(K_MCC_APPEND, k_mcc_count, std::max(1, std::min(div_up(g.nc, 256), g_sm_count * 8)), 256, 0, g, P, lists_of(neu), lists_of(ele), (const double*)m->wsv, dt, (uint32_t)m->step, m->stats + 11);
+    CHECK_LAUNCH();
+    u64 n_pairs = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n_pairs, m->stats + 11, 8, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaStreamSynchronize(g_stream));
+    rc = species_refresh_count(neu); if (rc) return rc;
     rc = species_refresh_count(ele); if (rc) return rc;
     rc = species_refresh_count(ion); if (rc) return rc;
     size_t n_before[3] = {neu->n_host, ele->n_host, ion->n_host};
     picg_species_s* sp3[3] = {neu, ele, ion};
-    size_t scap[3], scap_max = 0;                               // room = staging capacity of the store in this call
-    for (int k = 0; k < 3; k++) {
-        scap[k] = std::max<size_t>(std::max<size_t>(2 * m->last_appends[k], sp3[k]->n_host / 100), 65536);
-        if (sp3[k]->cap < sp3[k]->n_host + scap[k]) { rc = species_ensure_capacity(sp3[k], sp3[k]->n_host + scap[k]); if (rc) return rc; }
-        scap_max = std::max(scap_max, scap[k]);
-    }
+    size_t scap[3] = {(size_t)n_pairs, (size_t)n_pairs, (size_t)n_pairs * (size_t)(m->fixed_weight ? std::max(P.ions_to_create, 1) : 1)}, scap_max = 0;
+    for (int k = 0; k < 3; k++) { scap[k] = std::max<size_t>(scap[k], 64); scap_max = std::max(scap_max, scap[k]); }
     double zero = 0; CUDA_TRY(cudaMemcpyAsync(m->wsv + 1, &zero, 8, cudaMemcpyHostToDevice, g_stream));
-    m->step++;
     // staging areas in the scratch arena (free here: the list builds above are done with it): records | (cell, rank) pairs | per-cell
     // tables of the three stores, then the index list of the commit and the work area of the scan
     const size_t nt = (size_t)g.nc + 1;
@@ -472,10 +489,15 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     CUDA_TRY(cudaMemcpyAsync(host_stats, m->stats, 128, cudaMemcpyDeviceToHost, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));                  // host_stats is valid from here on
     // the staged products, store by store, in (cell, creation) order behind the store's particles
+    bool grown[3] = {false, false, false};
     for (int k = 0; k < 3; k++) {
         const size_t staged = (size_t)host_stats[8 + k];
         if (!staged) continue;
         picg_species_s* sp = sp3[k];
+        if (sp->cap < sp->n_host + staged) {                    // grow by what is needed plus headroom; the arena holds the staged records and is re-sized after the commits
+            rc = species_grow_store(sp, sp->n_host + staged + std::max<size_t>(2 * staged, sp->n_host / 100)); if (rc) return rc;
+            grown[k] = true;
+        }
         unsigned* sorted = (unsigned*)(base + sorted_off);
         rc = scan_cell_table(g, S[k].made, (unsigned*)(base + work_off)); if (rc) return rc;          // made[] -> records in the cells below; made[nc] = records kept
         const int egrid = std::max(1, std::min(div_up(staged, 256), g_sm_count * 8));
@@ -487,6 +509,7 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     rc = species_refresh_count(neu); if (rc) return rc;
     rc = species_refresh_count(ele); if (rc) return rc;
     rc = species_refresh_count(ion); if (rc) return rc;
+    for (int k = 0; k < 3; k++) if (grown[k]) { rc = species_scratch_for_store(sp3[k]); if (rc) return rc; }
     for (int k = 0; k < 3; k++) m->last_appends[k] = host_stats[5] ? std::max(sp3[k]->n_host - n_before[k], scap[k]) : sp3[k]->n_host - n_before[k];   // dropped collisions: twice the room next time
     if (host_stats[1]) { neu->sorted_valid = false; neu->lists_valid = false; neu->count_valid = false; ele->sorted_valid = false; ele->lists_valid = false; ele->count_valid = false; ion->sorted_valid = false; ion->lists_valid = false; ion->count_valid = false; }   // :751-754
     if (host_stats[5]) {                                        // grow so that the next call has room, and tell the caller

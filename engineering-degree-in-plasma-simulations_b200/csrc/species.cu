@@ -148,7 +148,9 @@ int species_refresh_count(picg_species_s* s) {
     return PICG_OK;
 }
 
-int species_ensure_capacity(picg_species_s* s, size_t cap) {
+// Grows the particle arrays only; the caller sizes the scratch arena afterwards (species_scratch_for_store) - used where the arena holds
+// live data while a store has to grow (mcc.cu: staged products).
+int species_grow_store(picg_species_s* s, size_t cap) {
     if (cap <= s->cap) return PICG_OK;
     int rc = species_refresh_count(s); if (rc) return rc;
     size_t exact = (cap + 255) & ~(size_t)255;
@@ -176,10 +178,16 @@ int species_ensure_capacity(picg_species_s* s, size_t cap) {
     }
     note_realloc("particle store", newcap * 64);
     s->cap = newcap;
-    // the shared scratch arena is sized for a full store as well (radix sort: 16 B per particle; push: dead / hole lists +
-    // the heavy push's impact list), so that it does not have to grow - free + allocate of GBs, tens of ms - while the
-    // population grows into the reserved capacity
-    return ensure_scratch(s->w, std::max(newcap * 16 + (1u << 20), compact_scratch_bytes(newcap) + newcap * 4 + 64));
+    return PICG_OK;
+}
+// the shared scratch arena is sized for a full store as well (radix sort: 16 B per particle; push: dead / hole lists +
+// the heavy push's impact list), so that it does not have to grow - free + allocate of GBs, tens of ms - while the
+// population grows into the reserved capacity
+int species_scratch_for_store(picg_species_s* s) { return ensure_scratch(s->w, std::max(s->cap * 16 + (1u << 20), compact_scratch_bytes(s->cap) + s->cap * 4 + 64)); }
+int species_ensure_capacity(picg_species_s* s, size_t cap) {
+    if (cap <= s->cap) return PICG_OK;
+    int rc = species_grow_store(s, cap); if (rc) return rc;
+    return species_scratch_for_store(s);
 }
 }  // namespace picg
 
