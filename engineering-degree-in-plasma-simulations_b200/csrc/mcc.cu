@@ -107,27 +107,29 @@ __device__ __forceinline__ bool collide(PhiloxStream& r, const MccParams& P, con
 // ---------------------------------------------------------------- appends: one atomic per warp iteration and store
 #define MCC_THREADS 128
 // A warp walks 32 consecutive cells in lockstep (lane = cell); iteration t handles candidate t of every cell that still has
-// one.  The lanes whose candidate creates a product take consecutive slots of ONE atomicAdd on the store's counter.
-// All 32 lanes call.  Returns the slot, or -1 (not wanted, or the store is full: the counter is clamped after the kernel).
-__device__ __forceinline__ long long warp_reserve(bool want, int lane, u64* cursor, u64 cap) {
-    const unsigned mask = __ballot_sync(0xffffffffu, want);
-    if (!mask) return -1;
-    const int leader = __ffs(mask) - 1;
+// one.  The lanes whose candidate creates products take consecutive records of ONE atomicAdd on the staging cursor (a lane may want
+// several).  All 32 lanes call.  Returns the first record of the lane, or -1 (nothing wanted, or the area is full - which the sizing
+// by the candidate count rules out).
+__device__ __forceinline__ long long warp_reserve(int want, int lane, u64* cursor, u64 cap) {
+    int incl = want;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (!total) return -1;
     u64 base = 0;
-    if (lane == leader) base = atomicAdd((unsigned long long*)cursor, (unsigned long long)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
+    if (lane == 31) base = atomicAdd((unsigned long long*)cursor, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
     if (!want) return -1;
-    const u64 dst = base + __popc(mask & ((1u << lane) - 1));
-    return dst < cap ? (long long)dst : -1;
+    const u64 first = base + (u64)(incl - want);
+    return first + (u64)want <= cap ? (long long)first : -1;
 }
-// Staging area of one store: 8 doubles per record (x y z u v w mpw, one spare), the cell of every record, the cursor.
-// kr: (cell, rank of the record among the records of its cell) - a cell's records are made by one thread, one after the other, so the
-// thread numbers them itself; made[c]: how many it made (table zeroed before the launch, written once per cell).
-struct Stage { double* rec; uint2* kr; unsigned* made; u64* cursor; u64 cap; };
-__device__ __forceinline__ void write_stage(const Stage& S, long long e, const double pos[3], const double v[3], double mpw, unsigned cell, int& rank) {
+// Staging area shared by the three stores: 8 words per record - x y z u v w mpw and a tag word: cell | rank << 32 | store << 62, where
+// rank numbers the records of one (cell, store) in order of creation.  A cell's records are made by one thread, one after the other, so
+// the thread numbers them itself; made[k][c]: how many it made for store k (tables zeroed before the launch, written once per cell).
+struct Stage { double* rec; unsigned* made[3]; u64* cursor; u64 cap; };
+__device__ __forceinline__ void write_stage(const Stage& S, long long e, const double pos[3], const double v[3], double mpw, unsigned cell, int store, int& rank) {
     double4* r = reinterpret_cast<double4*>(S.rec + 8 * e);
-    r[0] = make_double4(pos[0], pos[1], pos[2], v[0]); r[1] = make_double4(v[1], v[2], mpw, 0.0);
-    S.kr[e] = make_uint2(cell, (unsigned)rank++);
+    const u64 tag = (u64)cell | ((u64)(unsigned)rank++ << 32) | ((u64)store << 62);
+    r[0] = make_double4(pos[0], pos[1], pos[2], v[0]); r[1] = make_double4(v[1], v[2], mpw, __longlong_as_double((long long)tag));
 }
 __device__ __forceinline__ void atomic_max_pos_double(double* addr, double v) {     // valid for non-negative doubles
     atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
@@ -171,10 +173,9 @@ __global__ void __launch_bounds__(256) k_mcc_count(Grid g, MccParams P, CellList
 //        [5] dropped because a product store was full (collision skipped untouched)
 //        [6] split-off neutrals beyond MCC_EXTRA per cell and call (created, but not selectable by later candidates of the same call)
 //        [7] fixed-weight variant: created electrons with a NaN velocity (ionisation below the threshold, ch4/v2 only; appended as the reference does)
-// Sn / Se / Si: staging areas of the neutral / electron / ion products (a record whose collision could not complete, because the partner
-// store was full, gets the key nc and is dropped by the sort)
+// Sn: the staging area of the products (stores 0 neutrals, 1 electrons, 2 ions)
 template <int FIXED>
-__global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, CellLists Ln, CellLists Le, Stage Sn, Stage Se, Stage Si,
+__global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Store neu, Store ele, Store ion, CellLists Ln, CellLists Le, Stage Sn,
                                                         double* __restrict__ wsv, u64* __restrict__ stats, double dt, uint64_t seed, uint32_t stream, uint32_t call) {
     const int lane = threadIdx.x & 31;
     const double W_max = wsv[0];
@@ -252,46 +253,38 @@ __global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Sto
                     }
                 }
             }
-            // ---- the warp's products of this iteration take their slots (every lane is here: the loop bounds are warp-uniform)
-            if (FIXED) {
-                for (int q = 0; q < P.ions_to_create; q++) {                               // :623-626, one ion per round
-                    const bool want = kind == 2 && ion_ok[0];
-                    long long s1 = warp_reserve(want, lane, Si.cursor, Si.cap);
-                    if (want) { if (s1 < 0) n_drop++; else write_stage(Si, s1, pos, vi, P.ion_mpw0, (unsigned)c, made_i); }
+            // ---- the warp's products of this iteration take their records (every lane is here: the loop bounds are warp-uniform)
+            if (FIXED) {                                                                   // :623-629: ions_to_create ions, one electron
+                const int n_i = (kind == 2 && ion_ok[0]) ? P.ions_to_create : 0, n_e = (kind == 2 && ion_ok[1]) ? 1 : 0;
+                long long e0 = warp_reserve(n_i + n_e, lane, Sn.cursor, Sn.cap);
+                if (n_i + n_e) {
+                    if (e0 < 0) n_drop++;
+                    else {
+                        for (int q = 0; q < n_i; q++) write_stage(Sn, e0++, pos, vi, P.ion_mpw0, (unsigned)c, 2, made_i);
+                        if (n_e) write_stage(Sn, e0, pos, vnew, P.ele_mpw0, (unsigned)c, 1, made_e);
+                    }
                 }
-                const bool want = kind == 2 && ion_ok[1];
-                long long s2 = warp_reserve(want, lane, Se.cursor, Se.cap);
-                if (want) { if (s2 < 0) n_drop++; else write_stage(Se, s2, pos, vnew, P.ele_mpw0, (unsigned)c, made_e); }
                 continue;
             }
-            // Slot reservation BEFORE any state is changed: a collision whose products do not fit is skipped as a whole (and counted), so a
-            // full store can never leave half-applied collisions behind.
-            long long s0 = warp_reserve(kind == 1, lane, Sn.cursor, Sn.cap);
-            long long s1 = warp_reserve(kind == 2, lane, Si.cursor, Si.cap);
-            long long s2 = warp_reserve(kind == 2, lane, Se.cursor, Se.cap);
-            if (kind == 2 && (s1 < 0 || s2 < 0)) {                                         // the partner's record stays reserved: key nc, dropped by the sort
-                if (s1 >= 0) Si.kr[s1] = make_uint2((unsigned)g.nc, 0u);
-                if (s2 >= 0) Se.kr[s2] = make_uint2((unsigned)g.nc, 0u);
-                kind = -1;
-            }
-            if (kind == 1 && s0 < 0) kind = -1;
-            if (kind == -1) { n_drop++; n_coll--; }                                        // no room for the products: the collision is skipped untouched
+            // Record reservation BEFORE any state is changed: a collision whose products do not fit is skipped as a whole (and counted)
+            long long e0 = warp_reserve(kind == 1 ? 1 : kind == 2 ? 2 : 0, lane, Sn.cursor, Sn.cap);
+            if (kind > 0 && e0 < 0) { kind = -1; n_drop++; n_coll--; }
             if (kind > 0) {
                 if (staged) Sn.rec[8 * pn + 6] = Wn - We; else neu.a[6][pn] = Wn - We;
                 ele.a[3][pe] = ve_[0]; ele.a[4][pe] = ve_[1]; ele.a[5][pe] = ve_[2];
                 if (kind == 2) {
                     n_ion++;
-                    write_stage(Si, s1, pos, vn_, Wl, (unsigned)c, made_i);                      // no half-step rewind (:694-695)
-                    write_stage(Se, s2, pos, vnew, Wl, (unsigned)c, made_e);
+                    write_stage(Sn, e0, pos, vn_, Wl, (unsigned)c, 2, made_i);                 // no half-step rewind (:694-695)
+                    write_stage(Sn, e0 + 1, pos, vnew, Wl, (unsigned)c, 1, made_e);
                 } else {
-                    write_stage(Sn, s0, pos, vn_, We, (unsigned)c, made_n);                      // split-off neutral of the electron's weight
-                    if (n_extra < MCC_EXTRA) { extra[n_extra++] = s0; np_n++; } else n_capped++;
+                    write_stage(Sn, e0, pos, vn_, We, (unsigned)c, 0, made_n);                 // split-off neutral of the electron's weight
+                    if (n_extra < MCC_EXTRA) { extra[n_extra++] = e0; np_n++; } else n_capped++;
                 }
             }
         }
-        if (made_n) Sn.made[c] = (unsigned)made_n;
-        if (made_e) Se.made[c] = (unsigned)made_e;
-        if (made_i) Si.made[c] = (unsigned)made_i;
+        if (made_n) Sn.made[0][c] = (unsigned)made_n;
+        if (made_e) Sn.made[1][c] = (unsigned)made_e;
+        if (made_i) Sn.made[2][c] = (unsigned)made_i;
     }
     // block-level reduction of the statistics
     __shared__ u64 sh[7]; __shared__ double sh_max;
@@ -309,22 +302,24 @@ __global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Sto
     }
 }
 // After the kernel.  (1) W_sigma_v_rel_max <- max sampled value of this step, only if a collision happened (:751-756).  (2) A cursor
-// that ran past its staging area (the reservations beyond it failed) goes back to the capacity.  stats[8 + k]: records staged for store k.
-__global__ void k_mcc_finish(double* wsv, u64* stats, u64 cap0, u64 cap1, u64 cap2) {
+// that ran past the staging area (the reservations beyond it failed) goes back to the capacity.  stats[8]: records staged.
+__global__ void k_mcc_finish(double* wsv, u64* stats, u64 cap) {
     if (stats[1]) wsv[0] = wsv[1];
-    const u64 cap[3] = {cap0, cap1, cap2};
-    for (int k = 0; k < 3; k++) if (stats[8 + k] > cap[k]) stats[8 + k] = cap[k];
+    if (stats[8] > cap) stats[8] = cap;
 }
-// Staging index of the r-th record in (cell, creation) order: start[] = exclusive scan of made[] (records of the cells below).
-__global__ void __launch_bounds__(256) k_stage_index(const u64* __restrict__ n_staged, unsigned nc, const uint2* __restrict__ kr, const unsigned* __restrict__ start, unsigned* __restrict__ sorted) {
+// Staging index of the r-th record of every store in (cell, creation) order: start[k][] = exclusive scan of made[k][] (records of the
+// cells below).  One pass over the tag words serves the three stores.
+struct StageIndex { const unsigned* start[3]; unsigned* sorted[3]; };
+__global__ void __launch_bounds__(256) k_stage_index(const u64* __restrict__ n_staged, const double* __restrict__ rec, StageIndex X) {
     const u64 n = *n_staged;
     for (u64 e = blockIdx.x * (u64)blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x) {
-        const uint2 v = kr[e];
-        if (v.x < nc) sorted[start[v.x] + v.y] = (unsigned)e;
+        const u64 tag = (u64)__double_as_longlong(rec[8 * e + 7]);
+        const unsigned cell = (unsigned)(tag & 0xffffffffu), rank = (unsigned)((tag >> 32) & 0x3fffffffu); const int k = (int)(tag >> 62);
+        X.sorted[k][X.start[k][cell] + rank] = (unsigned)e;
     }
 }
 // The staged records of one store in (cell, creation) order -> the end of the store.  sorted[r]: staging index of the r-th record,
-// start[nc]: number of records that are kept.  One thread per record: a 64-byte record in, seven coalesced 8-byte columns out.
+// *n_keep: number of records of the store.  One thread per record: a 64-byte record in, seven coalesced 8-byte columns out.
 __global__ void __launch_bounds__(256) k_stage_commit(Store st, const double* __restrict__ rec, const unsigned* __restrict__ sorted, const unsigned* __restrict__ n_keep) {
     const u64 n0 = st.ctr->n, m = *n_keep;
     for (u64 r = blockIdx.x * (u64)blockDim.x + threadIdx.x; r < m; r += (u64)gridDim.x * blockDim.x) {
@@ -459,58 +454,63 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     rc = species_refresh_count(ion); if (rc) return rc;
     size_t n_before[3] = {neu->n_host, ele->n_host, ion->n_host};
     picg_species_s* sp3[3] = {neu, ele, ion};
-    size_t scap[3] = {(size_t)n_pairs, (size_t)n_pairs, (size_t)n_pairs * (size_t)(m->fixed_weight ? std::max(P.ions_to_create, 1) : 1)}, scap_max = 0;
-    for (int k = 0; k < 3; k++) { scap[k] = std::max<size_t>(scap[k], 64); scap_max = std::max(scap_max, scap[k]); }
+    // a pair makes one split-off neutral, or one ion and one electron (ch4/v2: ions_to_create ions and one electron)
+    const size_t per_pair = m->fixed_weight ? (size_t)std::max(P.ions_to_create, 1) + 1 : 2;
+    const size_t scap = std::max<size_t>((size_t)n_pairs * per_pair, 64);
     double zero = 0; CUDA_TRY(cudaMemcpyAsync(m->wsv + 1, &zero, 8, cudaMemcpyHostToDevice, g_stream));
-    // staging areas in the scratch arena (free here: the list builds above are done with it): records | (cell, rank) pairs | per-cell
-    // tables of the three stores, then the index list of the commit and the work area of the scan
+    // staging area in the scratch arena (free here: the list builds above are done with it): records | per-cell tables of the three stores |
+    // index lists of the commits | work area of the scans
     const size_t nt = (size_t)g.nc + 1;
-    size_t rec_off[3], kr_off[3], made_off[3], off = 0;
-    for (int k = 0; k < 3; k++) { rec_off[k] = off; off += ((scap[k] * 64 + 255) & ~(size_t)255); }
-    for (int k = 0; k < 3; k++) { kr_off[k] = off; off += ((scap[k] * 8 + 255) & ~(size_t)255); }
+    size_t made_off[3], sorted_off[3], off = (scap * 64 + 255) & ~(size_t)255;
     for (int k = 0; k < 3; k++) { made_off[k] = off; off += ((nt * 4 + 255) & ~(size_t)255); }
-    const size_t sorted_off = off; off += (scap_max * 4 + 255) & ~(size_t)255;
+    for (int k = 0; k < 3; k++) { sorted_off[k] = off; off += ((std::min(scap, (size_t)n_pairs * (k == 2 ? per_pair - 1 : 1) + 64) * 4 + 255) & ~(size_t)255); }
     const size_t work_off = off; off += counting_sort_words(g) * 4 + 256;
     rc = ensure_scratch(m->w, off); if (rc) return rc;
     char* base = (char*)m->w->scratch;
-    Stage S[3];
-    for (int k = 0; k < 3; k++) {
-        S[k].rec = (double*)(base + rec_off[k]); S[k].kr = (uint2*)(base + kr_off[k]); S[k].made = (unsigned*)(base + made_off[k]); S[k].cursor = m->stats + 8 + k; S[k].cap = scap[k];
-        CUDA_TRY(cudaMemsetAsync(S[k].made, 0, nt * 4, g_stream));
-    }
+    Stage S; S.rec = (double*)base; S.cursor = m->stats + 8; S.cap = scap;
+    for (int k = 0; k < 3; k++) { S.made[k] = (unsigned*)(base + made_off[k]); CUDA_TRY(cudaMemsetAsync(S.made[k], 0, nt * 4, g_stream)); }
     int grid = std::max(1, std::min(div_up(g.nc, MCC_THREADS), g_sm_count * 16));
-    if (m->fixed_weight) LAUNCH(K_MCC, k_mcc<1>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), S[0], S[1], S[2],
+    if (m->fixed_weight) LAUNCH(K_MCC, k_mcc<1>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), S,
                                 m->wsv, m->stats, dt, g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
-    else LAUNCH(K_MCC, k_mcc<0>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), S[0], S[1], S[2],
+    else LAUNCH(K_MCC, k_mcc<0>, grid, MCC_THREADS, 0, g, P, store_of(neu), store_of(ele), store_of(ion), lists_of(neu), lists_of(ele), S,
                 m->wsv, m->stats, dt, g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
     CHECK_LAUNCH();
-    LAUNCH(K_MCC_APPEND, k_mcc_finish, 1, 1, 0, m->wsv, m->stats, (u64)scap[0], (u64)scap[1], (u64)scap[2]); CHECK_LAUNCH();
+    LAUNCH(K_MCC_APPEND, k_mcc_finish, 1, 1, 0, m->wsv, m->stats, (u64)scap); CHECK_LAUNCH();
     u64 host_stats[16];
     CUDA_TRY(cudaMemcpyAsync(host_stats, m->stats, 128, cudaMemcpyDeviceToHost, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));                  // host_stats is valid from here on
     // the staged products, store by store, in (cell, creation) order behind the store's particles
     bool grown[3] = {false, false, false};
-    for (int k = 0; k < 3; k++) {
-        const size_t staged = (size_t)host_stats[8 + k];
-        if (!staged) continue;
-        picg_species_s* sp = sp3[k];
-        if (sp->cap < sp->n_host + staged) {                    // grow by what is needed plus headroom; the arena holds the staged records and is re-sized after the commits
-            rc = species_grow_store(sp, sp->n_host + staged + std::max<size_t>(2 * staged, sp->n_host / 100)); if (rc) return rc;
-            grown[k] = true;
+    const size_t staged = (size_t)host_stats[8];
+    if (staged) {
+        StageIndex X;
+        for (int k = 0; k < 3; k++) {                           // made[k][] -> records in the cells below; made[k][nc] = records of store k
+            rc = scan_cell_table(g, S.made[k], (unsigned*)(base + work_off)); if (rc) return rc;
+            X.start[k] = S.made[k]; X.sorted[k] = (unsigned*)(base + sorted_off[k]);
         }
-        unsigned* sorted = (unsigned*)(base + sorted_off);
-        rc = scan_cell_table(g, S[k].made, (unsigned*)(base + work_off)); if (rc) return rc;          // made[] -> records in the cells below; made[nc] = records kept
+        unsigned kept[3];
+        for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemcpyAsync(&kept[k], S.made[k] + g.nc, 4, cudaMemcpyDeviceToHost, g_stream));
         const int egrid = std::max(1, std::min(div_up(staged, 256), g_sm_count * 8));
-        LAUNCH(K_MCC_APPEND, k_stage_index, egrid, 256, 0, (const u64*)S[k].cursor, (unsigned)g.nc, (const uint2*)S[k].kr, (const unsigned*)S[k].made, sorted); CHECK_LAUNCH();
-        LAUNCH(K_MCC_APPEND, k_stage_commit, egrid, 256, 0, store_of(sp), (const double*)S[k].rec, (const unsigned*)sorted, (const unsigned*)(S[k].made + g.nc)); CHECK_LAUNCH();
-        LAUNCH(K_MCC_APPEND, k_stage_count, 1, 1, 0, sp->ctr, (const unsigned*)(S[k].made + g.nc)); CHECK_LAUNCH();
-        sp->n_host_valid = false; sp->n_upper = std::min(sp->cap, sp->n_host + staged);
+        LAUNCH(K_MCC_APPEND, k_stage_index, egrid, 256, 0, (const u64*)S.cursor, (const double*)S.rec, X); CHECK_LAUNCH();
+        CUDA_TRY(cudaStreamSynchronize(g_stream));
+        for (int k = 0; k < 3; k++) {
+            if (!kept[k]) continue;
+            picg_species_s* sp = sp3[k];
+            if (sp->cap < sp->n_host + kept[k]) {               // grow by what is needed plus headroom; the arena holds the staged records and is re-sized after the commits
+                rc = species_grow_store(sp, sp->n_host + kept[k] + std::max<size_t>(2 * (size_t)kept[k], sp->n_host / 100)); if (rc) return rc;
+                grown[k] = true;
+            }
+            const int cgrid = std::max(1, std::min(div_up((size_t)kept[k], 256), g_sm_count * 8));
+            LAUNCH(K_MCC_APPEND, k_stage_commit, cgrid, 256, 0, store_of(sp), (const double*)S.rec, (const unsigned*)X.sorted[k], (const unsigned*)(S.made[k] + g.nc)); CHECK_LAUNCH();
+            LAUNCH(K_MCC_APPEND, k_stage_count, 1, 1, 0, sp->ctr, (const unsigned*)(S.made[k] + g.nc)); CHECK_LAUNCH();
+            sp->n_host_valid = false; sp->n_upper = std::min(sp->cap, sp->n_host + (size_t)kept[k]);
+        }
     }
     rc = species_refresh_count(neu); if (rc) return rc;
     rc = species_refresh_count(ele); if (rc) return rc;
     rc = species_refresh_count(ion); if (rc) return rc;
     for (int k = 0; k < 3; k++) if (grown[k]) { rc = species_scratch_for_store(sp3[k]); if (rc) return rc; }
-    for (int k = 0; k < 3; k++) m->last_appends[k] = host_stats[5] ? std::max(sp3[k]->n_host - n_before[k], scap[k]) : sp3[k]->n_host - n_before[k];   // dropped collisions: twice the room next time
+    for (int k = 0; k < 3; k++) m->last_appends[k] = sp3[k]->n_host - n_before[k];
     if (host_stats[1]) { neu->sorted_valid = false; neu->lists_valid = false; neu->count_valid = false; ele->sorted_valid = false; ele->lists_valid = false; ele->count_valid = false; ion->sorted_valid = false; ion->lists_valid = false; ion->count_valid = false; }   // :751-754
     if (host_stats[5]) {                                        // grow so that the next call has room, and tell the caller
         for (int k = 0; k < 3; k++) { rc = species_ensure_capacity(sp3[k], sp3[k]->n_host + std::max<size_t>(4 * (size_t)host_stats[5], sp3[k]->n_host / 10)); if (rc) return rc; }
