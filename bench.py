@@ -612,11 +612,11 @@ def run_ours(args):
     traffic, traffic_src = None, None
     ncu_names = {"deposit_density": "k_cell_deposit", "push_heavy": "k_run<1, 1, 0, 0, 0>", "push_neutral": "k_run<1, 1, 0, 0, 1>", "push_electrons": "k_run<1, 0, 0, 0, 0>", "sor_redblack": "k_sor_row"}
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1b.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2b.json")))
         if world == 1 and m == 256 and abs(args.particles - 1e9) < 1 and dom in ncu_names:
             ent = [e for k, v in tj["kernels"].items() if k.startswith(ncu_names[dom]) for e in v]    # deposit: all lane-group variants
             traffic = float(np.mean([e["dram_bytes"] for e in ent]))
-            traffic_src = "profiles/ncu_traffic_r1b.json (%s, mean of %d captured launches)" % (ncu_names[dom], len(ent))
+            traffic_src = "profiles/ncu_traffic_r2b.json (%s, mean of %d captured launches)" % (ncu_names[dom], len(ent))
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac_of_peak"],

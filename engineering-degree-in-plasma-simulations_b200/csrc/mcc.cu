@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Sto
     const int lane = threadIdx.x & 31;
     const double W_max = wsv[0];
     u64 n_cand = 0, n_coll = 0, n_ion = 0, n_skip = 0, n_drop = 0, n_capped = 0, n_nan = 0; double step_max = 0;
+    unsigned tot_made[3] = {0, 0, 0};                                                      // records staged per store by this thread
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int c0 = warp * 32; c0 < g.nc; c0 += nwarps * 32) {
         const int c = c0 + lane;
@@ -282,22 +283,24 @@ __global__ void __launch_bounds__(MCC_THREADS, 6) k_mcc(Grid g, MccParams P, Sto
                 }
             }
         }
-        if (made_n) Sn.made[0][c] = (unsigned)made_n;
-        if (made_e) Sn.made[1][c] = (unsigned)made_e;
-        if (made_i) Sn.made[2][c] = (unsigned)made_i;
+        if (made_n) { Sn.made[0][c] = (unsigned)made_n; tot_made[0] += made_n; }
+        if (made_e) { Sn.made[1][c] = (unsigned)made_e; tot_made[1] += made_e; }
+        if (made_i) { Sn.made[2][c] = (unsigned)made_i; tot_made[2] += made_i; }
     }
     // block-level reduction of the statistics
-    __shared__ u64 sh[7]; __shared__ double sh_max;
-    if (threadIdx.x == 0) { for (int q = 0; q < 7; q++) sh[q] = 0; sh_max = 0; }
+    __shared__ u64 sh[10]; __shared__ double sh_max;
+    if (threadIdx.x == 0) { for (int q = 0; q < 10; q++) sh[q] = 0; sh_max = 0; }
     __syncthreads();
     if (n_cand) {
         atomicAdd(&sh[0], n_cand); atomicAdd(&sh[1], n_coll); atomicAdd(&sh[2], n_ion); atomicAdd(&sh[3], n_skip); atomicAdd(&sh[4], n_drop);
         atomicAdd(&sh[5], n_capped); atomicAdd(&sh[6], n_nan); atomic_max_pos_double(&sh_max, step_max);
+        for (int k = 0; k < 3; k++) if (tot_made[k]) atomicAdd(&sh[7 + k], (u64)tot_made[k]);
     }
     __syncthreads();
     if (threadIdx.x == 0 && sh[0]) {
         atomicAdd(&stats[0], sh[0]); atomicAdd(&stats[1], sh[1]); atomicAdd(&stats[2], sh[2]); atomicAdd(&stats[3], sh[3]); atomicAdd(&stats[5], sh[4]);
         atomicAdd(&stats[6], sh[5]); atomicAdd(&stats[7], sh[6]);
+        for (int k = 0; k < 3; k++) if (sh[7 + k]) atomicAdd(&stats[12 + k], sh[7 + k]);             // records of store k (0 neutrals, 1 electrons, 2 ions)
         atomic_max_pos_double(&wsv[1], sh_max);
     }
 }
@@ -484,26 +487,25 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     const size_t staged = (size_t)host_stats[8];
     if (staged) {
         StageIndex X;
+        size_t kept[3];
         for (int k = 0; k < 3; k++) {                           // made[k][] -> records in the cells below; made[k][nc] = records of store k
-            rc = scan_cell_table(g, S.made[k], (unsigned*)(base + work_off)); if (rc) return rc;
+            kept[k] = (size_t)host_stats[12 + k];
             X.start[k] = S.made[k]; X.sorted[k] = (unsigned*)(base + sorted_off[k]);
+            if (kept[k]) { rc = scan_cell_table(g, S.made[k], (unsigned*)(base + work_off)); if (rc) return rc; }
         }
-        unsigned kept[3];
-        for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemcpyAsync(&kept[k], S.made[k] + g.nc, 4, cudaMemcpyDeviceToHost, g_stream));
         const int egrid = std::max(1, std::min(div_up(staged, 256), g_sm_count * 8));
         LAUNCH(K_MCC_APPEND, k_stage_index, egrid, 256, 0, (const u64*)S.cursor, (const double*)S.rec, X); CHECK_LAUNCH();
-        CUDA_TRY(cudaStreamSynchronize(g_stream));
         for (int k = 0; k < 3; k++) {
             if (!kept[k]) continue;
             picg_species_s* sp = sp3[k];
             if (sp->cap < sp->n_host + kept[k]) {               // grow by what is needed plus headroom; the arena holds the staged records and is re-sized after the commits
-                rc = species_grow_store(sp, sp->n_host + kept[k] + std::max<size_t>(2 * (size_t)kept[k], sp->n_host / 100)); if (rc) return rc;
+                rc = species_grow_store(sp, sp->n_host + kept[k] + std::max<size_t>(2 * kept[k], sp->n_host / 100)); if (rc) return rc;
                 grown[k] = true;
             }
-            const int cgrid = std::max(1, std::min(div_up((size_t)kept[k], 256), g_sm_count * 8));
+            const int cgrid = std::max(1, std::min(div_up(kept[k], 256), g_sm_count * 8));
             LAUNCH(K_MCC_APPEND, k_stage_commit, cgrid, 256, 0, store_of(sp), (const double*)S.rec, (const unsigned*)X.sorted[k], (const unsigned*)(S.made[k] + g.nc)); CHECK_LAUNCH();
             LAUNCH(K_MCC_APPEND, k_stage_count, 1, 1, 0, sp->ctr, (const unsigned*)(S.made[k] + g.nc)); CHECK_LAUNCH();
-            sp->n_host_valid = false; sp->n_upper = std::min(sp->cap, sp->n_host + (size_t)kept[k]);
+            sp->n_host_valid = false; sp->n_upper = std::min(sp->cap, sp->n_host + kept[k]);
         }
     }
     rc = species_refresh_count(neu); if (rc) return rc;

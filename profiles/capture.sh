@@ -8,7 +8,7 @@ CMD="python bench.py --mesh $MESH --particles $NP --steps 2 --warmup 2 --skip_cp
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches.csv $CMD > $OUT/launches.log 2>&1
 python profiles/launch_list.py $OUT/launches.csv "$CMD" > $OUT/launches.md
 # (2) full-set capture of the hot kernels, a few launches each, taken from the timed region (skip set-up + warm-up launches)
-for K in k_run:16:6 k_cell_deposit:6:3 k_sor_row:300:2 k_mcc:2:1 k_sort_permute:14:2; do
+for K in k_run:16:6 k_cell_deposit:6:3 k_sor_row:300:2 'k_mcc<':2:1 k_sort_permute:14:2; do
   IFS=: read NAME SKIP COUNT <<< "$K"
   ncu --set full --clock-control none --import-source on -k regex:"^$NAME" -s $SKIP -c $COUNT -o $OUT/$NAME -f $CMD > $OUT/$NAME.log 2>&1
   python profiles/ncu_summary.py $OUT/$NAME.ncu-rep 0 > $OUT/$NAME.summary.txt 2>&1
