@@ -33,7 +33,28 @@ using namespace picg;
 
 #define RUN_THREADS 256
 #define RUN_WARPS (RUN_THREADS / 32)
-#define RUN_LEN_PUSH 4                                       // particles per thread run when the kernel pushes (7 arrays live in registers)
+#define RUN_LEN_PUSH 4                                       // particles per thread run when the kernel pushes (7 arrays live in registers); 2 and 4 are supported
+// The electron push (gather + kick + drift, no wall interaction) is bound by latency, not by registers in flight: runs of 2 particles at
+// 4 blocks per SM (64 registers, 32 warps) beat runs of 4 at 2 blocks (128 registers, 16 warps) by 12 %; the heavy push and the drift-only
+// push of the neutrals do not gain (profiles/r2_push_runlen.md).
+#ifndef ELE_RL
+#define ELE_RL 2
+#endif
+#ifndef ELE_BLOCKS
+#define ELE_BLOCKS 4
+#endif
+#ifndef HEAVY_RL
+#define HEAVY_RL 4
+#endif
+#ifndef HEAVY_BLOCKS
+#define HEAVY_BLOCKS 2
+#endif
+__host__ __device__ constexpr int run_len(bool push, bool heavy, bool deposit, bool drift) {
+    return !push ? 8 : (deposit || drift) ? RUN_LEN_PUSH : heavy ? HEAVY_RL : ELE_RL;
+}
+__host__ __device__ constexpr int run_blocks(bool push, bool heavy, bool deposit, bool drift) {
+    return (!push || deposit || drift) ? 2 : heavy ? HEAVY_BLOCKS : ELE_BLOCKS;
+}
 #define RUN_LEN_SCAN 8                                       // deposit / count only (4 arrays): longer runs, fewer flushes per particle
 #define RUN_WINDOW 64                                        // nodes along k in the per-warp window (4 rows x 64 x 8 B = 2 KB)
 
@@ -50,9 +71,16 @@ __device__ __forceinline__ void ld4_stream(const double* p, double v[4]) {
 __device__ __forceinline__ void st4_stream(double* p, const double v[4]) {
     asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
+__device__ __forceinline__ void ld2_stream(const double* p, double v[2]) {
+    asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+}
+__device__ __forceinline__ void st2_stream(double* p, const double v[2]) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+}
 template <int RL>
 __device__ __forceinline__ void load_run(const double* base, u64 p0, bool full, u64 lo, u64 n, double* v) {
     if (full) {
+        if (RL == 2) ld2_stream(base + p0, v);
 #pragma unroll
         for (int q = 0; q < RL / 4; q++) ld4_stream(base + p0 + 4 * q, v + 4 * q);
     } else {
@@ -63,6 +91,7 @@ __device__ __forceinline__ void load_run(const double* base, u64 p0, bool full, 
 template <int RL>
 __device__ __forceinline__ void store_run(double* base, u64 p0, bool full, u64 lo, u64 n, const double* v) {
     if (full) {
+        if (RL == 2) st2_stream(base + p0, v);
 #pragma unroll
         for (int q = 0; q < RL / 4; q++) st4_stream(base + p0 + 4 * q, v + 4 * q);
     } else {
@@ -75,7 +104,7 @@ __device__ __forceinline__ void store_run(double* base, u64 p0, bool full, u64 l
 // and the velocity write-back are skipped (72 B per particle instead of 96).  Same values as the reference for every finite E
 // (a -0.0 velocity component would become +0.0 there and stays -0.0 here: equal under ==).
 template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT, bool DRIFT = false>
-__global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, HeavyArgs H) {
+__global__ void __launch_bounds__(RUN_THREADS, run_blocks(PUSH, HEAVY, DEPOSIT, DRIFT)) k_run(Grid g, StepArgs A, HeavyArgs H) {
     __shared__ unsigned s_lo[DEPOSIT ? RUN_WARPS : 1][RUN_WINDOW * 4], s_hi[DEPOSIT ? RUN_WARPS : 1][RUN_WINDOW * 4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     unsigned* wlo = s_lo[DEPOSIT ? wib : 0]; unsigned* whi = s_hi[DEPOSIT ? wib : 0];
@@ -84,7 +113,7 @@ __global__ void __launch_bounds__(RUN_THREADS, 2) k_run(Grid g, StepArgs A, Heav
     const u64 lo = A.tail_from ? (u64)*A.tail_from : 0;
     const u64 warp = (u64)blockIdx.x * RUN_WARPS + wib, nwarps = (u64)gridDim.x * RUN_WARPS;
 
-    constexpr int RL = PUSH ? RUN_LEN_PUSH : RUN_LEN_SCAN;
+    constexpr int RL = run_len(PUSH, HEAVY, DEPOSIT, DRIFT);
     constexpr int WARP_CHUNK = 32 * RL;
     for (u64 chunk = (lo & ~(u64)3) + warp * WARP_CHUNK; chunk < n; chunk += nwarps * WARP_CHUNK) {
         const u64 p0 = chunk + (u64)lane * RL;
@@ -279,8 +308,8 @@ int check_scale_after(picg_species_s* s);
 
 template <bool PUSH, bool HEAVY, bool DEPOSIT, bool COUNT, bool DRIFT = false>
 static int launch_variant(const Grid& g, const StepArgs& A, const HeavyArgs& H, size_t n_upper, int kid) {
-    constexpr int chunk = 32 * (PUSH ? RUN_LEN_PUSH : RUN_LEN_SCAN) * RUN_WARPS;
-    int grid = std::max(1, std::min(div_up(std::max<size_t>(n_upper, 1), chunk), g_sm_count * 2 * 4));
+    constexpr int chunk = 32 * run_len(PUSH, HEAVY, DEPOSIT, DRIFT) * RUN_WARPS;
+    int grid = std::max(1, std::min(div_up(std::max<size_t>(n_upper, 1), chunk), g_sm_count * run_blocks(PUSH, HEAVY, DEPOSIT, DRIFT) * 4));
     LAUNCH(kid, (k_run<PUSH, HEAVY, DEPOSIT, COUNT, DRIFT>), grid, RUN_THREADS, 0, g, A, H);
     CHECK_LAUNCH();
     return PICG_OK;
