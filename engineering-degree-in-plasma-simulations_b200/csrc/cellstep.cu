@@ -32,7 +32,14 @@ using namespace picg;
 
 #define CG_THREADS 256
 #define CG_WARPS (CG_THREADS / 32)
-#define CG_CAP 192                                  // particles per stage and array (1.5 KB)
+#ifndef CG_CAP
+#define CG_CAP 208                                  // particles per stage and array: the largest that lets two blocks share an SM (2 x 111 KB).  A pass longer than a
+                                                    // stage is split and the lane groups whose cells ended in the first part idle through the second: 176 / 192 / 208 -> 10.2 / 10.0 / 9.7 ms
+                                                    // per step for the three deposits of the bench; 128 -> 14.2 (profiles/r2_deposit_stage.md)
+#endif
+#ifndef CG_BLOCKS
+#define CG_BLOCKS 2                                 // blocks per SM (registers per thread = 65536 / (256 * CG_BLOCKS))
+#endif
 #define CG_CHUNK (CG_CAP - 2)                       // the copied range is widened to even particle indices (16-byte alignment)
 #define CG_MVB 64                                   // movers staged per warp before they go to the global list (one atomic per batch)
 
@@ -50,7 +57,7 @@ struct Cursor { int pass; unsigned cs, cs_next, pos, end; };
 struct Item { int pass; unsigned cs, lo, hi; bool last; };
 
 template <bool DEPOSIT, bool COUNT, int LG>
-__global__ void __launch_bounds__(CG_THREADS, 2) k_cell_deposit(Grid g, CellArgs A) {
+__global__ void __launch_bounds__(CG_THREADS, CG_BLOCKS) k_cell_deposit(Grid g, CellArgs A) {
     constexpr int NA = DEPOSIT ? 4 : 3;
     constexpr int G = 1 << LG, P = 32 >> LG;                    // lanes per cell, cells per pass
     extern __shared__ __align__(128) unsigned char cg_smem[];
@@ -255,7 +262,7 @@ static int launch_cell_variant(const Grid& g, const CellArgs& A, int kid) {
     const size_t smem = cell_smem_bytes(DEPOSIT ? 4 : 3);
     if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_cell_deposit<DEPOSIT, COUNT, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
     const int npass = div_up((size_t)g.nc, 32 >> LG);
-    int grid = std::max(1, std::min(div_up((size_t)npass, CG_WARPS), g_sm_count * 2));
+    int grid = std::max(1, std::min(div_up((size_t)npass, CG_WARPS), g_sm_count * CG_BLOCKS));
     LAUNCH(kid, (k_cell_deposit<DEPOSIT, COUNT, LG>), grid, CG_THREADS, smem, g, A);
     CHECK_LAUNCH();
     return PICG_OK;
