@@ -227,26 +227,6 @@ def run_ours(args):
     cold.solveGS(); cold.computeEF()
     init_iters = cold.iterations
 
-    species = {}
-    for s in wl["species"]:
-        sp = pg.Species(s["name"], s["mass"], s["charge"], w, s["mpw0"], wl["E_ion"] if s["name"] == "O" else -666.0)
-        per_rank = s["count"] // world + 1
-        # no store may be re-allocated inside a timed region: the neutral store grows by the split-off neutrals of the MC collisions
-        # (about 0.5 % per step of this workload), also over the steps of the subcycled loop
-        head = 1.25 + (0.85 if s["name"] == "O" else 0.0)     # the neutral store doubles within the run (split-off neutrals of the MC collisions)
-        sp.reserve(int(per_rank * head) + args.inject * (args.steps + args.warmup + 8))
-        sp.loadParticleBoxThermal(wl["box_c"], wl["box_s"], s["den"], s["T"])
-        sp.sort()
-        species[s["name"]] = sp
-    neu, ion, ele = species["O"], species["O+"], species["e-"]
-    order = [neu, ion, ele]
-    mcc = None
-    if not args.no_mcc:
-        import util
-        E, sg = util.momentum_transfer_table()
-        mcc = pg.MC_MEX_Ionization(neu, ion, ele, w, E, sg)
-
-    # a common fixed-point scale on every rank (the all-reduce sums raw int64 accumulators)
     mg = importlib.import_module(PKG + ".multigpu")
 
     def reduce_min(v):
@@ -259,18 +239,58 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for sp in order:
-        sp.computeNumberDensity()
-        sp.setDensityScale(mg.common_scale(sp.densityScale(), world, reduce_min))
-    fixed_views = {sp.name: mg.fixed_view(torch, sp, pg.SF_DEN_FIXED) for sp in order} if world > 1 else {}
-    # Slab Poisson reads rho only on this rank's planes: reduce-scatter the accumulators onto the slabs (in place: rank r's output is
-    # the r-th chunk of its own input) and finalize / sum charges there only.  Needs equal chunks = planes divisible by the ranks.
+    phi_initial = w.download(pg.F_PHI).copy()                # the potential every (re-)created plasma starts from
+    species = {}
+    neu = ion = ele = mcc = None
+    order = []
+    fixed_views = {}
     slab_range, scatter_chunks, density_mode = None, None, "all-reduce (full grids on every rank)"
-    if world > 1 and poisson_mode.startswith("slab") and m % world == 0 and not args.allreduce_density:
-        slab_range = sol.slabRange()
-        scatter_chunks = {name: list(v.chunk(world)) for name, v in fixed_views.items()}
-        assert slab_range == (rank * (nv_total // world), (rank + 1) * (nv_total // world))
-        density_mode = "reduce-scatter onto the Poisson slabs (density and rho finalised on the owned planes only)"
+
+    def create_plasma():
+        """Species, particles, collision handler and fixed-point scales of the run.  Called again before the end-to-end leg: the runs
+        are reproducible, so the second plasma is the first one over again, particle for particle."""
+        nonlocal neu, ion, ele, mcc, order, fixed_views, slab_range, scatter_chunks, density_mode
+        for s in wl["species"]:
+            sp = pg.Species(s["name"], s["mass"], s["charge"], w, s["mpw0"], wl["E_ion"] if s["name"] == "O" else -666.0)
+            per_rank = s["count"] // world + 1
+            # no store may be re-allocated inside a timed region: the neutral store grows by the split-off neutrals of the MC collisions
+            # (about 0.5 % per step of this workload), also over the steps of the subcycled loop
+            head = 1.25 + (0.85 if s["name"] == "O" else 0.0)     # the neutral store doubles within the run (split-off neutrals of the MC collisions)
+            sp.reserve(int(per_rank * head) + args.inject * (args.steps + args.warmup + 8))
+            sp.loadParticleBoxThermal(wl["box_c"], wl["box_s"], s["den"], s["T"])
+            sp.sort()
+            species[s["name"]] = sp
+        neu, ion, ele = species["O"], species["O+"], species["e-"]
+        order = [neu, ion, ele]
+        mcc = None
+        if not args.no_mcc:
+            import util
+            E, sg = util.momentum_transfer_table()
+            mcc = pg.MC_MEX_Ionization(neu, ion, ele, w, E, sg)
+        # a common fixed-point scale on every rank (the all-reduce sums raw int64 accumulators)
+        for sp in order:
+            sp.computeNumberDensity()
+            sp.setDensityScale(mg.common_scale(sp.densityScale(), world, reduce_min))
+        fixed_views = {sp.name: mg.fixed_view(torch, sp, pg.SF_DEN_FIXED) for sp in order} if world > 1 else {}
+        # Slab Poisson reads rho only on this rank's planes: reduce-scatter the accumulators onto the slabs (in place: rank r's output is
+        # the r-th chunk of its own input) and finalize / sum charges there only.  Needs equal chunks = planes divisible by the ranks.
+        slab_range, scatter_chunks, density_mode = None, None, "all-reduce (full grids on every rank)"
+        if world > 1 and poisson_mode.startswith("slab") and m % world == 0 and not args.allreduce_density:
+            slab_range = sol.slabRange()
+            scatter_chunks = {name: list(v.chunk(world)) for name, v in fixed_views.items()}
+            assert slab_range == (rank * (nv_total // world), (rank + 1) * (nv_total // world))
+            density_mode = "reduce-scatter onto the Poisson slabs (density and rho finalised on the owned planes only)"
+
+    def destroy_plasma():
+        nonlocal mcc, fixed_views, scatter_chunks
+        fixed_views = {}; scatter_chunks = None
+        if mcc is not None:
+            mcc.close(); mcc = None
+        for sp in order:
+            sp.close()
+        species.clear()
+
+    create_plasma()
     comm_stream = torch.cuda.Stream(device=local) if world > 1 else None
     setup_s = time.time() - t0
 
@@ -636,12 +656,26 @@ def run_ours(args):
         inj.append(a)
     rho_pin = torch.empty(nv, dtype=torch.float64).pin_memory()
     rho_host = rho_pin.numpy()
-    e2e_steps = max(2, min(args.steps, 5))
+    # One GPU: the same steps as the device-resident leg, on the same plasma - the run is re-created (runs are reproducible, so this is the
+    # first plasma over again), warmed up like the first, and the K steps are then taken through the host-buffer path.  Several GPUs: the
+    # end-to-end steps follow the timed ones (five of them), as in round 1.
+    if world == 1:
+        e2e_steps = args.steps
+        destroy_plasma()
+        w.upload(pg.F_PHI, phi_initial); sol.computeEF()
+        create_plasma()
+        ts = 1
+        for _ in range(args.warmup):
+            step(ts); ts += 1
+    else:
+        e2e_steps = max(2, min(args.steps, 5))
+    e2e_first_step_population = global_count()
     reallocs1 = pg.realloc_count()
     pg.timers_reset(); pg.timers_enable(True)
     if prof is not None:
         prof.clear()
     ms_e2e, ps_local, _ = timed(e2e_steps, ts, e2e=True, inject_bufs=inj, rho_host=rho_host)
+    ts += e2e_steps
     if prof is not None and rank == 0:
         print("e2e host profile (ms/step): " + json.dumps({k: round(v / e2e_steps, 2) for k, v in prof.items()}), file=sys.stderr)
     pg.timers_enable(False)
@@ -651,7 +685,9 @@ def run_ours(args):
     e2e = {"value": ps_local / (ms_e2e * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": int(n_inj * 56 * world),
            "d2h_bytes_per_step": int((nv * 8 + 3 * 5 * 8 + 3 * 64) * world), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
            "kernel_ms_per_step": kt_e2e, "device_reallocs": int(pg.realloc_count() - reallocs1),
-           "what": "C-ABI step with host buffers: H2D of injected electrons (pinned), D2H of per-species counters + diagnostics and of rho every step"}
+           "what": "C-ABI step with host buffers: H2D of injected electrons (pinned), D2H of per-species counters + diagnostics and of rho every step; "
+                   + ("the plasma of the device-resident leg re-created (same seed: the same particles) and taken through the SAME step numbers" if world == 1 else
+                      "the steps that follow the device-resident leg"), "same_start_as_value": (bool(e2e_first_step_population == n_start) if world == 1 else None)}
 
     # ---- Poisson to the reference's tolerance.  The step above runs the solve warm-started with a cap of --s_max_it iterations (both arms);
     # here the SAME solve is run once with the reference's own budget (main.cpp:82 --s_max_it 8000, tolerance main.cpp:83) from the

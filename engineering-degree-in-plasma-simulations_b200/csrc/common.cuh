@@ -50,7 +50,7 @@ struct SpeciesCounters {    // lives in device memory, one per species
 struct picg_world_s {
     Grid g;
     double dt = 1e-4; int num_ts = 0;
-    uint32_t n_species = 0;
+    uint32_t n_species = 0, live_species = 0;      // ids handed out / species alive: when the last one goes the ids start again (a re-created plasma draws the same streams)
     double *phi = nullptr, *rho = nullptr, *node_vol = nullptr, *ef = nullptr;   // ef: 3*nv interleaved
     int *object_id = nullptr, *node_type = nullptr;
     // scratch arena shared by sort / compaction (never live at the same time)

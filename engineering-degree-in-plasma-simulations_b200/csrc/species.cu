@@ -219,7 +219,7 @@ int picg_species_create(picg_world_t w, double mass, double charge, double mpw0,
     REQUIRE_ARG(mass > 0 && mpw0 > 0, "picg_species_create: mass and mpw0 must be positive");
     picg_species_s* s = new picg_species_s();
     s->w = w; s->mass = mass; s->charge = charge; s->mpw0 = mpw0;
-    s->id = w->n_species++;
+    s->id = w->n_species++; w->live_species++;
     size_t nv = w->g.nv, nc = w->g.nc;
     cudaError_t e;
     double** nodef[] = {&s->den, &s->den_avg, &s->T, &s->n_sum, &s->nuu, &s->nvv, &s->nww};
@@ -249,6 +249,7 @@ int picg_species_destroy(picg_species_t s) {
     cudaFree(s->den_fixed); cudaFree(s->den); cudaFree(s->den_avg); cudaFree(s->T); cudaFree(s->vel); cudaFree(s->n_sum);
     cudaFree(s->nv_sum); cudaFree(s->nuu); cudaFree(s->nvv); cudaFree(s->nww); cudaFree(s->macro_count); cudaFree(s->cell_start);
     cudaFree(s->ctr); if (s->ctr_host) cudaFreeHost(s->ctr_host);
+    if (s->w && s->w->live_species && --s->w->live_species == 0) s->w->n_species = 0;
     delete s;
     return PICG_OK;
 }
