@@ -34,8 +34,8 @@ using namespace picg;
 #define CG_WARPS (CG_THREADS / 32)
 #ifndef CG_CAP
 #define CG_CAP 208                                  // particles per stage and array: the largest that lets two blocks share an SM (2 x 111 KB).  A pass longer than a
-                                                    // stage is split and the lane groups whose cells ended in the first part idle through the second: 176 / 192 / 208 -> 10.2 / 10.0 / 9.7 ms
-                                                    // per step for the three deposits of the bench; 128 -> 14.2 (profiles/r2_deposit_stage.md)
+                                                    // stage is split and the lane groups whose cells ended in the first part idle through the second: 128 / 176 / 208 -> 14.2 / 10.2 / 9.7 ms
+                                                    // per step for the three deposits of the bench (profiles/r2_deposit_stage.md; the last step 192 -> 208 is worth 2-3 %)
 #endif
 #ifndef CG_BLOCKS
 #define CG_BLOCKS 2                                 // blocks per SM (registers per thread = 65536 / (256 * CG_BLOCKS))
