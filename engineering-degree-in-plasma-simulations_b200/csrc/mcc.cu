@@ -452,11 +452,10 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     u64 n_pairs = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_pairs, m->stats + 11, 8, cudaMemcpyDeviceToHost, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));
-    rc = species_refresh_count(neu); if (rc) return rc;
-    rc = species_refresh_count(ele); if (rc) return rc;
-    rc = species_refresh_count(ion); if (rc) return rc;
-    size_t n_before[3] = {neu->n_host, ele->n_host, ion->n_host};
+    // exact counts of the collision partners are known from the list builds above; the ion store only receives: its upper bound will do
     picg_species_s* sp3[3] = {neu, ele, ion};
+    size_t n_before[3];
+    for (int k = 0; k < 3; k++) n_before[k] = sp3[k]->n_host_valid ? sp3[k]->n_host : sp3[k]->n_upper;
     // a pair makes one split-off neutral, or one ion and one electron (ch4/v2: ions_to_create ions and one electron)
     const size_t per_pair = m->fixed_weight ? (size_t)std::max(P.ions_to_create, 1) + 1 : 2;
     const size_t scap = std::max<size_t>((size_t)n_pairs * per_pair, 64);
@@ -479,17 +478,19 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
                 m->wsv, m->stats, dt, g_seed, rng_stream_id(RNG_MCC, neu->id, g_rank), (uint32_t)m->step);
     CHECK_LAUNCH();
     LAUNCH(K_MCC_APPEND, k_mcc_finish, 1, 1, 0, m->wsv, m->stats, (u64)scap); CHECK_LAUNCH();
-    u64 host_stats[16];
+    u64 host_stats[16]; double host_wmax = 0;
     CUDA_TRY(cudaMemcpyAsync(host_stats, m->stats, 128, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_TRY(cudaMemcpyAsync(&host_wmax, m->wsv, 8, cudaMemcpyDeviceToHost, g_stream));
     CUDA_TRY(cudaStreamSynchronize(g_stream));                  // host_stats is valid from here on
     // the staged products, store by store, in (cell, creation) order behind the store's particles
     bool grown[3] = {false, false, false};
+    size_t kept_all[3] = {0, 0, 0};
     const size_t staged = (size_t)host_stats[8];
     if (staged) {
         StageIndex X;
         size_t kept[3];
         for (int k = 0; k < 3; k++) {                           // made[k][] -> records in the cells below; made[k][nc] = records of store k
-            kept[k] = (size_t)host_stats[12 + k];
+            kept[k] = kept_all[k] = (size_t)host_stats[12 + k];
             X.start[k] = S.made[k]; X.sorted[k] = (unsigned*)(base + sorted_off[k]);
             if (kept[k]) { rc = scan_cell_table(g, S.made[k], (unsigned*)(base + work_off)); if (rc) return rc; }
         }
@@ -498,21 +499,20 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
         for (int k = 0; k < 3; k++) {
             if (!kept[k]) continue;
             picg_species_s* sp = sp3[k];
-            if (sp->cap < sp->n_host + kept[k]) {               // grow by what is needed plus headroom; the arena holds the staged records and is re-sized after the commits
-                rc = species_grow_store(sp, sp->n_host + kept[k] + std::max<size_t>(2 * kept[k], sp->n_host / 100)); if (rc) return rc;
+            if (sp->cap < n_before[k] + kept[k]) {              // grow by what is needed plus headroom; the arena holds the staged records and is re-sized after the commits
+                if (!sp->n_host_valid) { rc = species_refresh_count(sp); if (rc) return rc; n_before[k] = sp->n_host; }      // growing copies n_host particles: it must be exact
+                rc = species_grow_store(sp, n_before[k] + kept[k] + std::max<size_t>(2 * kept[k], n_before[k] / 100)); if (rc) return rc;
                 grown[k] = true;
             }
             const int cgrid = std::max(1, std::min(div_up(kept[k], 256), g_sm_count * 8));
             LAUNCH(K_MCC_APPEND, k_stage_commit, cgrid, 256, 0, store_of(sp), (const double*)S.rec, (const unsigned*)X.sorted[k], (const unsigned*)(S.made[k] + g.nc)); CHECK_LAUNCH();
             LAUNCH(K_MCC_APPEND, k_stage_count, 1, 1, 0, sp->ctr, (const unsigned*)(S.made[k] + g.nc)); CHECK_LAUNCH();
-            sp->n_host_valid = false; sp->n_upper = std::min(sp->cap, sp->n_host + kept[k]);
+            // the store grew by exactly kept[k]: the host-side count follows without a read-back
+            if (sp->n_host_valid) { sp->n_host += kept[k]; sp->n_upper = sp->n_host; } else sp->n_upper = std::min(sp->cap, sp->n_upper + kept[k]);
         }
     }
-    rc = species_refresh_count(neu); if (rc) return rc;
-    rc = species_refresh_count(ele); if (rc) return rc;
-    rc = species_refresh_count(ion); if (rc) return rc;
     for (int k = 0; k < 3; k++) if (grown[k]) { rc = species_scratch_for_store(sp3[k]); if (rc) return rc; }
-    for (int k = 0; k < 3; k++) m->last_appends[k] = sp3[k]->n_host - n_before[k];
+    for (int k = 0; k < 3; k++) m->last_appends[k] = staged ? kept_all[k] : 0;
     if (host_stats[1]) { neu->sorted_valid = false; neu->lists_valid = false; neu->count_valid = false; ele->sorted_valid = false; ele->lists_valid = false; ele->count_valid = false; ion->sorted_valid = false; ion->lists_valid = false; ion->count_valid = false; }   // :751-754
     if (host_stats[5]) {                                        // grow so that the next call has room, and tell the caller
         for (int k = 0; k < 3; k++) { rc = species_ensure_capacity(sp3[k], sp3[k]->n_host + std::max<size_t>(4 * (size_t)host_stats[5], sp3[k]->n_host / 10)); if (rc) return rc; }
@@ -521,8 +521,7 @@ int picg_mcc_apply(picg_mcc_t m, double dt, picg_mcc_stats* out) {
     if (out) {
         out->candidates = host_stats[0]; out->collisions = host_stats[1]; out->ionizations = host_stats[2]; out->dropped = host_stats[5];
         out->extras_capped = host_stats[6]; out->nan_products = host_stats[7];
-        double wmax; CUDA_TRY(cudaMemcpyAsync(&wmax, m->wsv, 8, cudaMemcpyDeviceToHost, g_stream)); CUDA_TRY(cudaStreamSynchronize(g_stream));
-        out->w_sigma_v_max = wmax;
+        out->w_sigma_v_max = host_wmax;
     }
     return PICG_OK;
 }

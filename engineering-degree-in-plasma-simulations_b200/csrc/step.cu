@@ -323,7 +323,7 @@ int launch_step(picg_species_s* s, int mode, double dt, picg_species_s* neutrals
     StepArgs A;
     A.tail_from = nullptr;
     for (int c = 0; c < 7; c++) A.a[c] = s->a[c];
-    A.ctr = s->ctr; A.use_fixed_n = (mode & 2) ? 1 : 0; A.n_fixed = n_snapshot;
+    A.ctr = s->ctr; A.use_fixed_n = 0; A.n_fixed = n_snapshot;                     // (the snapshot is an upper bound only: see species_step)
     A.ef = s->w->ef; A.qm_dt = dt * s->charge / s->mass; A.dt = dt;                 // Species.cpp:372 `dt*charge/mass`
     A.dead_list = (unsigned*)s->w->scratch; A.impact_list = (unsigned*)((char*)s->w->scratch + compact_scratch_bytes(std::max<size_t>(n_snapshot, 1)));
     A.den_fixed = (u64*)s->den_fixed; A.scale = std::ldexp(1.0, s->S); A.macro_count = s->macro_count;
@@ -390,10 +390,14 @@ int species_step(picg_species_s* s, bool push, bool heavy, bool deposit, bool fi
     if (deposit && finalize && !s->S_pinned && !s->S_calibrated) { rc = calibrate_scale(s, false); if (rc < 0) return rc; }
     size_t cap = std::max<size_t>(s->n_upper, 1), n_snapshot = 0;
     if (heavy) {
-        rc = species_refresh_count(s); if (rc) return rc;
-        n_snapshot = s->n_host; cap = std::max<size_t>(n_snapshot, 1);
+        // The reference walks a snapshot of the count (Species.cpp:176) because its loop appends to the store it walks.  Here nothing appends to the
+        // store being pushed while its kernels run (emitted particles join their stores after the kernels, k_emit_finish), so the kernels read the
+        // count on the device and the host only needs an upper bound: no synchronisation.
+        n_snapshot = s->n_upper; cap = std::max<size_t>(n_snapshot, 1);
         if (s->charge != 0) {                          // room for injected neutrals / sputtered material
             for (picg_species_s* t : {neutrals, sputtering ? spherium : neutrals}) {
+                const double per_ion_ub = std::min(64.0, s->mpw0 / t->mpw0 + 1.0);
+                if (t->cap >= t->n_upper + (size_t)(per_ion_ub * (double)n_snapshot / 16.0) + 65536) continue;      // enough room by the upper bounds: no need for the exact count
                 rc = species_refresh_count(t); if (rc) return rc;
                 // every impacting ion emits int(mpw / mpw0_target + rnd()) particles (Species.cpp:225-232); at most a few per cent of a
                 // species reach an electrode in one (possibly sub-cycled) push.  A store that still runs full is safe: the appends beyond
