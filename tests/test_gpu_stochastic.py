@@ -121,7 +121,7 @@ def test_mover_lists_are_exact_and_equivalent_to_resorting(picgpu, orc=None):
         return out
     A = [run(s, 0.10) for s in range(N_SEEDS)]            # patched lists
     B = [run(100 + s, 0.0) for s in range(N_SEEDS)]       # full re-sort, as the reference does every step
-    pg.set_mover_fraction(0.10)
+    pg.set_mover_fraction(0.15)
     assert np.mean([b["coll"] for b in B]) > 100
     for key in ("coll", "ion", "ne", "nn", "ke"):
         _agree([a[key] for a in A], [b[key] for b in B], key)
@@ -160,7 +160,44 @@ def test_mover_lists_from_the_deposit_pass(picgpu):
     f1, s1, r1 = pg.mover_stats()
     # the deposit's list was re-used (MC products pile up beyond the partition, so a periodic full sort may also occur: r1 >= r0)
     assert f1 - f0 >= 3 and r1 >= r0
-    pg.set_mover_fraction(0.10)
+    pg.set_mover_fraction(0.15)
+    for o in (m, sn, si, se, w):
+        o.close()
+
+
+def test_repeated_collision_calls_without_a_push_keep_the_lists_exact(picgpu):
+    """Several MC calls in a row on species that are not pushed in between (the reference's subcycled loop: neutrals are advanced every
+    100th step, the interaction runs every step): every list build starts from the deposit's mover list again and appends only the tail
+    that the previous call created - no slot may be listed twice (sort.cu)."""
+    pg = picgpu
+    ni, nj, nk = 9, 9, 13
+    x0, xm, rects = util.discharge_geometry(ni, nj, nk)
+    E, sg = util.momentum_transfer_table()
+    E_ion = 1313.9 * 1000 / util.NA
+    neu0 = util.random_particles(40000, x0, xm, seed=181, vth=600.0, mpw=(5e11, 5e11), lo_frac=(0, 0, 0.15), hi_frac=(1, 1, 0.85))
+    ele0 = util.random_particles(20000, x0, xm, seed=182, vth=2.5e6, mpw=(100.0, 100.0), lo_frac=(0, 0, 0.15), hi_frac=(1, 1, 0.85))
+    pg.set_mover_fraction(0.4); pg.set_merge_fraction(0.5); pg.seed(6)
+    w = util.build_world(pg.World, ni, nj, nk, x0, xm, rects, dt=1e-10)
+    w.upload(pg.F_EF, util.smooth_ef((ni, nj, nk), x0, xm, seed=3, amp=2e6))
+    sn = pg.Species("O", 16 * util.AMU, 0.0, w, 5e11, E_ion); si = pg.Species("O+", 16 * util.AMU, util.QE, w, 100.0); se = pg.Species("e-", util.ME, -util.QE, w, 100.0)
+    sn.setParticles(neu0); se.setParticles(ele0)
+    sn.sort(); se.sort()
+    m = pg.MC_MEX_Ionization(sn, si, se, w, E, sg)
+    m.setWsvMax(5e11 * 8e-20 * 8e6)
+    m.apply(1e-10)                                        # first use of the lists
+    se.advanceElectrons(2e-12); se.computeNumberDensity()     # the deposit passes list the movers of both partitions
+    sn.advanceNonElectron(sn, sn, 6e-9); sn.computeNumberDensity()
+    n_neu = [sn.getNumParticles()]
+    for it in range(4):                                   # no push, no deposit in between: the tails grow call by call
+        st = m.apply(1e-10)
+        assert st.collisions > 0 and st.dropped == 0
+        n_neu.append(sn.getNumParticles())
+        se.computeMacroParticlesCount(); sn.computeMacroParticlesCount()
+        le, ln = m.listCounts(1, w), m.listCounts(0, w)
+        assert np.array_equal(le, se.macro_part_count) and le.sum() == se.getNumParticles()
+        assert np.array_equal(ln, sn.macro_part_count) and ln.sum() == sn.getNumParticles()
+    assert all(b > a for a, b in zip(n_neu, n_neu[1:]))   # every call split neutrals off
+    pg.set_mover_fraction(0.15); pg.set_merge_fraction(0.12)
     for o in (m, sn, si, se, w):
         o.close()
 
@@ -206,7 +243,7 @@ def test_tail_merge_keeps_particles_lists_and_deposit_exact(picgpu, orc):
         assert np.array_equal(m.listCounts(1, w), se.macro_part_count)
         st = m.apply(1e-10)                               # the collision kernel on the merged partition
         assert st.collisions > 0
-    pg.set_mover_fraction(0.10); pg.set_merge_fraction(0.05)
+    pg.set_mover_fraction(0.15); pg.set_merge_fraction(0.12)
     for o in (m, sn, si, se, w):
         o.close()
 
