@@ -656,16 +656,20 @@ def run_ours(args):
         inj.append(a)
     rho_pin = torch.empty(nv, dtype=torch.float64).pin_memory()
     rho_host = rho_pin.numpy()
-    # One GPU: the same steps as the device-resident leg, on the same plasma - the run is re-created (runs are reproducible, so this is the
-    # first plasma over again), warmed up like the first, and the K steps are then taken through the host-buffer path.  Several GPUs: the
-    # end-to-end steps follow the timed ones (five of them), as in round 1.
-    if world == 1:
+    # The same steps as the device-resident leg, on the same plasma: the run is re-created (runs are reproducible, so this is the first
+    # plasma over again), warmed up like the first (the multi-GPU self-check took one step on every rank), and the K steps are then taken
+    # through the host-buffer path.  PICG_E2E_AFTER=1: the round-1 behaviour (five steps following the timed ones).
+    did_self_check = world > 1 and not os.environ.get("PICG_SKIP_SELF_CHECK")          # the same on every rank (mg_parity is only set on rank 0)
+    if not os.environ.get("PICG_E2E_AFTER"):
         e2e_steps = args.steps
+        barrier()
         destroy_plasma()
+        barrier()
         w.upload(pg.F_PHI, phi_initial); sol.computeEF()
+        barrier()                                              # no rank starts a slab sweep (peer stores into the neighbours' phi) before every rank holds the initial potential
         create_plasma()
         ts = 1
-        for _ in range(args.warmup):
+        for _ in range(args.warmup + (1 if did_self_check else 0)):
             step(ts); ts += 1
     else:
         e2e_steps = max(2, min(args.steps, 5))
@@ -686,8 +690,8 @@ def run_ours(args):
            "d2h_bytes_per_step": int((nv * 8 + 3 * 5 * 8 + 3 * 64) * world), "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
            "kernel_ms_per_step": kt_e2e, "device_reallocs": int(pg.realloc_count() - reallocs1),
            "what": "C-ABI step with host buffers: H2D of injected electrons (pinned), D2H of per-species counters + diagnostics and of rho every step; "
-                   + ("the plasma of the device-resident leg re-created (same seed: the same particles) and taken through the SAME step numbers" if world == 1 else
-                      "the steps that follow the device-resident leg"), "same_start_as_value": (bool(e2e_first_step_population == n_start) if world == 1 else None)}
+                   + ("the plasma of the device-resident leg re-created (same seed: the same particles) and taken through the SAME step numbers" if not os.environ.get("PICG_E2E_AFTER") else
+                      "the steps that follow the device-resident leg"), "same_start_as_value": (bool(e2e_first_step_population == n_start) if not os.environ.get("PICG_E2E_AFTER") else None)}
 
     # ---- Poisson to the reference's tolerance.  The step above runs the solve warm-started with a cap of --s_max_it iterations (both arms);
     # here the SAME solve is run once with the reference's own budget (main.cpp:82 --s_max_it 8000, tolerance main.cpp:83) from the
